@@ -1,0 +1,180 @@
+/* stmqr_b200.h -- C ABI of the B200-native numeric multifrontal-QR engine.
+ *
+ * This is the drop-in boundary for the reference's numeric phase
+ *     qr_numeric *qr_factorize (sparse_csc **Ahandle, Long freeA, double tol,
+ *                               Long ntol, qr_symbolic *QRsym, sparse_common *cc)
+ * (reference: STMMQR/include/SparseQR.h:127-135, definition
+ *  STMMQR/src/qr/SparseQR_factorize.c:222-749).  A host-side qr_factorize
+ * written against the reference's own headers (stmqr_b200/host/qr_factorize_b200.c)
+ * fills the plain views below from qr_symbolic / sparse_csc and calls these
+ * entry points; no reference header and no torch type crosses this boundary.
+ *
+ * Everything here is extern "C", plain pointers and sizes.  All index arrays
+ * are 64-bit signed (the reference's `Long` = Sparse_long), all values IEEE
+ * double.  Every function returns STMQR_OK (0) or a negative status that the
+ * host side maps onto the reference's cc->status codes
+ * (STMMQR/include/SparseCore.h:48-54).
+ *
+ * There is NO CPU fallback: if no sm_100 device is present the calls fail
+ * with STMQR_ERR_NO_DEVICE.
+ */
+#ifndef STMQR_B200_H
+#define STMQR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STMQR_OK                 0
+#define STMQR_ERR_NO_DEVICE    (-1)
+#define STMQR_ERR_OUT_OF_MEMORY (-2)   /* -> SPARSE_OUT_OF_MEMORY (SparseCore.h:50) */
+#define STMQR_ERR_TOO_LARGE    (-3)    /* -> SPARSE_TOO_LARGE     (SparseCore.h:51) */
+#define STMQR_ERR_INVALID      (-4)    /* -> SPARSE_INVALID       (SparseCore.h:52) */
+#define STMQR_ERR_CUDA         (-5)    /* any other CUDA runtime error -> SPARSE_INVALID */
+
+typedef struct stmqr_handle_s *stmqr_handle ;
+
+/* Read-only view of the reference's qr_symbolic (STMMQR/include/SparseQR_struct.h:26-137).
+ * Field names are the reference's.  Only the fields the numeric phase reads are here
+ * (the task-tree fields TaskChild/TaskFront/TaskStack/On_stack/Stack_maxstack belong to
+ * the CPU scheduler, SparseQR_multithreads.c, which this engine replaces). */
+typedef struct
+{
+    int64_t m, n, anz ;              /* S = A(P,Q) is m-by-n with anz entries              */
+    int64_t nf ;                     /* number of fronts                                   */
+    int64_t maxfn ;                  /* max # columns of any front                         */
+    int64_t rjsize ;                 /* size of Rj, HStair, HTau                           */
+    int64_t hisize ;                 /* size of Hii (= Hip[nf])                            */
+    int64_t do_rank_detection ;      /* 0: Fm/Cm are exact, 1: they are upper bounds       */
+    int64_t keepH ;                  /* always 1 in the reference (SparseQR_analyze.c:205) */
+    const int64_t *Sp ;              /* [m+1]  row pointers of S                           */
+    const int64_t *Sj ;              /* [anz]  column indices of S, ascending in each row  */
+    const int64_t *Qfill ;           /* [n] or NULL: column k of S is column Qfill[k] of A */
+    const int64_t *PLinv ;           /* [m]    row i of A is row PLinv[i] of S             */
+    const int64_t *Sleft ;           /* [n+2]  rows Sleft[j]..Sleft[j+1]-1 have leftmost col j */
+    const int64_t *Parent ;          /* [nf+1]                                             */
+    const int64_t *Child ;           /* [nf+1]                                             */
+    const int64_t *Childp ;          /* [nf+2]                                             */
+    const int64_t *Super ;           /* [nf+1] pivot columns of front f: Super[f]..Super[f+1]-1 */
+    const int64_t *Rp ;              /* [nf+1]                                             */
+    const int64_t *Rj ;              /* [rjsize] columns of front f: Rj[Rp[f]..Rp[f+1]-1]  */
+    const int64_t *Post ;            /* [nf+1] postordering of the fronts                  */
+    const int64_t *Hip ;             /* [nf+1] Hii of front f starts at Hip[f]             */
+    const int64_t *Fm ;              /* [nf+1] (bound on) # rows of each front             */
+    const int64_t *Cm ;              /* [nf+1] (bound on) # rows of each contribution block*/
+} stmqr_symbolic_view ;
+
+/* The input matrix: the reference's sparse_csc, packed, Long indices, real double
+ * (STMMQR/include/SparseCore.h:514).  Rows need not be sorted. */
+typedef struct
+{
+    int64_t nrow, ncol, nzmax ;
+    const int64_t *p ;               /* [ncol+1] */
+    const int64_t *i ;               /* [p[ncol]] */
+    const double  *x ;               /* [p[ncol]] */
+} stmqr_csc_view ;
+
+/* Scalars produced by the numeric phase (members of qr_numeric, SparseQR_struct.h:145-209). */
+typedef struct
+{
+    int64_t rank ;                   /* # live pivot columns                         */
+    int64_t rank1 ;                  /* # live pivot columns among the first ntol    */
+    int64_t maxfrank ;               /* max # rows of any R block (>= 1)             */
+    int64_t maxfm ;                  /* max (Hm [0..nf-1])                           */
+    int64_t rh_size ;                /* total # doubles of all packed R+H blocks     */
+    double  flops ;                  /* reference flop count, SparseQR_factorize.c:1571 */
+} stmqr_numeric_info ;
+
+/* Destination of the numeric factorization on the host.  All arrays are allocated by the
+ * caller (the host side uses SparseCore_malloc so that qr_freenum, SparseQR.c:1245-1270,
+ * can free them).  Layouts are the reference's qr_numeric. */
+typedef struct
+{
+    double  *stack ;                 /* [rh_size] all packed R+H blocks, one stack (ns = 1)  */
+    int64_t *Roff ;                  /* [nf] Rblock[f] = stack + Roff[f]                     */
+    char    *Rdead ;                 /* [n]                                                  */
+    int64_t *HStair ;                /* [rjsize]                                             */
+    double  *HTau ;                  /* [rjsize]                                             */
+    int64_t *Hii ;                   /* [hisize] (already permuted as qr_hpinv leaves it)    */
+    int64_t *Hm ;                    /* [nf]                                                 */
+    int64_t *Hr ;                    /* [nf]                                                 */
+    int64_t *HPinv ;                 /* [m]                                                  */
+} stmqr_numeric_view ;
+
+/* Timing / traffic counters of the last factorization (device times from CUDA events on the
+ * engine's stream, milliseconds). */
+typedef struct
+{
+    double ms_plan ;                 /* stmqr_b200_analyze: level sets, maps, arenas (host+device) */
+    double ms_h2d ;                  /* upload of A                                              */
+    double ms_numeric ;              /* all numeric kernels (build S .. hpinv), device time      */
+    double ms_d2h ;                  /* download of the qr_numeric arrays                        */
+    double ms_assemble ;             /* device time in setup+assemble+pack kernels (if profiled) */
+    double ms_front ;                /* device time in front-QR kernels (if profiled)            */
+    double bytes_assemble ;          /* algorithmic bytes of assembly+pack, SURVEY.md 8(d)       */
+    double flops ;                   /* same as stmqr_numeric_info.flops                         */
+    int64_t launches ;               /* kernels launched by the last factorization               */
+    int64_t nlevels ;
+    int64_t nf_small, nf_big ;       /* fronts that took the fused shared-memory / tiled path    */
+    int64_t device_bytes ;           /* device memory held by the handle                         */
+} stmqr_stats ;
+
+/* Blocking parameters: the reference keeps them in mutable globals set by
+ * chunk_getSettings (SparseQR_factorize.c:44-96, SparseQR.h:16-19).  They only affect
+ * performance, never the result's structure. */
+typedef struct
+{
+    int32_t panel ;                  /* Householder panel width of the tiled path (default 32) */
+    int32_t small_elems ;            /* fronts with at most this many doubles take the fused
+                                        shared-memory path (0 = engine default)               */
+    int32_t profile_phases ;         /* 1: time assemble/front phases separately (adds syncs)  */
+    int32_t reserved ;
+} stmqr_options ;
+
+int  stmqr_b200_device_count (void) ;
+int  stmqr_b200_create  (int device, stmqr_handle *out) ;
+void stmqr_b200_destroy (stmqr_handle h) ;
+int  stmqr_b200_set_options (stmqr_handle h, const stmqr_options *opt) ;
+
+/* Build the device-side plan for a symbolic analysis: etree level sets, per-front static
+ * bounds, child->parent column maps, S entry -> front column maps, memory arenas.
+ * Replaces the per-stack workspace set-up of qr_factorize (SparseQR_factorize.c:295-468). */
+int  stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym) ;
+
+/* Upload A (pattern + values) and build S = A(P,Q) values on the device
+ * (replaces qr_stranspose2, SparseQR_factorize.c:755-785). */
+int  stmqr_b200_upload_matrix (stmqr_handle h, const stmqr_csc_view *A) ;
+
+/* Numeric factorization of the resident matrix: per etree level, front set-up (qr_fsize
+ * :1066), assembly (qr_assemble :1151), front QR (qr_front :1383, qr_larftb :1851) and
+ * packing (qr_cpack :1639, qr_rhpack :1691), then the row permutation (qr_hpinv :991).
+ * tol < 0 or !do_rank_detection disables rank detection (:285-289).  Results stay on the
+ * device until stmqr_b200_download. */
+int  stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol,
+                                    stmqr_numeric_info *info) ;
+
+/* Copy the factorization into caller-allocated host arrays (layout of qr_numeric). */
+int  stmqr_b200_download (stmqr_handle h, const stmqr_numeric_view *out) ;
+
+/* Convenience: upload_matrix + factorize_resident (the whole of qr_factorize's device work
+ * with host buffers on both sides; download is separate because the caller must size
+ * `stack` from info->rh_size first). */
+int  stmqr_b200_factorize (stmqr_handle h, const stmqr_csc_view *A, double tol, int64_t ntol,
+                           stmqr_numeric_info *info) ;
+
+int  stmqr_b200_get_stats (stmqr_handle h, stmqr_stats *out) ;
+const char *stmqr_b200_last_error (stmqr_handle h) ;
+
+/* Debug / parity taps used by the tests: copy one front's assembled F (before the QR) or
+ * its factorized F to the host.  Only valid when the handle was created with
+ * stmqr_b200_set_debug_capture (h, 1) before factorize. */
+int  stmqr_b200_set_debug_capture (stmqr_handle h, int on) ;
+int  stmqr_b200_get_front (stmqr_handle h, int64_t f, int which /*0 assembled, 1 factorized*/,
+                           double *F, int64_t capacity, int64_t *fm, int64_t *fn) ;
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STMQR_B200_H */

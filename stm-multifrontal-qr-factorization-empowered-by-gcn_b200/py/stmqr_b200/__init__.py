@@ -1,0 +1,301 @@
+"""stmqr_b200 -- thin ctypes binding of the C ABI in include/stmqr_b200.h.
+
+The product is the CUDA library ``lib/libstmqr_b200.so`` (hand-written sm_100a kernels behind
+an ``extern "C"`` boundary) plus the C drop-in ``lib/libstmqr_dropin.so`` that replaces the
+reference's ``qr_factorize`` (STMMQR/src/qr/SparseQR_factorize.c:222).  This module only
+marshals numpy arrays into the plain views of the header; it is used by ``bench.py``, by the
+tests and by ``__graft_entry__.smoke()``.  There is no CPU fallback: importing works without a
+GPU (so that symbol/ABI checks can run), every compute call raises if the library or an
+sm_100 device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_PKG_ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
+LIB_DIR = os.path.join(_PKG_ROOT, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libstmqr_b200.so")
+DROPIN_PATH = os.path.join(LIB_DIR, "libstmqr_dropin.so")
+
+_i64p = C.POINTER(C.c_int64)
+_f64p = C.POINTER(C.c_double)
+
+STMQR_OK = 0
+ERRORS = {-1: "NO_DEVICE", -2: "OUT_OF_MEMORY", -3: "TOO_LARGE", -4: "INVALID", -5: "CUDA"}
+
+
+class SymbolicView(C.Structure):
+    """stmqr_symbolic_view (mirrors qr_symbolic, STMMQR/include/SparseQR_struct.h:26-137)."""
+    _fields_ = [(k, C.c_int64) for k in
+                ("m", "n", "anz", "nf", "maxfn", "rjsize", "hisize", "do_rank_detection", "keepH")] + \
+               [(k, _i64p) for k in
+                ("Sp", "Sj", "Qfill", "PLinv", "Sleft", "Parent", "Child", "Childp", "Super",
+                 "Rp", "Rj", "Post", "Hip", "Fm", "Cm")]
+
+
+SYM_ARRAYS = {  # name -> length as a function of the scalars
+    "Sp": lambda s: s["m"] + 1, "Sj": lambda s: s["anz"], "Qfill": lambda s: s["n"],
+    "PLinv": lambda s: s["m"], "Sleft": lambda s: s["n"] + 2, "Parent": lambda s: s["nf"] + 1,
+    "Child": lambda s: s["nf"] + 1, "Childp": lambda s: s["nf"] + 2, "Super": lambda s: s["nf"] + 1,
+    "Rp": lambda s: s["nf"] + 1, "Rj": lambda s: s["rjsize"], "Post": lambda s: s["nf"] + 1,
+    "Hip": lambda s: s["nf"] + 1, "Fm": lambda s: s["nf"] + 1, "Cm": lambda s: s["nf"] + 1,
+}
+SYM_SCALARS = ("m", "n", "anz", "nf", "maxfn", "rjsize", "hisize", "do_rank_detection", "keepH")
+
+
+class CscView(C.Structure):
+    _fields_ = [("nrow", C.c_int64), ("ncol", C.c_int64), ("nzmax", C.c_int64),
+                ("p", _i64p), ("i", _i64p), ("x", _f64p)]
+
+
+class NumericInfo(C.Structure):
+    _fields_ = [("rank", C.c_int64), ("rank1", C.c_int64), ("maxfrank", C.c_int64),
+                ("maxfm", C.c_int64), ("rh_size", C.c_int64), ("flops", C.c_double)]
+
+
+class NumericView(C.Structure):
+    _fields_ = [("stack", _f64p), ("Roff", _i64p), ("Rdead", C.c_void_p), ("HStair", _i64p),
+                ("HTau", _f64p), ("Hii", _i64p), ("Hm", _i64p), ("Hr", _i64p), ("HPinv", _i64p)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("ms_plan", C.c_double), ("ms_h2d", C.c_double), ("ms_numeric", C.c_double),
+                ("ms_d2h", C.c_double), ("ms_assemble", C.c_double), ("ms_front", C.c_double),
+                ("bytes_assemble", C.c_double), ("flops", C.c_double),
+                ("launches", C.c_int64), ("nlevels", C.c_int64), ("nf_small", C.c_int64),
+                ("nf_big", C.c_int64), ("device_bytes", C.c_int64)]
+
+
+class Options(C.Structure):
+    _fields_ = [("panel", C.c_int32), ("small_elems", C.c_int32), ("profile_phases", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+EXPORTS = (
+    "stmqr_b200_device_count", "stmqr_b200_create", "stmqr_b200_destroy", "stmqr_b200_set_options",
+    "stmqr_b200_analyze", "stmqr_b200_upload_matrix", "stmqr_b200_factorize_resident",
+    "stmqr_b200_download", "stmqr_b200_factorize", "stmqr_b200_get_stats", "stmqr_b200_last_error",
+    "stmqr_b200_set_debug_capture", "stmqr_b200_get_front",
+)
+
+_lib = None
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    """dlopen the CUDA library; raises (no fallback) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the B200 engine has no CPU fallback)")
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    lib.stmqr_b200_device_count.restype = C.c_int
+    lib.stmqr_b200_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.stmqr_b200_destroy.argtypes = [C.c_void_p]
+    lib.stmqr_b200_destroy.restype = None
+    lib.stmqr_b200_set_options.argtypes = [C.c_void_p, C.POINTER(Options)]
+    lib.stmqr_b200_analyze.argtypes = [C.c_void_p, C.POINTER(SymbolicView)]
+    lib.stmqr_b200_upload_matrix.argtypes = [C.c_void_p, C.POINTER(CscView)]
+    lib.stmqr_b200_factorize_resident.argtypes = [C.c_void_p, C.c_double, C.c_int64, C.POINTER(NumericInfo)]
+    lib.stmqr_b200_download.argtypes = [C.c_void_p, C.POINTER(NumericView)]
+    lib.stmqr_b200_factorize.argtypes = [C.c_void_p, C.POINTER(CscView), C.c_double, C.c_int64,
+                                         C.POINTER(NumericInfo)]
+    lib.stmqr_b200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    lib.stmqr_b200_last_error.argtypes = [C.c_void_p]
+    lib.stmqr_b200_last_error.restype = C.c_char_p
+    lib.stmqr_b200_set_debug_capture.argtypes = [C.c_void_p, C.c_int]
+    lib.stmqr_b200_get_front.argtypes = [C.c_void_p, C.c_int64, C.c_int, _f64p, C.c_int64, _i64p, _i64p]
+    _lib = lib
+    return lib
+
+
+def _i64(a):
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    return a, a.ctypes.data_as(_i64p)
+
+
+class Symbolic:
+    """Owns numpy copies of the qr_symbolic arrays and exposes a SymbolicView over them."""
+
+    def __init__(self, scalars: dict, arrays: dict):
+        self.scalars = {k: int(scalars[k]) for k in SYM_SCALARS}
+        self.arrays = {}
+        self.view = SymbolicView()
+        for k in SYM_SCALARS:
+            setattr(self.view, k, self.scalars[k])
+        for k, lenf in SYM_ARRAYS.items():
+            a = arrays.get(k)
+            if a is None:
+                setattr(self.view, k, None)
+                continue
+            a, p = _i64(a)
+            assert a.shape[0] >= lenf(self.scalars), (k, a.shape, lenf(self.scalars))
+            self.arrays[k] = a
+            setattr(self.view, k, p)
+
+    @classmethod
+    def from_view(cls, v: SymbolicView) -> "Symbolic":
+        """Deep-copy a view whose pointers belong to someone else (e.g. the reference's QRsym)."""
+        scal = {k: int(getattr(v, k)) for k in SYM_SCALARS}
+        arrs = {}
+        for k, lenf in SYM_ARRAYS.items():
+            p = getattr(v, k)
+            if not p:
+                arrs[k] = None
+            else:
+                n = lenf(scal)
+                arrs[k] = np.ctypeslib.as_array(p, shape=(max(n, 1),))[:n].copy()
+        return cls(scal, arrs)
+
+    def __getattr__(self, k):
+        if k in ("scalars", "arrays", "view"):
+            raise AttributeError(k)
+        if k in self.scalars:
+            return self.scalars[k]
+        if k in self.arrays:
+            return self.arrays[k]
+        raise AttributeError(k)
+
+    def save(self, path):
+        np.savez_compressed(path, **{("s_" + k): np.int64(v) for k, v in self.scalars.items()},
+                            **{("a_" + k): v for k, v in self.arrays.items()})
+
+    @classmethod
+    def load(cls, path):
+        z = np.load(path)
+        scal = {k[2:]: int(z[k]) for k in z.files if k.startswith("s_")}
+        arrs = {k[2:]: z[k] for k in z.files if k.startswith("a_")}
+        return cls(scal, arrs)
+
+
+class Csc:
+    def __init__(self, nrow, ncol, p, i, x):
+        self.nrow, self.ncol = int(nrow), int(ncol)
+        self.p, pp = _i64(p)
+        self.i, pi = _i64(i)
+        self.x = np.ascontiguousarray(x, dtype=np.float64)
+        self.view = CscView(self.nrow, self.ncol, int(self.p[-1]), pp, pi, self.x.ctypes.data_as(_f64p))
+
+    @property
+    def nnz(self):
+        return int(self.p[-1])
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csc_matrix((self.x, self.i, self.p), shape=(self.nrow, self.ncol))
+
+
+@dataclass
+class Numeric:
+    """Host copy of the qr_numeric members (STMMQR/include/SparseQR_struct.h:145-209)."""
+    rank: int
+    rank1: int
+    maxfrank: int
+    maxfm: int
+    rh_size: int
+    flops: float
+    stack: np.ndarray
+    Roff: np.ndarray
+    Rdead: np.ndarray
+    HStair: np.ndarray
+    HTau: np.ndarray
+    Hii: np.ndarray
+    Hm: np.ndarray
+    Hr: np.ndarray
+    HPinv: np.ndarray
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Engine:
+    """One handle = one GPU + one symbolic plan."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        st = self.lib.stmqr_b200_create(device, C.byref(self.h))
+        if st != STMQR_OK:
+            raise EngineError(f"stmqr_b200_create failed: {ERRORS.get(st, st)} (no CPU fallback)")
+        self.sym = None
+
+    def _check(self, st, what):
+        if st != STMQR_OK:
+            msg = self.lib.stmqr_b200_last_error(self.h)
+            raise EngineError(f"{what}: {ERRORS.get(st, st)}: {msg.decode() if msg else ''}")
+
+    def set_options(self, panel=0, small_elems=0, profile_phases=0):
+        o = Options(panel, small_elems, profile_phases, 0)
+        self._check(self.lib.stmqr_b200_set_options(self.h, C.byref(o)), "set_options")
+
+    def analyze(self, sym: Symbolic):
+        self.sym = sym
+        self._check(self.lib.stmqr_b200_analyze(self.h, C.byref(sym.view)), "analyze")
+
+    def upload_matrix(self, A: Csc):
+        self._check(self.lib.stmqr_b200_upload_matrix(self.h, C.byref(A.view)), "upload_matrix")
+
+    def factorize_resident(self, tol: float, ntol: int) -> NumericInfo:
+        info = NumericInfo()
+        self._check(self.lib.stmqr_b200_factorize_resident(self.h, tol, ntol, C.byref(info)), "factorize_resident")
+        return info
+
+    def factorize(self, A: Csc, tol: float, ntol: int) -> NumericInfo:
+        info = NumericInfo()
+        self._check(self.lib.stmqr_b200_factorize(self.h, C.byref(A.view), tol, ntol, C.byref(info)), "factorize")
+        return info
+
+    def download(self, info: NumericInfo) -> Numeric:
+        s = self.sym
+        out = Numeric(int(info.rank), int(info.rank1), int(info.maxfrank), int(info.maxfm),
+                      int(info.rh_size), float(info.flops),
+                      stack=np.empty(max(int(info.rh_size), 1), np.float64),
+                      Roff=np.empty(max(s.nf, 1), np.int64), Rdead=np.zeros(max(s.n, 1), np.int8),
+                      HStair=np.empty(max(s.rjsize, 1), np.int64), HTau=np.empty(max(s.rjsize, 1), np.float64),
+                      Hii=np.empty(max(s.hisize, 1), np.int64), Hm=np.empty(max(s.nf, 1), np.int64),
+                      Hr=np.empty(max(s.nf, 1), np.int64), HPinv=np.empty(max(s.m, 1), np.int64))
+        v = NumericView()
+        v.stack = out.stack.ctypes.data_as(_f64p)
+        v.Roff = out.Roff.ctypes.data_as(_i64p)
+        v.Rdead = out.Rdead.ctypes.data
+        v.HStair = out.HStair.ctypes.data_as(_i64p)
+        v.HTau = out.HTau.ctypes.data_as(_f64p)
+        v.Hii = out.Hii.ctypes.data_as(_i64p)
+        v.Hm = out.Hm.ctypes.data_as(_i64p)
+        v.Hr = out.Hr.ctypes.data_as(_i64p)
+        v.HPinv = out.HPinv.ctypes.data_as(_i64p)
+        self._check(self.lib.stmqr_b200_download(self.h, C.byref(v)), "download")
+        return out
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self._check(self.lib.stmqr_b200_get_stats(self.h, C.byref(s)), "get_stats")
+        return s
+
+    def set_debug_capture(self, on=True):
+        self._check(self.lib.stmqr_b200_set_debug_capture(self.h, int(on)), "set_debug_capture")
+
+    def get_front(self, f: int, which: int) -> np.ndarray:
+        fm, fn = C.c_int64(), C.c_int64()
+        cap = int(self.sym.Fm[f]) * int(self.sym.Rp[f + 1] - self.sym.Rp[f])
+        buf = np.zeros(max(cap, 1), np.float64)
+        self._check(self.lib.stmqr_b200_get_front(self.h, f, which, buf.ctypes.data_as(_f64p), cap,
+                                                  C.byref(fm), C.byref(fn)), "get_front")
+        return buf[: fm.value * fn.value].reshape((fn.value, fm.value)).T  # column-major -> (fm, fn)
+
+    def close(self):
+        if self.h:
+            self.lib.stmqr_b200_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,390 @@
+"""tests/refapi.py -- ctypes access to the CHECKERS (test infrastructure only):
+
+* ``Oracle``  : oracle/libstmqr_oracle.so, the plain-C restatement (kind "port").
+* ``Reference``: oracle/_ref/libref_harness.so + libstmmqr_ref.so, the UNMODIFIED reference
+  compiled from /root/reference (kind "reference").  Present here and (prebuilt) on the GPU box.
+
+Nothing under stm-multifrontal-qr-factorization-empowered-by-gcn_b200/ imports this file.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+PKG = os.path.join(ROOT, "stm-multifrontal-qr-factorization-empowered-by-gcn_b200")
+sys.path.insert(0, os.path.join(PKG, "py"))
+
+import stmqr_b200 as sq  # noqa: E402
+
+ORACLE_SO = os.path.join(ROOT, "oracle", "libstmqr_oracle.so")
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+HARNESS_SO = os.path.join(REF_DIR, "libref_harness.so")
+DATA_DIR = os.path.join(REF_DIR, "data")
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+_i64p = C.POINTER(C.c_int64)
+_f64p = C.POINTER(C.c_double)
+
+
+def have_reference() -> bool:
+    return os.path.exists(HARNESS_SO)
+
+
+def have_oracle() -> bool:
+    return os.path.exists(ORACLE_SO)
+
+
+# --------------------------------------------------------------------------------------------
+# plain-C oracle
+# --------------------------------------------------------------------------------------------
+class _OracleResult(C.Structure):
+    _fields_ = [("rank", C.c_int64), ("rank1", C.c_int64), ("maxfrank", C.c_int64), ("maxfm", C.c_int64),
+                ("rh_size", C.c_int64), ("flops", C.c_double),
+                ("stack", _f64p), ("Roff", _i64p), ("Rdead", C.POINTER(C.c_int8)), ("HStair", _i64p),
+                ("HTau", _f64p), ("Hii", _i64p), ("Hii_raw", _i64p), ("Hm", _i64p), ("Hr", _i64p),
+                ("HPinv", _i64p), ("Cm", _i64p), ("Sx", _f64p),
+                ("Fasm", C.POINTER(_f64p)), ("Ffac", C.POINTER(_f64p)), ("Cblk", C.POINTER(_f64p)),
+                ("min_tol_margin", C.c_double), ("nf", C.c_int64), ("n", C.c_int64), ("m", C.c_int64)]
+
+
+class OracleNumeric(sq.Numeric):
+    pass
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = C.CDLL(ORACLE_SO)
+        self.lib.stmqr_oracle_factorize.restype = C.POINTER(_OracleResult)
+        self.lib.stmqr_oracle_factorize.argtypes = [C.POINTER(sq.SymbolicView), C.POINTER(sq.CscView),
+                                                    C.c_double, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                                    C.c_int64, C.c_int]
+        self.lib.stmqr_oracle_free.argtypes = [C.POINTER(_OracleResult)]
+        self.lib.stmqr_oracle_free.restype = None
+
+    def factorize(self, sym: sq.Symbolic, A: sq.Csc, tol: float, ntol: int, capture: bool = False,
+                  fchunk=32, small=5000, minchunk=4, minchunk_ratio=4):
+        rp = self.lib.stmqr_oracle_factorize(C.byref(sym.view), C.byref(A.view), tol, ntol,
+                                             fchunk, small, minchunk, minchunk_ratio, int(capture))
+        r = rp.contents
+
+        def arr(p, n, dt=None):
+            n = int(n)
+            if n == 0:
+                return np.zeros(0, dt or np.float64)
+            return np.ctypeslib.as_array(p, shape=(n,)).copy()
+
+        s = sym
+        out = sq.Numeric(int(r.rank), int(r.rank1), int(r.maxfrank), int(r.maxfm), int(r.rh_size),
+                         float(r.flops), stack=arr(r.stack, r.rh_size), Roff=arr(r.Roff, s.nf),
+                         Rdead=arr(r.Rdead, s.n), HStair=arr(r.HStair, s.rjsize), HTau=arr(r.HTau, s.rjsize),
+                         Hii=arr(r.Hii, s.hisize), Hm=arr(r.Hm, s.nf), Hr=arr(r.Hr, s.nf),
+                         HPinv=arr(r.HPinv, s.m))
+        out.Hii_raw = arr(r.Hii_raw, s.hisize)
+        out.Cm = arr(r.Cm, s.nf)
+        out.Sx = arr(r.Sx, s.anz)
+        out.min_tol_margin = float(r.min_tol_margin)
+        if capture:
+            fn = (s.Rp[1:s.nf + 1] - s.Rp[:s.nf])
+            fp = (s.Super[1:s.nf + 1] - s.Super[:s.nf])
+            out.Fasm, out.Ffac, out.Cblk = [], [], []
+            for f in range(s.nf):
+                fm = int(out.Hm[f])
+                n = fm * int(fn[f])
+                out.Fasm.append(arr(r.Fasm[f], n).reshape((int(fn[f]), fm)).T if n else np.zeros((fm, int(fn[f]))))
+                out.Ffac.append(arr(r.Ffac[f], n).reshape((int(fn[f]), fm)).T if n else np.zeros((fm, int(fn[f]))))
+                cm = int(out.Cm[f]); cn = int(fn[f] - fp[f])
+                out.Cblk.append(arr(r.Cblk[f], cm * (cm + 1) // 2 + cm * (cn - cm)))
+        self.lib.stmqr_oracle_free(rp)
+        return out
+
+
+# --------------------------------------------------------------------------------------------
+# the real reference through the harness
+# --------------------------------------------------------------------------------------------
+class Reference:
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = C.CDLL(HARNESS_SO, mode=C.RTLD_GLOBAL)
+            L.rh_start.restype = C.c_void_p
+            L.rh_finish.argtypes = [C.c_void_p]
+            L.rh_status.argtypes = [C.c_void_p]
+            L.rh_clear_status.argtypes = [C.c_void_p]
+            L.rh_memory_inuse.argtypes = [C.c_void_p]; L.rh_memory_inuse.restype = C.c_long
+            L.rh_malloc_count.argtypes = [C.c_void_p]; L.rh_malloc_count.restype = C.c_long
+            L.rh_flopcount.argtypes = [C.c_void_p]; L.rh_flopcount.restype = C.c_double
+            L.rh_flopcount_bound.argtypes = [C.c_void_p]; L.rh_flopcount_bound.restype = C.c_double
+            L.rh_read_mtx.argtypes = [C.c_void_p, C.c_char_p]; L.rh_read_mtx.restype = C.c_void_p
+            L.rh_csc_from_arrays.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_long, _i64p, _i64p, _f64p]
+            L.rh_csc_from_arrays.restype = C.c_void_p
+            L.rh_csc_view.argtypes = [C.c_void_p, C.POINTER(sq.CscView)]
+            L.rh_tap_matrix.restype = C.c_void_p
+            L.rh_tap_tol.restype = C.c_double
+            L.rh_tap_ntol.restype = C.c_long
+            L.rh_free_sparse.argtypes = [C.c_void_p, C.c_void_p]
+            L.rh_default_tol.argtypes = [C.c_void_p, C.c_void_p]; L.rh_default_tol.restype = C.c_double
+            L.rh_sparseqr.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int]
+            L.rh_sparseqr.restype = C.c_void_p
+            L.rh_free_qr.argtypes = [C.c_void_p, C.c_void_p]
+            L.rh_qr_info.argtypes = [C.c_void_p, _f64p]
+            L.rh_sym_view.argtypes = [C.c_void_p, C.POINTER(sq.SymbolicView)]
+            L.rh_num_view.argtypes = [C.c_void_p, C.POINTER(sq.NumericView), _i64p, _i64p]
+            L.rh_num_copy_stacks.argtypes = [C.c_void_p, _f64p]
+            L.rh_qmult.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_long, C.c_long, _f64p, _f64p]
+            L.rh_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_long, C.c_long, _f64p, C.c_long, _f64p]
+            L.rh_sdmult.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_long, C.c_long, _f64p, C.c_long, _f64p]
+            L.rh_check_error.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]; L.rh_check_error.restype = C.c_double
+            L.rh_set_backend.argtypes = [C.c_int, C.c_char_p]
+            L.rh_set_tap.argtypes = [C.c_int]
+            L.rh_last_fac_seconds.restype = C.c_double
+            L.rh_set_blas_threads.argtypes = [C.c_int]
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self):
+        self.L = self.lib()
+        self.cc = C.c_void_p(self.L.rh_start())
+        self.L.rh_set_blas_threads(1)
+
+    def close(self):
+        if self.cc:
+            self.L.rh_finish(self.cc)
+            self.cc = None
+
+    # ---- matrices
+    def read_mtx(self, path):
+        A = self.L.rh_read_mtx(self.cc, path.encode())
+        if not A:
+            raise FileNotFoundError(path)
+        return C.c_void_p(A)
+
+    def csc_from_arrays(self, m, n, Ap, Ai, Ax):
+        Ap = np.ascontiguousarray(Ap, np.int64); Ai = np.ascontiguousarray(Ai, np.int64)
+        Ax = np.ascontiguousarray(Ax, np.float64)
+        A = self.L.rh_csc_from_arrays(self.cc, m, n, int(Ap[-1]), Ap.ctypes.data_as(_i64p),
+                                      Ai.ctypes.data_as(_i64p), Ax.ctypes.data_as(_f64p))
+        return C.c_void_p(A)
+
+    def csc_to_numpy(self, A) -> sq.Csc:
+        v = sq.CscView()
+        self.L.rh_csc_view(A, C.byref(v))
+        n = int(v.ncol)
+        p = np.ctypeslib.as_array(v.p, shape=(n + 1,)).copy()
+        nz = int(p[-1])
+        i = np.ctypeslib.as_array(v.i, shape=(max(nz, 1),))[:nz].copy()
+        x = np.ctypeslib.as_array(v.x, shape=(max(nz, 1),))[:nz].copy()
+        return sq.Csc(int(v.nrow), n, p, i, x)
+
+    def free_sparse(self, A):
+        self.L.rh_free_sparse(self.cc, A)
+
+    def default_tol(self, A):
+        return float(self.L.rh_default_tol(self.cc, A))
+
+    # ---- factorization through the reference's SparseQR()
+    def set_backend(self, backend: str):
+        if backend == "reference":
+            assert self.L.rh_set_backend(0, None) == 0
+        elif backend == "b200":
+            sq.load_library()
+            assert self.L.rh_set_backend(1, sq.DROPIN_PATH.encode()) == 0
+        else:
+            raise ValueError(backend)
+
+    def sparseqr(self, A, ordering_arg: int, tol: float, grain: float = 1.0, pool: int = 0,
+                 blas_threads: int = 1, tap: bool = False):
+        self.L.rh_set_blas_threads(blas_threads)
+        self.L.rh_set_tap(int(tap))
+        self.L.rh_clear_status(self.cc)
+        QR = self.L.rh_sparseqr(self.cc, A, ordering_arg, tol, grain, pool)
+        self.L.rh_set_tap(0)
+        if not QR:
+            raise RuntimeError(f"SparseQR failed, cc->status = {self.L.rh_status(self.cc)}")
+        return C.c_void_p(QR)
+
+    def free_qr(self, QR):
+        self.L.rh_free_qr(self.cc, QR)
+
+    def qr_info(self, QR) -> dict:
+        out = np.zeros(12)
+        self.L.rh_qr_info(QR, out.ctypes.data_as(_f64p))
+        keys = ("Ana_time", "Fac_time", "tol", "n1rows", "n1cols", "rank", "num_rank", "rank1", "maxfrank",
+                "maxfm", "ns", "ntasks")
+        d = dict(zip(keys, out.tolist()))
+        d["fac_seconds"] = float(self.L.rh_last_fac_seconds())
+        d["flopcount"] = float(self.L.rh_flopcount(self.cc))
+        return d
+
+    def tapped(self):
+        """(Csc copy of the matrix handed to qr_factorize, tol, ntol) of the last tapped run."""
+        A = self.L.rh_tap_matrix()
+        return self.csc_to_numpy(C.c_void_p(A)), float(self.L.rh_tap_tol()), int(self.L.rh_tap_ntol())
+
+    def symbolic(self, QR) -> sq.Symbolic:
+        v = sq.SymbolicView()
+        self.L.rh_sym_view(QR, C.byref(v))
+        return sq.Symbolic.from_view(v)
+
+    def numeric(self, QR, sym: sq.Symbolic) -> sq.Numeric:
+        v = sq.NumericView()
+        roff = np.zeros(max(sym.nf, 1), np.int64)
+        tot = C.c_int64()
+        self.L.rh_num_view(QR, C.byref(v), roff.ctypes.data_as(_i64p), C.byref(tot))
+        stack = np.zeros(max(tot.value, 1))
+        self.L.rh_num_copy_stacks(QR, stack.ctypes.data_as(_f64p))
+        info = self.qr_info(QR)
+
+        def arr(p, n):
+            n = int(n)
+            return np.ctypeslib.as_array(p, shape=(max(n, 1),))[:n].copy()
+
+        rdead = np.ctypeslib.as_array(C.cast(v.Rdead, C.POINTER(C.c_int8)), shape=(max(sym.n, 1),))[:sym.n].copy()
+        return sq.Numeric(int(info["num_rank"]), int(info["rank1"]), int(info["maxfrank"]), int(info["maxfm"]),
+                          int(tot.value), info["flopcount"], stack=stack, Roff=roff, Rdead=rdead,
+                          HStair=arr(v.HStair, sym.rjsize), HTau=arr(v.HTau, sym.rjsize),
+                          Hii=arr(v.Hii, sym.hisize), Hm=arr(v.Hm, sym.nf), Hr=arr(v.Hr, sym.nf),
+                          HPinv=arr(v.HPinv, sym.m))
+
+    # ---- consumers
+    def qmult(self, QR, method: int, X: np.ndarray) -> np.ndarray:
+        X = np.asfortranarray(X, dtype=np.float64)
+        if X.ndim == 1:
+            X = X.reshape(-1, 1, order="F")
+        Y = np.zeros_like(X, order="F")
+        st = self.L.rh_qmult(self.cc, QR, method, X.shape[0], X.shape[1], X.ctypes.data_as(_f64p),
+                             Y.ctypes.data_as(_f64p))
+        assert st == 0, st
+        return Y
+
+    def solve(self, QR, system: int, B: np.ndarray, xrow: int) -> np.ndarray:
+        B = np.asfortranarray(B, dtype=np.float64)
+        if B.ndim == 1:
+            B = B.reshape(-1, 1, order="F")
+        X = np.zeros((xrow, B.shape[1]), order="F")
+        st = self.L.rh_solve(self.cc, QR, system, B.shape[0], B.shape[1], B.ctypes.data_as(_f64p), xrow,
+                             X.ctypes.data_as(_f64p))
+        assert st == 0, st
+        return X
+
+    def check_error(self, A, QR) -> float:
+        return float(self.L.rh_check_error(self.cc, A, QR))
+
+    def memory_inuse(self):
+        return int(self.L.rh_memory_inuse(self.cc))
+
+    def malloc_count(self):
+        return int(self.L.rh_malloc_count(self.cc))
+
+
+QR_QTX, QR_QX = 0, 1
+QR_RX_EQUALS_B, QR_RETX_EQUALS_B = 0, 1
+
+
+# --------------------------------------------------------------------------------------------
+# comparison helpers (the parity contract of SURVEY.md 8(c))
+# --------------------------------------------------------------------------------------------
+def front_shapes(sym: sq.Symbolic):
+    nf = sym.nf
+    fp = (sym.Super[1:nf + 1] - sym.Super[:nf]).astype(np.int64)
+    fn = (sym.Rp[1:nf + 1] - sym.Rp[:nf]).astype(np.int64)
+    return fp, fn
+
+
+def unpack_R_rows(sym: sq.Symbolic, num: sq.Numeric, f: int):
+    """Dense (rm x fn) R block of front f from the packed R+H layout (qr_rhpack,
+    SparseQR_factorize.c:1691-1784): pivot col k holds rows 0..t-1 (t = Stair or rm when dead),
+    non-pivot col holds rows 0..rm-1 then H rows."""
+    fp, fn = front_shapes(sym)
+    fpf, fnf = int(fp[f]), int(fn[f])
+    fm = int(num.Hm[f]); rm_final = int(num.Hr[f])
+    st = num.HStair[int(sym.Rp[f]): int(sym.Rp[f]) + fnf]
+    R = np.zeros((rm_final, fnf))
+    p = int(num.Roff[f])
+    rm = 0
+    size = 0
+    for k in range(fnf):
+        if k < fpf:
+            t = int(st[k])
+            if t == 0:
+                t = rm
+            elif rm < fm:
+                rm += 1
+            col = num.stack[p: p + t]
+            nr = min(rm, t)
+            R[:nr, k] = col[:nr]
+            p += t; size += t
+        else:
+            if k == fpf:
+                h = rm
+            col = num.stack[p: p + rm]
+            R[:rm, k] = col
+            p += rm; size += rm
+            t = int(st[k])
+            h = min(h + 1, fm)
+            extra = max(t - h, 0)
+            p += extra; size += extra
+    return R, size
+
+
+def packed_front_size(sym, num, f):
+    return unpack_R_rows(sym, num, f)[1]
+
+
+def compare_R(sym, a: sq.Numeric, b: sq.Numeric, scale: float):
+    """max |R_a - R_b| over all fronts after one sign per R row, relative to scale."""
+    worst = 0.0
+    for f in range(sym.nf):
+        Ra, sa = unpack_R_rows(sym, a, f)
+        Rb, sb = unpack_R_rows(sym, b, f)
+        assert Ra.shape == Rb.shape and sa == sb, (f, Ra.shape, Rb.shape, sa, sb)
+        if Ra.size == 0:
+            continue
+        # row sign: sign of the diagonal-ish entry (first structurally non-zero of each row)
+        for i in range(Ra.shape[0]):
+            ra, rb = Ra[i], Rb[i]
+            j = int(np.argmax(np.abs(ra) > 0)) if np.any(ra != 0) else 0
+            s = 1.0
+            if ra[j] * rb[j] < 0:
+                s = -1.0
+            worst = max(worst, float(np.max(np.abs(ra - s * rb))))
+    return worst / scale
+
+
+def valid_hii_mask(sym, num):
+    """Hii is allocated by the symbolic bound (Hip); only Hii[Hip[f] .. Hip[f]+Hm[f]) is defined
+    (the reference mallocs it, SparseQR_factorize.c:362, and never touches the slack)."""
+    mask = np.zeros(max(sym.hisize, 1), bool)
+    for f in range(sym.nf):
+        mask[int(sym.Hip[f]): int(sym.Hip[f]) + int(num.Hm[f])] = True
+    return mask[:sym.hisize]
+
+
+def _copy_with(num, **kw):
+    import copy
+    c = copy.copy(num)
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def structural_equal(a: sq.Numeric, b: sq.Numeric, sym=None):
+    """bit-exact integer outputs"""
+    bad = []
+    if sym is not None and np.array_equal(a.Hm, b.Hm):
+        mask = valid_hii_mask(sym, a)
+        a = _copy_with(a, Hii=np.where(mask, a.Hii, -1))
+        b = _copy_with(b, Hii=np.where(mask, b.Hii, -1))
+    for k in ("rank", "rank1", "maxfrank", "maxfm"):
+        if getattr(a, k) != getattr(b, k):
+            bad.append((k, getattr(a, k), getattr(b, k)))
+    for k in ("Rdead", "HStair", "Hii", "Hm", "Hr", "HPinv"):
+        x, y = getattr(a, k), getattr(b, k)
+        if x.shape != y.shape or not np.array_equal(x, y):
+            bad.append((k, int(np.sum(x != y)) if x.shape == y.shape else "shape"))
+    return bad
