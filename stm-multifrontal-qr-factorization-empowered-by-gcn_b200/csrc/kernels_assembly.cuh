@@ -1,0 +1,399 @@
+// kernels_assembly.cuh -- S construction, front set-up (qr_fsize), assembly (qr_assemble),
+// packing (qr_cpack, qr_rhpack) and the row permutation (qr_hpinv).  All HBM-bound
+// integer/copy work: coalesced along front columns (column-major F, ld = fm).
+#pragma once
+#include "engine.cuh"
+
+namespace stmqr {
+
+// ---------------------------------------------------------------------------------------------
+// S = A(P,Q) values in row form.  Reference: qr_stranspose2, SparseQR_factorize.c:755-785, a
+// serial scatter through a running row cursor.  Here one thread per entry of A finds its slot by
+// binary search of the permuted column inside the (ascending) row of S: no atomics, deterministic.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_build_S (I32 n, const I64 *__restrict__ Ap, const I64 *__restrict__ Ai,
+    const double *__restrict__ Ax, DSym S, double *__restrict__ Sx, I32 *err)
+{
+    // one warp per column of A keeps the reads of Ai/Ax coalesced
+    const int lane = threadIdx.x & 31 ;
+    const I64 warp = ((I64) blockIdx.x * blockDim.x + threadIdx.x) >> 5 ;
+    const I64 nwarps = ((I64) gridDim.x * blockDim.x) >> 5 ;
+    for (I64 j = warp ; j < n ; j += nwarps)
+    {
+        const I32 col = S.Qinv [j] ;
+        const I64 p1 = Ap [j], p2 = Ap [j+1] ;
+        for (I64 p = p1 + lane ; p < p2 ; p += 32)
+        {
+            const I32 row = S.PLinv [Ai [p]] ;
+            I32 lo = S.Sp [row], hi = S.Sp [row+1] - 1 ;
+            while (lo < hi)
+            {
+                I32 mid = (lo + hi) >> 1 ;
+                if (S.Sj [mid] < col) lo = mid + 1 ; else hi = mid ;
+            }
+            if (lo < S.Sp [row+1] && S.Sj [lo] == col) Sx [lo] = Ax [p] ;
+            else atomicExch (err, 1) ;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Front set-up for every front of one etree level: qr_fsize (SparseQR_factorize.c:1066-1145)
+// plus the integer half of qr_assemble (:1188-1248): row start of every column (Stair), # rows
+// fm, the row of every original row of S (rowpos), the row of every child C row (Cmap) and the
+// row ids Hii.  One CTA per front.  After the kernel stair[] holds the row END of each column.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_front_setup (const I32 *__restrict__ fronts, DSym S, DNum N)
+{
+    __shared__ I32 sh [34] ;
+    const I32 slot = blockIdx.x ;
+    const I32 f = fronts [slot] ;
+    const I32 col1 = S.Super [f], fp = S.Super [f+1] - col1 ;
+    const I32 p1 = S.Rp [f], fn = S.Rp [f+1] - p1 ;
+    I32 *st = N.stair + p1 ;
+    const int tid = threadIdx.x, nt = blockDim.x ;
+
+    for (I32 j = tid ; j < fn ; j += nt)
+        st [j] = (j < fp) ? (S.Sleft [col1+j+1] - S.Sleft [col1+j]) : 0 ;
+    __syncthreads () ;
+    const I32 c1 = S.Childp [f], c2 = S.Childp [f+1] ;
+    for (I32 q = c1 ; q < c2 ; q++)
+    {
+        const I32 c = S.Child [q] ;
+        const I32 pc = S.Rp [c] + (S.Super [c+1] - S.Super [c]) ;
+        const I32 cm = N.Cm [c] ;
+        // the cm columns of one child are distinct: no atomics needed inside a child
+        for (I32 ci = tid ; ci < cm ; ci += nt) st [S.Cj [pc+ci]] += 1 ;
+        __syncthreads () ;
+    }
+    const I32 fm = block_exclusive_scan<I32> (st, fn, sh) ;
+    __syncthreads () ;
+
+    I32 *Hi = N.Hii + S.Hip [f] ;
+    // original rows of S whose leftmost column is a pivot of this front (:1188-1208)
+    const I32 r1 = S.Sleft [col1], r2 = S.Sleft [col1+fp] ;
+    for (I32 r = r1 + tid ; r < r2 ; r += nt)
+    {
+        const I32 k = S.Sj [S.Sp [r]] - col1 ;          // leftmost column of the row
+        const I32 i = st [k] + (r - S.Sleft [col1+k]) ;
+        N.rowpos [r] = i ;
+        Hi [i] = r ;
+    }
+    __syncthreads () ;
+    for (I32 k = tid ; k < fp ; k += nt) st [k] += S.Sleft [col1+k+1] - S.Sleft [col1+k] ;
+    __syncthreads () ;
+    // child rows, children in order (:1239-1248)
+    for (I32 q = c1 ; q < c2 ; q++)
+    {
+        const I32 c = S.Child [q] ;
+        const I32 pc = S.Rp [c] + (S.Super [c+1] - S.Super [c]) ;
+        const I32 cm = N.Cm [c] ;
+        const I32 *Hichild = N.Hii + S.Hip [c] + N.Hr [c] ;
+        for (I32 ci = tid ; ci < cm ; ci += nt)
+        {
+            const I32 j = S.Cj [pc+ci] ;
+            const I32 i = st [j] ;
+            st [j] = i + 1 ;
+            N.Cmap [pc+ci] = i ;
+            Hi [i] = Hichild [ci] ;
+        }
+        __syncthreads () ;
+    }
+    if (tid == 0)
+    {
+        N.Hm [f] = fm ;
+        N.rank [f] = min (fm, fp) ;
+        N.g [slot] = 0 ;
+        N.done [slot] = 0 ;
+        atomicMax (N.maxfm, fm) ;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Numeric assembly: F <- 0, scatter the rows of S, extend-add the children's packed C blocks
+// (qr_assemble, SparseQR_factorize.c:1176-1281).  grid = (fronts of the level, column slices);
+// each CTA owns a contiguous block of columns of F, so zero-fill and scatter need no inter-CTA
+// ordering and the zero-fill is a fully coalesced stream.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_assemble (const I32 *__restrict__ fronts, DSym S, DNum N)
+{
+    const I32 f = fronts [blockIdx.x] ;
+    const I32 col1 = S.Super [f], fp = S.Super [f+1] - col1 ;
+    const I32 p1 = S.Rp [f], fn = S.Rp [f+1] - p1 ;
+    const I32 fm = N.Hm [f] ;
+    if (fm == 0) return ;
+    const I32 nsl = gridDim.y ;
+    const I32 cb = (fn + nsl - 1) / nsl ;
+    const I32 j1 = blockIdx.y * cb, j2 = min (fn, j1 + cb) ;
+    if (j1 >= j2) return ;
+    double *F = N.F + S.Foff [f] ;
+    const int tid = threadIdx.x, nt = blockDim.x ;
+    const int lane = tid & 31, w = tid >> 5, nw = nt >> 5 ;
+
+    {   // zero my columns (contiguous)
+        double *z = F + (I64) j1 * fm ;
+        const I64 cnt = (I64) (j2 - j1) * fm ;
+        for (I64 i = tid ; i < cnt ; i += nt) z [i] = 0.0 ;
+    }
+    __syncthreads () ;
+
+    // rows of S: one warp per row, lanes over its entries
+    const I32 r1 = S.Sleft [col1], r2 = S.Sleft [col1+fp] ;
+    for (I32 r = r1 + w ; r < r2 ; r += nw)
+    {
+        const I32 i = N.rowpos [r] ;
+        const I32 e2 = S.Sp [r+1] ;
+        for (I32 p = S.Sp [r] + lane ; p < e2 ; p += 32)
+        {
+            const I32 j = S.Sjf [p] ;
+            if (j >= j1 && j < j2) F [i + (I64) j * fm] = N.Sx [p] ;
+        }
+    }
+
+    // children: one warp per column of the child's C block
+    for (I32 q = S.Childp [f] ; q < S.Childp [f+1] ; q++)
+    {
+        const I32 c = S.Child [q] ;
+        const I32 fpc = S.Super [c+1] - S.Super [c] ;
+        const I32 pc = S.Rp [c] + fpc ;
+        const I32 cn = (S.Rp [c+1] - S.Rp [c]) - fpc ;
+        const I32 cm = N.Cm [c] ;
+        if (cm <= 0) continue ;
+        const double *C = N.C + S.Coff [c] ;
+        const I32 *Cmap = N.Cmap + pc ;
+        for (I32 cj = w ; cj < cn ; cj += nw)
+        {
+            const I32 j = S.Cj [pc+cj] ;
+            if (j < j1 || j >= j2) continue ;
+            const I32 len = min (cj+1, cm) ;
+            const double *src = C + cblock_col_offset (cj, cm) ;
+            double *Fj = F + (I64) j * fm ;
+            for (I32 ci = lane ; ci < len ; ci += 32) Fj [Cmap [ci]] = src [ci] ;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// After the front QR: sizes of the packed blocks.  qr_fcsize (:1623), the column lengths of
+// qr_rhpack (:1726-1780) as two block scans, Hr, Cm, HStair.  One CTA per front.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_front_finish (const I32 *__restrict__ fronts, DSym S, DNum N)
+{
+    __shared__ I64 sh64 [34] ;
+    __shared__ I32 sh32 [34] ;
+    const I32 f = fronts [blockIdx.x] ;
+    const I32 fp = S.Super [f+1] - S.Super [f] ;
+    const I32 p1 = S.Rp [f], fn = S.Rp [f+1] - p1 ;
+    const I32 fm = N.Hm [f] ;
+    const I32 *st = N.stair + p1 ;
+    I64 *colp = N.colp + p1 ;
+    const int tid = threadIdx.x, nt = blockDim.x ;
+
+    // rm before/after each pivot column = # live pivots so far (capped at fm)
+    // use colp as int64 scratch for the live flags
+    for (I32 k = tid ; k < fp ; k += nt) colp [k] = (st [k] != 0) ? 1 : 0 ;
+    __syncthreads () ;
+    const I64 nlive = block_exclusive_scan<I64> (colp, fp, sh64) ;
+    __syncthreads () ;
+    const I32 rm = (I32) min ((I64) fm, nlive) ;
+    // column lengths
+    for (I32 k = tid ; k < fn ; k += nt)
+    {
+        I64 len ;
+        if (k < fp)
+        {
+            const I32 t = st [k] ;
+            const I64 before = min ((I64) fm, colp [k]) ;           // rm before this column
+            len = (t == 0) ? before : (I64) t ;
+        }
+        else
+        {
+            const I32 h = min (rm + (k - fp + 1), fm) ;
+            len = (I64) rm + max (0, st [k] - h) ;
+        }
+        colp [k] = len ;
+    }
+    __syncthreads () ;
+    const I64 rsize = (fm > 0) ? block_exclusive_scan<I64> (colp, fn, sh64) : 0 ;
+    (void) sh32 ;
+    if (tid == 0)
+    {
+        const I32 cn = fn - fp ;
+        const I32 rank = N.rank [f] ;
+        I32 cm = min (fm - rank, cn) ;
+        if (cm < 0 || cn <= 0) cm = 0 ;
+        N.Cm [f] = cm ;
+        N.Hr [f] = (fm > 0) ? rm : 0 ;
+        N.rsize [f] = rsize ;
+        atomicAdd (N.sumrank, rank) ;
+        atomicMax (N.maxfrank, rank) ;
+    }
+}
+
+// Deterministic bump allocation of the level's R+H blocks: exclusive scan over the level's
+// fronts (in list order) on one CTA.
+__global__ void k_level_alloc (const I32 *__restrict__ fronts, I32 count, DNum N)
+{
+    __shared__ I64 sh [34] ;
+    __shared__ I64 carry_s ;
+    const int tid = threadIdx.x, nt = blockDim.x ;
+    if (tid == 0) carry_s = (I64) *N.rcursor ;
+    __syncthreads () ;
+    const int lane = tid & 31, w = tid >> 5, nw = nt >> 5 ;
+    for (I32 base = 0 ; base < count ; base += nt)
+    {
+        const I32 i = base + tid ;
+        const I64 v = (i < count) ? N.rsize [fronts [i]] : 0 ;
+        I64 inc = v ;
+        for (int o = 1 ; o < 32 ; o <<= 1)
+        {
+            I64 u = __shfl_up_sync (STMQR_FULL_MASK, inc, o) ;
+            if (lane >= o) inc += u ;
+        }
+        if (lane == 31) sh [w] = inc ;
+        __syncthreads () ;
+        if (w == 0)
+        {
+            I64 t = (lane < nw) ? sh [lane] : 0 ;
+            I64 ti = t ;
+            for (int o = 1 ; o < 32 ; o <<= 1)
+            {
+                I64 u = __shfl_up_sync (STMQR_FULL_MASK, ti, o) ;
+                if (lane >= o) ti += u ;
+            }
+            sh [lane] = ti - t ;
+            if (lane == 31) sh [32] = ti ;
+        }
+        __syncthreads () ;
+        if (i < count) N.Roff [fronts [i]] = carry_s + sh [w] + inc - v ;
+        __syncthreads () ;
+        if (tid == 0) carry_s += sh [32] ;
+        __syncthreads () ;
+    }
+    if (tid == 0) *N.rcursor = (unsigned long long) carry_s ;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pack: copy the upper-trapezoidal C block (qr_cpack :1639-1685) and the R+H staircase
+// (qr_rhpack :1691-1784) out of F.  grid = (fronts, column slices); reads and writes are
+// contiguous per column.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pack (const I32 *__restrict__ fronts, DSym S, DNum N)
+{
+    const I32 f = fronts [blockIdx.x] ;
+    const I32 fp = S.Super [f+1] - S.Super [f] ;
+    const I32 p1 = S.Rp [f], fn = S.Rp [f+1] - p1 ;
+    const I32 fm = N.Hm [f] ;
+    if (fm == 0) return ;
+    const I32 nsl = gridDim.y ;
+    const I32 cb = (fn + nsl - 1) / nsl ;
+    const I32 j1 = blockIdx.y * cb, j2 = min (fn, j1 + cb) ;
+    if (j1 >= j2) return ;
+    const double *F = N.F + S.Foff [f] ;
+    const I32 *st = N.stair + p1 ;
+    const I64 *colp = N.colp + p1 ;
+    double *R = N.R + N.Roff [f] ;
+    double *C = N.C + S.Coff [f] ;
+    const I32 rm = N.Hr [f], cm = N.Cm [f], rank = N.rank [f] ;
+    const I64 rsize = N.rsize [f] ;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5 ;
+
+    for (I32 k = j1 + w ; k < j2 ; k += nw)
+    {
+        const double *Fk = F + (I64) k * fm ;
+        double *Rk = R + colp [k] ;
+        const I64 len = ((k+1 < fn) ? colp [k+1] : rsize) - colp [k] ;
+        if (k < fp)
+        {
+            for (I64 i = lane ; i < len ; i += 32) Rk [i] = Fk [i] ;
+        }
+        else
+        {
+            // rows 0..rm-1, then rows h..t-1 with h = min (rm + (k-fp+1), fm)
+            const I32 h = min (rm + (k - fp + 1), fm) ;
+            for (I64 i = lane ; i < len ; i += 32) Rk [i] = (i < rm) ? Fk [i] : Fk [h + (i - rm)] ;
+            // contribution block column cj = k - fp: rows rank .. rank+min(cj+1,cm)-1
+            const I32 cj = k - fp ;
+            const I32 clen = min (cj+1, cm) ;
+            double *Ck = C + cblock_col_offset (cj, cm) ;
+            for (I32 i = lane ; i < clen ; i += 32) Ck [i] = Fk [rank + i] ;
+        }
+        (void) st ;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// qr_hpinv (SparseQR_factorize.c:991-1060) in parallel: the serial row counters row1/row2
+// become two exclusive scans over the fronts.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_hpinv_counts (DSym S, DNum N)
+{
+    const I32 f = blockIdx.x * blockDim.x + threadIdx.x ;
+    if (f >= S.nf) return ;
+    const I32 fm = N.Hm [f], rm = N.Hr [f] ;
+    const I32 cn = (S.Rp [f+1] - S.Rp [f]) - (S.Super [f+1] - S.Super [f]) ;
+    const I32 cm = min (fm - rm, cn) ;
+    N.base1 [f] = rm ;
+    N.base2 [f] = max (0, fm - rm - cm) ;
+}
+__global__ void k_scan_i64 (I64 *a, I64 *b, I32 n)
+{
+    __shared__ I64 sh [34] ;
+    block_exclusive_scan<I64> (a, n, sh) ;
+    __syncthreads () ;
+    block_exclusive_scan<I64> (b, n, sh) ;
+}
+__global__ void k_hpinv_rows (DSym S, DNum N)
+{
+    // one warp per front
+    const int lane = threadIdx.x & 31 ;
+    const I32 f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5 ;
+    if (f >= S.nf) return ;
+    const I32 fm = N.Hm [f], rm = N.Hr [f] ;
+    const I32 cn = (S.Rp [f+1] - S.Rp [f]) - (S.Super [f+1] - S.Super [f]) ;
+    const I32 cm = min (fm - rm, cn) ;
+    const I32 *Hi = N.Hii + S.Hip [f] ;
+    const I64 b1 = N.base1 [f] ;
+    const I64 nempty = S.m - S.Sleft [S.n] ;
+    const I64 b2 = (I64) S.m - nempty - N.base2 [f] ;    // value of row2 when front f is reached
+    for (I32 i = lane ; i < rm ; i += 32) N.W [Hi [i]] = (I32) (b1 + i) ;
+    for (I32 i = rm + cm + lane ; i < fm ; i += 32) N.W [Hi [i]] = (I32) (b2 - (fm - i)) ;
+}
+__global__ void k_hpinv_empty (DSym S, DNum N)
+{
+    const I32 i = S.Sleft [S.n] + blockIdx.x * blockDim.x + threadIdx.x ;
+    if (i < S.m) N.W [i] = S.m - 1 - (i - S.Sleft [S.n]) ;
+}
+__global__ void k_hpinv_apply (DSym S, DNum N, I64 *HPinv64, I64 *Hii64)
+{
+    const int lane = threadIdx.x & 31 ;
+    const I64 gw = ((I64) blockIdx.x * blockDim.x + threadIdx.x) >> 5 ;
+    const I64 nwarp = ((I64) gridDim.x * blockDim.x) >> 5 ;
+    const I64 gt = (I64) blockIdx.x * blockDim.x + threadIdx.x ;
+    const I64 ntot = (I64) gridDim.x * blockDim.x ;
+    for (I64 i = gt ; i < S.m ; i += ntot) HPinv64 [i] = N.W [S.PLinv [i]] ;
+    for (I64 f = gw ; f < S.nf ; f += nwarp)
+    {
+        const I32 fm = N.Hm [f] ;
+        const I32 *Hi = N.Hii + S.Hip [f] ;
+        I64 *Ho = Hii64 + S.Hip [f] ;
+        for (I32 i = lane ; i < fm ; i += 32) Ho [i] = N.W [Hi [i]] ;
+    }
+}
+
+__global__ void k_rank1 (const char *Rdead, I64 ntol, I32 *rank1)
+{
+    I64 i = (I64) blockIdx.x * blockDim.x + threadIdx.x ;
+    int live = (i < ntol) ? (Rdead [i] == 0) : 0 ;
+    live = warp_sum_i (live) ;
+    if ((threadIdx.x & 31) == 0 && live) atomicAdd (rank1, live) ;
+}
+
+__global__ void k_widen (const I32 *__restrict__ a, I64 *__restrict__ b, I64 n)
+{
+    I64 i = (I64) blockIdx.x * blockDim.x + threadIdx.x ;
+    const I64 s = (I64) gridDim.x * blockDim.x ;
+    for ( ; i < n ; i += s) b [i] = a [i] ;
+}
+
+} // namespace stmqr

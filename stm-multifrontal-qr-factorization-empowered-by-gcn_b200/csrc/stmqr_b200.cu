@@ -1,0 +1,685 @@
+// stmqr_b200.cu -- host side of the B200 multifrontal-QR engine and its C ABI
+// (include/stmqr_b200.h).  Replaces the numeric phase of the reference,
+// qr_factorize / qr_kernel / qr_multithreads (STMMQR/src/qr/SparseQR_factorize.c:222-985,
+// SparseQR_multithreads.c:14-115): instead of one CPU task per etree subtree on per-task
+// stacks, the fronts are processed level by level (all fronts of an etree level are
+// independent), every level as a handful of batched launches on one CUDA stream, with
+// device-side arenas sized from the symbolic bounds.  No host synchronisation between levels:
+// all data-dependent shapes (fm, Cm, rank, R+H sizes) stay on the device.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/stmqr_b200.h"
+#include "kernels_assembly.cuh"
+#include "kernels_front.cuh"
+
+using namespace stmqr ;
+
+namespace {
+
+struct Level
+{
+    I32 first ;         // offset into the level-ordered front list
+    I32 count ;
+    I32 maxfn ;         // max # columns in the level
+    I64 maxFelems ;     // max bound Fm*fn in the level
+} ;
+
+template <typename T> struct DevBuf
+{
+    T *p = nullptr ;
+    size_t n = 0 ;
+} ;
+
+} // namespace
+
+struct stmqr_handle_s
+{
+    int device = 0 ;
+    cudaStream_t stream = nullptr ;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr ;
+    std::string err ;
+    stmqr_options opt {32, 0, 0, 0} ;
+    bool analyzed = false, have_matrix = false, factorized = false ;
+    int debug_capture = 0 ;
+
+    // host copy of what the host needs
+    I64 m = 0, n = 0, anz = 0, nf = 0, rjsize = 0, hisize = 0, maxfn = 0 ;
+    int do_rank_detection = 1 ;
+    std::vector<I32> h_Super, h_Rp, h_Hip, h_FmB ;
+    std::vector<I32> h_levelFronts ;
+    std::vector<Level> levels ;
+    std::vector<I64> h_Foff, h_Coff ;
+    I64 Fcap = 0, Ccap = 0, Rcap = 0 ;
+    I32 maxLevelWidth = 0 ;
+
+    std::vector<void *> allocs ;
+    size_t device_bytes = 0 ;
+
+    DSym S {} ;
+    DNum N {} ;
+    I32 *d_levelFronts = nullptr ;
+    I32 *d_err = nullptr ;
+    // matrix
+    I64 *d_Ap = nullptr, *d_Ai = nullptr ;
+    double *d_Ax = nullptr ;
+    I64 a_ncol = 0, a_nnz_cap = 0 ;
+    // int64 staging for the download
+    I64 *d_HPinv64 = nullptr, *d_Hii64 = nullptr, *d_wide = nullptr ;
+    // debug capture
+    double *d_capA = nullptr, *d_capF = nullptr ;
+    std::vector<I64> h_capOff ;
+
+    stmqr_numeric_info info {} ;
+    stmqr_stats stats {} ;
+    I64 launches = 0 ;
+} ;
+
+namespace {
+
+int fail (stmqr_handle h, int code, const std::string &msg)
+{
+    if (h) h->err = msg ;
+    return code ;
+}
+
+#define CK(call) do { cudaError_t e_ = (call) ; if (e_ != cudaSuccess) { \
+    return fail (h, (e_ == cudaErrorMemoryAllocation) ? STMQR_ERR_OUT_OF_MEMORY : STMQR_ERR_CUDA, \
+        std::string (#call) + ": " + cudaGetErrorString (e_)) ; } } while (0)
+
+template <typename T> int dev_alloc (stmqr_handle h, T **p, size_t count)
+{
+    *p = nullptr ;
+    size_t bytes = std::max<size_t> (count, 1) * sizeof (T) ;
+    cudaError_t e = cudaMalloc ((void **) p, bytes) ;
+    if (e != cudaSuccess)
+    {
+        return fail (h, STMQR_ERR_OUT_OF_MEMORY, std::string ("cudaMalloc of ") +
+            std::to_string (bytes) + " bytes: " + cudaGetErrorString (e)) ;
+    }
+    h->allocs.push_back ((void *) *p) ;
+    h->device_bytes += bytes ;
+    return STMQR_OK ;
+}
+#define ALLOC(ptr, count) do { int s_ = dev_alloc (h, &(ptr), (size_t) (count)) ; if (s_ != STMQR_OK) return s_ ; } while (0)
+
+template <typename T> int upload (stmqr_handle h, T **dst, const std::vector<T> &src)
+{
+    int s = dev_alloc (h, dst, src.size ()) ;
+    if (s != STMQR_OK) return s ;
+    if (!src.empty ())
+    {
+        cudaError_t e = cudaMemcpyAsync (*dst, src.data (), src.size () * sizeof (T),
+            cudaMemcpyHostToDevice, h->stream) ;
+        if (e != cudaSuccess) return fail (h, STMQR_ERR_CUDA, cudaGetErrorString (e)) ;
+    }
+    return STMQR_OK ;
+}
+#define UPLOAD(ptr, vec) do { int s_ = upload (h, &(ptr), vec) ; if (s_ != STMQR_OK) return s_ ; } while (0)
+
+void free_all (stmqr_handle h)
+{
+    for (void *p : h->allocs) cudaFree (p) ;
+    h->allocs.clear () ;
+    h->device_bytes = 0 ;
+    h->analyzed = h->have_matrix = h->factorized = false ;
+    h->d_Ap = h->d_Ai = nullptr ; h->d_Ax = nullptr ; h->a_ncol = h->a_nnz_cap = 0 ;
+}
+
+bool narrow (const int64_t *src, I64 count, std::vector<I32> &dst)
+{
+    dst.resize ((size_t) count) ;
+    for (I64 i = 0 ; i < count ; i++)
+    {
+        int64_t v = src [i] ;
+        if (v < INT32_MIN || v > INT32_MAX) return false ;
+        dst [(size_t) i] = (I32) v ;
+    }
+    return true ;
+}
+
+inline int grid_for (I64 n, int block, int cap = 148 * 16)
+{
+    I64 g = (n + block - 1) / block ;
+    return (int) std::max<I64> (1, std::min<I64> (g, cap)) ;
+}
+
+} // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int stmqr_b200_device_count (void)
+{
+    int n = 0 ;
+    if (cudaGetDeviceCount (&n) != cudaSuccess) { cudaGetLastError () ; return 0 ; }
+    return n ;
+}
+
+int stmqr_b200_create (int device, stmqr_handle *out)
+{
+    if (!out) return STMQR_ERR_INVALID ;
+    *out = nullptr ;
+    int n = stmqr_b200_device_count () ;
+    if (n <= 0 || device < 0 || device >= n) return STMQR_ERR_NO_DEVICE ;
+    cudaDeviceProp prop ;
+    if (cudaGetDeviceProperties (&prop, device) != cudaSuccess) return STMQR_ERR_NO_DEVICE ;
+    if (prop.major < 10) return STMQR_ERR_NO_DEVICE ;       // sm_100a code only, no fallback
+    stmqr_handle h = new stmqr_handle_s ;
+    h->device = device ;
+    if (cudaSetDevice (device) != cudaSuccess ||
+        cudaStreamCreateWithFlags (&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate (&h->ev0) != cudaSuccess || cudaEventCreate (&h->ev1) != cudaSuccess ||
+        cudaEventCreate (&h->ev2) != cudaSuccess || cudaEventCreate (&h->ev3) != cudaSuccess)
+    {
+        delete h ;
+        return STMQR_ERR_CUDA ;
+    }
+    *out = h ;
+    return STMQR_OK ;
+}
+
+void stmqr_b200_destroy (stmqr_handle h)
+{
+    if (!h) return ;
+    cudaSetDevice (h->device) ;
+    free_all (h) ;
+    if (h->ev0) cudaEventDestroy (h->ev0) ;
+    if (h->ev1) cudaEventDestroy (h->ev1) ;
+    if (h->ev2) cudaEventDestroy (h->ev2) ;
+    if (h->ev3) cudaEventDestroy (h->ev3) ;
+    if (h->stream) cudaStreamDestroy (h->stream) ;
+    delete h ;
+}
+
+int stmqr_b200_set_options (stmqr_handle h, const stmqr_options *opt)
+{
+    if (!h || !opt) return STMQR_ERR_INVALID ;
+    h->opt = *opt ;
+    if (h->opt.panel <= 0 || h->opt.panel > PANEL_MAX) h->opt.panel = PANEL_MAX ;
+    return STMQR_OK ;
+}
+
+const char *stmqr_b200_last_error (stmqr_handle h) { return h ? h->err.c_str () : "null handle" ; }
+
+int stmqr_b200_set_debug_capture (stmqr_handle h, int on)
+{
+    if (!h) return STMQR_ERR_INVALID ;
+    h->debug_capture = on ;
+    return STMQR_OK ;
+}
+
+// -------------------------------------------------------------------------------------------------
+// analyze: the plan.  Everything here depends only on qr_symbolic.
+// -------------------------------------------------------------------------------------------------
+int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
+{
+    if (!h || !sym) return STMQR_ERR_INVALID ;
+    auto t0 = std::chrono::steady_clock::now () ;
+    cudaSetDevice (h->device) ;
+    free_all (h) ;
+    h->err.clear () ;
+    const I64 m = sym->m, n = sym->n, nf = sym->nf, anz = sym->anz, rjsize = sym->rjsize,
+        hisize = sym->hisize ;
+    if (m < 0 || n < 0 || nf < 0 || !sym->Sp || !sym->Sleft || !sym->Super || !sym->Rp ||
+        !sym->Childp || !sym->Child || !sym->Hip || !sym->Fm || !sym->Cm || !sym->PLinv ||
+        (anz > 0 && !sym->Sj) || (rjsize > 0 && !sym->Rj))
+        return fail (h, STMQR_ERR_INVALID, "analyze: missing symbolic arrays") ;
+    if (m > INT32_MAX - 2 || n > INT32_MAX - 2 || anz > INT32_MAX - 2 || rjsize > INT32_MAX - 2 ||
+        hisize > INT32_MAX - 2)
+        return fail (h, STMQR_ERR_TOO_LARGE, "analyze: index range exceeds int32 device indices") ;
+    h->m = m ; h->n = n ; h->nf = nf ; h->anz = anz ; h->rjsize = rjsize ; h->hisize = hisize ;
+    h->maxfn = sym->maxfn ;
+    h->do_rank_detection = (int) sym->do_rank_detection ;
+
+    std::vector<I32> Super, Rp, Rj, Sleft, Sp, Sj, Child, Childp, Hip, PLinv, FmB, CmB ;
+    bool ok = narrow (sym->Super, nf+1, Super) && narrow (sym->Rp, nf+1, Rp) &&
+        narrow (sym->Rj, rjsize, Rj) && narrow (sym->Sleft, n+2, Sleft) &&
+        narrow (sym->Sp, m+1, Sp) && narrow (sym->Sj, anz, Sj) &&
+        narrow (sym->Child, nf+1, Child) && narrow (sym->Childp, nf+2, Childp) &&
+        narrow (sym->Hip, nf+1, Hip) && narrow (sym->PLinv, m, PLinv) &&
+        narrow (sym->Fm, nf, FmB) && narrow (sym->Cm, nf, CmB) ;
+    if (!ok) return fail (h, STMQR_ERR_TOO_LARGE, "analyze: symbolic value exceeds int32") ;
+    std::vector<I32> Qinv ((size_t) n) ;
+    for (I64 k = 0 ; k < n ; k++)
+    {
+        I64 j = sym->Qfill ? sym->Qfill [k] : k ;
+        if (j < 0 || j >= n) return fail (h, STMQR_ERR_INVALID, "analyze: Qfill is not a permutation") ;
+        Qinv [(size_t) j] = (I32) k ;
+    }
+
+    // ---- parent of each front, etree levels (all fronts of a level are independent) --------------
+    std::vector<I32> parent ((size_t) nf, -1), level ((size_t) nf, 0) ;
+    for (I64 f = 0 ; f < nf ; f++)
+        for (I32 q = Childp [f] ; q < Childp [f+1] ; q++)
+        {
+            I32 c = Child [q] ;
+            if (c < 0 || c >= nf) return fail (h, STMQR_ERR_INVALID, "analyze: bad Child") ;
+            parent [c] = (I32) f ;
+        }
+    {
+        // children have smaller postorder index than parents; Post may be absent -> iterate to fixpoint
+        // using the fact that in SPQR's supernodal tree parent index > child index.
+        bool monotone = true ;
+        for (I64 f = 0 ; f < nf ; f++) if (parent [f] >= 0 && parent [f] <= f) monotone = false ;
+        if (monotone)
+        {
+            for (I64 f = 0 ; f < nf ; f++)
+                if (parent [f] >= 0) level [parent [f]] = std::max (level [parent [f]], level [f] + 1) ;
+        }
+        else
+        {
+            if (!sym->Post) return fail (h, STMQR_ERR_INVALID, "analyze: Post required") ;
+            for (I64 k = 0 ; k < nf ; k++)
+            {
+                I64 f = sym->Post [k] ;
+                if (parent [f] >= 0) level [parent [f]] = std::max (level [parent [f]], level [f] + 1) ;
+            }
+        }
+    }
+    I32 nlev = 0 ;
+    for (I64 f = 0 ; f < nf ; f++) nlev = std::max (nlev, level [f] + 1) ;
+    std::vector<std::vector<I32>> byLevel ((size_t) nlev) ;
+    for (I64 f = 0 ; f < nf ; f++) byLevel [level [f]].push_back ((I32) f) ;
+    h->levels.clear () ; h->h_levelFronts.clear () ;
+    h->h_Foff.assign ((size_t) nf, 0) ; h->h_Coff.assign ((size_t) nf, 0) ;
+    h->Fcap = 0 ; h->maxLevelWidth = 0 ;
+    for (I32 l = 0 ; l < nlev ; l++)
+    {
+        auto &v = byLevel [l] ;
+        std::stable_sort (v.begin (), v.end (), [&] (I32 a, I32 b) {
+            return (Rp [a+1] - Rp [a]) > (Rp [b+1] - Rp [b]) ; }) ;
+        Level L ; L.first = (I32) h->h_levelFronts.size () ; L.count = (I32) v.size () ;
+        L.maxfn = 0 ; L.maxFelems = 0 ;
+        I64 off = 0 ;
+        for (I32 f : v)
+        {
+            const I64 fn = Rp [f+1] - Rp [f] ;
+            const I64 fe = (I64) FmB [f] * fn ;
+            L.maxfn = std::max<I32> (L.maxfn, (I32) fn) ;
+            L.maxFelems = std::max (L.maxFelems, fe) ;
+            h->h_Foff [f] = off ;
+            off += (fe + 1) & ~(I64) 1 ;            // keep every front 16-byte aligned
+            h->h_levelFronts.push_back (f) ;
+        }
+        h->Fcap = std::max (h->Fcap, off) ;
+        h->maxLevelWidth = std::max (h->maxLevelWidth, L.count) ;
+        h->levels.push_back (L) ;
+    }
+
+    // ---- contribution-block arena (bound sizes) and R+H arena bound ------------------------------
+    // csize bound: qr_analyze's Cm[f] rows by cn columns (SparseQR_analyze.c:536-550).
+    // R+H bound per front: sum_j min (max (j+1, Stair_j), fm) with the bound staircase (:559-573).
+    {
+        I64 coff = 0, rcap = 0 ;
+        std::vector<I32> stairB ((size_t) std::max<I64> (sym->maxfn, 1)) ;
+        std::vector<I32> Fmap ((size_t) std::max<I64> (n, 1)) ;
+        for (I64 f = 0 ; f < nf ; f++)
+        {
+            const I64 fp = Super [f+1] - Super [f], fn = Rp [f+1] - Rp [f] ;
+            const I64 cn = fn - fp, cm = std::min<I64> (CmB [f], cn) ;
+            const I64 csize = (cm * (cm + 1)) / 2 + cm * (cn - cm) ;
+            h->h_Coff [f] = coff ;
+            coff += (csize + 1) & ~(I64) 1 ;
+            // staircase bound
+            for (I64 j = 0 ; j < fn ; j++) Fmap [Rj [Rp [f] + j]] = (I32) j ;
+            for (I64 j = 0 ; j < fn ; j++)
+                stairB [j] = (j < fp) ? (Sleft [Super [f]+j+1] - Sleft [Super [f]+j]) : 0 ;
+            for (I32 q = Childp [f] ; q < Childp [f+1] ; q++)
+            {
+                const I32 c = Child [q] ;
+                const I64 fpc = Super [c+1] - Super [c] ;
+                const I64 cnc = (Rp [c+1] - Rp [c]) - fpc ;
+                const I64 cmc = std::min<I64> (CmB [c], cnc) ;
+                for (I64 ci = 0 ; ci < cmc ; ci++) stairB [Fmap [Rj [Rp [c] + fpc + ci]]]++ ;
+            }
+            I64 fm = 0, rh = 0, run = 0 ;
+            for (I64 j = 0 ; j < fn ; j++) fm += stairB [j] ;
+            for (I64 j = 0 ; j < fn ; j++)
+            {
+                run += stairB [j] ;
+                rh += std::min<I64> (std::max<I64> (j + 1, run), fm) ;
+            }
+            if (fm > FmB [f]) FmB [f] = (I32) fm ;     // never trust a smaller bound
+            rcap += rh ;
+        }
+        h->Ccap = coff ;
+        h->Rcap = rcap + 16 ;
+    }
+
+    // ---- symbolic maps: Cj (child column -> parent column), Sjf (S entry -> front column) -------
+    std::vector<I32> Cj ((size_t) std::max<I64> (rjsize, 1), 0), Sjf ((size_t) std::max<I64> (anz, 1), 0) ;
+    {
+        std::vector<I32> Fmap ((size_t) std::max<I64> (n, 1), -1) ;
+        for (I64 f = 0 ; f < nf ; f++)
+        {
+            const I64 p1 = Rp [f], fn = Rp [f+1] - p1, col1 = Super [f], fp = Super [f+1] - col1 ;
+            for (I64 j = 0 ; j < fn ; j++) Fmap [Rj [p1+j]] = (I32) j ;
+            for (I32 r = Sleft [col1] ; r < Sleft [col1+fp] ; r++)
+                for (I32 p = Sp [r] ; p < Sp [r+1] ; p++) Sjf [p] = Fmap [Sj [p]] ;
+            for (I32 q = Childp [f] ; q < Childp [f+1] ; q++)
+            {
+                const I32 c = Child [q] ;
+                const I64 fpc = Super [c+1] - Super [c] ;
+                for (I64 p = Rp [c] + fpc ; p < Rp [c+1] ; p++) Cj [p] = Fmap [Rj [p]] ;
+            }
+        }
+    }
+
+    // ---- device memory -----------------------------------------------------------------------------
+    h->h_Super = Super ; h->h_Rp = Rp ; h->h_Hip = Hip ; h->h_FmB = FmB ;
+    DSym &S = h->S ;
+    S.m = (I32) m ; S.n = (I32) n ; S.nf = (I32) nf ;
+    I32 *p ;
+    UPLOAD (p, Super) ; S.Super = p ;   UPLOAD (p, Rp) ; S.Rp = p ;       UPLOAD (p, Rj) ; S.Rj = p ;
+    UPLOAD (p, Sleft) ; S.Sleft = p ;   UPLOAD (p, Sp) ; S.Sp = p ;       UPLOAD (p, Sj) ; S.Sj = p ;
+    UPLOAD (p, Child) ; S.Child = p ;   UPLOAD (p, Childp) ; S.Childp = p ; UPLOAD (p, Hip) ; S.Hip = p ;
+    UPLOAD (p, PLinv) ; S.PLinv = p ;   UPLOAD (p, Qinv) ; S.Qinv = p ;
+    UPLOAD (p, Cj) ; S.Cj = p ;         UPLOAD (p, Sjf) ; S.Sjf = p ;
+    I64 *p64 ;
+    UPLOAD (p64, h->h_Foff) ; S.Foff = p64 ;
+    UPLOAD (p64, h->h_Coff) ; S.Coff = p64 ;
+    UPLOAD (h->d_levelFronts, h->h_levelFronts) ;
+
+    DNum &N = h->N ;
+    ALLOC (N.Sx, anz) ;
+    ALLOC (N.F, h->Fcap) ;
+    ALLOC (N.C, h->Ccap) ;
+    ALLOC (N.R, h->Rcap) ;
+    ALLOC (N.HTau, rjsize) ;
+    ALLOC (N.Tws, (I64) h->maxLevelWidth * PANEL_MAX * PANEL_MAX) ;
+    ALLOC (N.stair, rjsize) ;
+    ALLOC (N.Cmap, rjsize) ;
+    ALLOC (N.rowpos, m) ;
+    ALLOC (N.Hii, hisize) ;
+    ALLOC (N.Hm, nf) ; ALLOC (N.Hr, nf) ; ALLOC (N.Cm, nf) ; ALLOC (N.rank, nf) ;
+    ALLOC (N.colp, rjsize) ;
+    ALLOC (N.rsize, nf) ; ALLOC (N.Roff, nf) ;
+    ALLOC (N.Rdead, n) ;
+    ALLOC (N.g, h->maxLevelWidth) ; ALLOC (N.done, h->maxLevelWidth) ;
+    ALLOC (N.pnl_g1, h->maxLevelWidth) ; ALLOC (N.pnl_nv, h->maxLevelWidth) ;
+    ALLOC (N.pnl_tend, h->maxLevelWidth) ;
+    ALLOC (N.pnl_cols, (I64) h->maxLevelWidth * PANEL_MAX) ;
+    ALLOC (N.rcursor, 1) ;
+    ALLOC (N.sumrank, 4) ; N.maxfrank = N.sumrank + 1 ; N.maxfm = N.sumrank + 2 ; N.rank1 = N.sumrank + 3 ;
+    ALLOC (N.flops, 1) ;
+    ALLOC (N.W, m) ;
+    ALLOC (N.base1, nf) ; ALLOC (N.base2, nf) ;
+    ALLOC (h->d_err, 1) ;
+    ALLOC (h->d_HPinv64, m) ;
+    ALLOC (h->d_Hii64, hisize) ;
+    ALLOC (h->d_wide, std::max<I64> (rjsize, nf)) ;
+    if (h->debug_capture)
+    {
+        h->h_capOff.assign ((size_t) nf + 1, 0) ;
+        for (I64 f = 0 ; f < nf ; f++)
+            h->h_capOff [f+1] = h->h_capOff [f] + (I64) FmB [f] * (Rp [f+1] - Rp [f]) ;
+        ALLOC (h->d_capA, h->h_capOff [nf]) ;
+        ALLOC (h->d_capF, h->h_capOff [nf]) ;
+    }
+    CK (cudaStreamSynchronize (h->stream)) ;
+    h->analyzed = true ;
+    memset (&h->stats, 0, sizeof (h->stats)) ;
+    h->stats.ms_plan = std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now () - t0).count () ;
+    h->stats.nlevels = (I64) h->levels.size () ;
+    h->stats.device_bytes = (I64) h->device_bytes ;
+    return STMQR_OK ;
+}
+
+// -------------------------------------------------------------------------------------------------
+int stmqr_b200_upload_matrix (stmqr_handle h, const stmqr_csc_view *A)
+{
+    if (!h || !A || !h->analyzed) return fail (h, STMQR_ERR_INVALID, "upload_matrix: analyze first") ;
+    cudaSetDevice (h->device) ;
+    if (A->nrow != h->m || A->ncol != h->n || !A->p || (A->p [A->ncol] > 0 && (!A->i || !A->x)))
+        return fail (h, STMQR_ERR_INVALID, "upload_matrix: matrix does not match the analysis") ;
+    const I64 nnz = A->p [A->ncol] ;
+    if (nnz != h->anz) return fail (h, STMQR_ERR_INVALID, "upload_matrix: nnz(A) != anz of the analysis") ;
+    if (!h->d_Ap || h->a_ncol != A->ncol || h->a_nnz_cap < nnz)
+    {
+        ALLOC (h->d_Ap, A->ncol + 1) ;
+        ALLOC (h->d_Ai, nnz) ;
+        ALLOC (h->d_Ax, nnz) ;
+        h->a_ncol = A->ncol ; h->a_nnz_cap = nnz ;
+    }
+    CK (cudaEventRecord (h->ev0, h->stream)) ;
+    CK (cudaMemcpyAsync (h->d_Ap, A->p, (A->ncol + 1) * sizeof (I64), cudaMemcpyHostToDevice, h->stream)) ;
+    if (nnz > 0)
+    {
+        CK (cudaMemcpyAsync (h->d_Ai, A->i, nnz * sizeof (I64), cudaMemcpyHostToDevice, h->stream)) ;
+        CK (cudaMemcpyAsync (h->d_Ax, A->x, nnz * sizeof (double), cudaMemcpyHostToDevice, h->stream)) ;
+    }
+    CK (cudaEventRecord (h->ev1, h->stream)) ;
+    CK (cudaStreamSynchronize (h->stream)) ;
+    float ms = 0 ;
+    cudaEventElapsedTime (&ms, h->ev0, h->ev1) ;
+    h->stats.ms_h2d = ms ;
+    h->have_matrix = true ;
+    return STMQR_OK ;
+}
+
+// -------------------------------------------------------------------------------------------------
+int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stmqr_numeric_info *info)
+{
+    if (!h || !h->analyzed || !h->have_matrix)
+        return fail (h, STMQR_ERR_INVALID, "factorize: analyze and upload_matrix first") ;
+    cudaSetDevice (h->device) ;
+    cudaStream_t st = h->stream ;
+    DSym &S = h->S ; DNum &N = h->N ;
+    if (!h->do_rank_detection) tol = -1 ;           // SparseQR_factorize.c:285-289
+    h->launches = 0 ;
+    const int PB = (h->opt.panel > 0 && h->opt.panel <= PANEL_MAX) ? h->opt.panel : PANEL_MAX ;
+
+    CK (cudaEventRecord (h->ev0, st)) ;
+    CK (cudaMemsetAsync (N.Rdead, 0, std::max<I64> (h->n, 1), st)) ;
+    CK (cudaMemsetAsync (N.rcursor, 0, sizeof (unsigned long long), st)) ;
+    CK (cudaMemsetAsync (N.sumrank, 0, 4 * sizeof (I32), st)) ;
+    CK (cudaMemsetAsync (N.flops, 0, sizeof (double), st)) ;
+    CK (cudaMemsetAsync (h->d_err, 0, sizeof (I32), st)) ;
+    CK (cudaMemsetAsync (N.HTau, 0, std::max<I64> (h->rjsize, 1) * sizeof (double), st)) ;
+
+    if (h->anz > 0)
+    {
+        k_build_S<<<grid_for (h->n * 32, 256), 256, 0, st>>> ((I32) h->n, h->d_Ap, h->d_Ai, h->d_Ax, S, N.Sx, h->d_err) ;
+        h->launches++ ;
+    }
+
+    for (const Level &Lv : h->levels)
+    {
+        const I32 *fr = h->d_levelFronts + Lv.first ;
+        k_front_setup<<<Lv.count, 128, 0, st>>> (fr, S, N) ;
+        int nsl = (int) std::min<I64> (148, std::max<I64> (1, Lv.maxFelems / 8192)) ;
+        k_assemble<<<dim3 (Lv.count, nsl), 256, 0, st>>> (fr, S, N) ;
+        h->launches += 2 ;
+        if (h->debug_capture)
+        {
+            CK (cudaStreamSynchronize (st)) ;
+            std::vector<I32> hm ((size_t) h->nf) ;
+            CK (cudaMemcpy (hm.data (), N.Hm, h->nf * sizeof (I32), cudaMemcpyDeviceToHost)) ;
+            for (I32 i = 0 ; i < Lv.count ; i++)
+            {
+                I32 f = h->h_levelFronts [Lv.first + i] ;
+                I64 cnt = (I64) hm [f] * (h->h_Rp [f+1] - h->h_Rp [f]) ;
+                if (cnt > 0) CK (cudaMemcpy (h->d_capA + h->h_capOff [f], N.F + h->h_Foff [f],
+                    cnt * sizeof (double), cudaMemcpyDeviceToDevice)) ;
+            }
+        }
+        LevelArgs L ; L.fronts = fr ; L.count = Lv.count ; L.tol = tol ; L.ntol = ntol ;
+        const int pthreads = (Lv.maxFelems >= 64 * 1024) ? 1024 : ((Lv.maxFelems >= 4096) ? 256 : 64) ;
+        for (I32 k1 = 0 ; k1 < Lv.maxfn ; k1 += PB)
+        {
+            // fronts are sorted by # columns descending: the active ones are a prefix
+            I32 lo = 0, hi = Lv.count ;
+            while (lo < hi)
+            {
+                I32 mid = (lo + hi) / 2 ;
+                I32 f = h->h_levelFronts [Lv.first + mid] ;
+                if (h->h_Rp [f+1] - h->h_Rp [f] > k1) lo = mid + 1 ; else hi = mid ;
+            }
+            const I32 active = lo ;
+            if (active == 0) break ;
+            k_panel<<<active, pthreads, 0, st>>> (L, S, N, k1, PB) ;
+            h->launches++ ;
+            const I32 k2 = k1 + PB ;
+            if (k2 < Lv.maxfn)
+            {
+                I32 lo2 = 0, hi2 = active ;
+                while (lo2 < hi2)
+                {
+                    I32 mid = (lo2 + hi2) / 2 ;
+                    I32 f = h->h_levelFronts [Lv.first + mid] ;
+                    if (h->h_Rp [f+1] - h->h_Rp [f] > k2) lo2 = mid + 1 ; else hi2 = mid ;
+                }
+                if (lo2 > 0)
+                {
+                    const int tiles = (Lv.maxfn - k2 + UPD_TB - 1) / UPD_TB ;
+                    k_update<<<dim3 (lo2, tiles), 256, 0, st>>> (L, S, N, k2) ;
+                    h->launches++ ;
+                }
+            }
+        }
+        if (h->debug_capture)
+        {
+            CK (cudaStreamSynchronize (st)) ;
+            std::vector<I32> hm ((size_t) h->nf) ;
+            CK (cudaMemcpy (hm.data (), N.Hm, h->nf * sizeof (I32), cudaMemcpyDeviceToHost)) ;
+            for (I32 i = 0 ; i < Lv.count ; i++)
+            {
+                I32 f = h->h_levelFronts [Lv.first + i] ;
+                I64 cnt = (I64) hm [f] * (h->h_Rp [f+1] - h->h_Rp [f]) ;
+                if (cnt > 0) CK (cudaMemcpy (h->d_capF + h->h_capOff [f], N.F + h->h_Foff [f],
+                    cnt * sizeof (double), cudaMemcpyDeviceToDevice)) ;
+            }
+        }
+        k_front_finish<<<Lv.count, 128, 0, st>>> (fr, S, N) ;
+        k_level_alloc<<<1, 1024, 0, st>>> (fr, Lv.count, N) ;
+        k_pack<<<dim3 (Lv.count, nsl), 256, 0, st>>> (fr, S, N) ;
+        h->launches += 3 ;
+    }
+
+    // qr_hpinv (:991-1060)
+    if (h->nf > 0)
+    {
+        k_hpinv_counts<<<grid_for (h->nf, 256, 1 << 20), 256, 0, st>>> (S, N) ;
+        k_scan_i64<<<1, 1024, 0, st>>> (N.base1, N.base2, (I32) h->nf) ;
+        k_hpinv_rows<<<grid_for (h->nf * 32, 256, 1 << 22), 256, 0, st>>> (S, N) ;
+        h->launches += 3 ;
+    }
+    {
+        I64 nempty = 0 ;    // rows Sleft[n]..m-1; count is symbolic but lives on the device: launch by bound
+        (void) nempty ;
+        k_hpinv_empty<<<grid_for (std::max<I64> (h->m, 1), 256, 1 << 22), 256, 0, st>>> (S, N) ;
+        k_hpinv_apply<<<grid_for (std::max<I64> (std::max (h->m, h->nf * 32), 1), 256), 256, 0, st>>> (S, N, h->d_HPinv64, h->d_Hii64) ;
+        const I64 nt = std::min<I64> (std::max<I64> (ntol, 0), h->n) ;
+        if (nt > 0) { k_rank1<<<(unsigned) ((nt + 255) / 256), 256, 0, st>>> (N.Rdead, nt, N.rank1) ; h->launches++ ; }
+        h->launches += 2 ;
+    }
+    CK (cudaEventRecord (h->ev1, st)) ;
+
+    // scalars back
+    unsigned long long rcur = 0 ; I32 sc [4] = {0, 0, 0, 0} ; double fl = 0 ; I32 err = 0 ;
+    CK (cudaMemcpyAsync (&rcur, N.rcursor, sizeof (rcur), cudaMemcpyDeviceToHost, st)) ;
+    CK (cudaMemcpyAsync (sc, N.sumrank, sizeof (sc), cudaMemcpyDeviceToHost, st)) ;
+    CK (cudaMemcpyAsync (&fl, N.flops, sizeof (fl), cudaMemcpyDeviceToHost, st)) ;
+    CK (cudaMemcpyAsync (&err, h->d_err, sizeof (err), cudaMemcpyDeviceToHost, st)) ;
+    CK (cudaStreamSynchronize (st)) ;
+    CK (cudaGetLastError ()) ;
+    if (err) return fail (h, STMQR_ERR_INVALID, "factorize: an entry of A is not in the pattern of S") ;
+    if ((I64) rcur > h->Rcap) return fail (h, STMQR_ERR_INVALID, "factorize: R+H arena bound exceeded") ;
+    float ms = 0 ;
+    cudaEventElapsedTime (&ms, h->ev0, h->ev1) ;
+    h->stats.ms_numeric = ms ;
+    h->stats.launches = h->launches ;
+    h->stats.flops = fl ;
+    h->info.rank = sc [0] ;
+    h->info.maxfrank = std::max<I32> (1, sc [1]) ;       // maxfrank starts at 1 (:555)
+    h->info.maxfm = sc [2] ;
+    h->info.rank1 = (ntol >= h->n) ? sc [0] : sc [3] ;
+    h->info.rh_size = (I64) rcur ;
+    h->info.flops = fl ;
+    if (info) *info = h->info ;
+    h->factorized = true ;
+    return STMQR_OK ;
+}
+
+int stmqr_b200_factorize (stmqr_handle h, const stmqr_csc_view *A, double tol, int64_t ntol,
+    stmqr_numeric_info *info)
+{
+    int s = stmqr_b200_upload_matrix (h, A) ;
+    if (s != STMQR_OK) return s ;
+    return stmqr_b200_factorize_resident (h, tol, ntol, info) ;
+}
+
+// -------------------------------------------------------------------------------------------------
+int stmqr_b200_download (stmqr_handle h, const stmqr_numeric_view *out)
+{
+    if (!h || !out || !h->factorized) return fail (h, STMQR_ERR_INVALID, "download: factorize first") ;
+    cudaSetDevice (h->device) ;
+    cudaStream_t st = h->stream ;
+    DNum &N = h->N ;
+    CK (cudaEventRecord (h->ev2, st)) ;
+    if (out->stack && h->info.rh_size > 0)
+        CK (cudaMemcpyAsync (out->stack, N.R, h->info.rh_size * sizeof (double), cudaMemcpyDeviceToHost, st)) ;
+    if (out->Roff && h->nf > 0)
+        CK (cudaMemcpyAsync (out->Roff, N.Roff, h->nf * sizeof (I64), cudaMemcpyDeviceToHost, st)) ;
+    if (out->Rdead && h->n > 0)
+        CK (cudaMemcpyAsync (out->Rdead, N.Rdead, h->n, cudaMemcpyDeviceToHost, st)) ;
+    if (out->HTau && h->rjsize > 0)
+        CK (cudaMemcpyAsync (out->HTau, N.HTau, h->rjsize * sizeof (double), cudaMemcpyDeviceToHost, st)) ;
+    if (out->HPinv && h->m > 0)
+        CK (cudaMemcpyAsync (out->HPinv, h->d_HPinv64, h->m * sizeof (I64), cudaMemcpyDeviceToHost, st)) ;
+    if (out->Hii && h->hisize > 0)
+        CK (cudaMemcpyAsync (out->Hii, h->d_Hii64, h->hisize * sizeof (I64), cudaMemcpyDeviceToHost, st)) ;
+    auto widen = [&] (const I32 *src, I64 *dst, I64 cnt) -> int {
+        if (!dst || cnt <= 0) return STMQR_OK ;
+        k_widen<<<grid_for (cnt, 256), 256, 0, st>>> (src, h->d_wide, cnt) ;
+        CK (cudaMemcpyAsync (dst, h->d_wide, cnt * sizeof (I64), cudaMemcpyDeviceToHost, st)) ;
+        return STMQR_OK ;
+    } ;
+    int s ;
+    if ((s = widen (N.stair, out->HStair, h->rjsize)) != STMQR_OK) return s ;
+    if ((s = widen (N.Hm, out->Hm, h->nf)) != STMQR_OK) return s ;
+    if ((s = widen (N.Hr, out->Hr, h->nf)) != STMQR_OK) return s ;
+    CK (cudaEventRecord (h->ev3, st)) ;
+    CK (cudaStreamSynchronize (st)) ;
+    float ms = 0 ;
+    cudaEventElapsedTime (&ms, h->ev2, h->ev3) ;
+    h->stats.ms_d2h = ms ;
+    return STMQR_OK ;
+}
+
+int stmqr_b200_get_stats (stmqr_handle h, stmqr_stats *out)
+{
+    if (!h || !out) return STMQR_ERR_INVALID ;
+    h->stats.device_bytes = (I64) h->device_bytes ;
+    *out = h->stats ;
+    return STMQR_OK ;
+}
+
+int stmqr_b200_get_front (stmqr_handle h, int64_t f, int which, double *F, int64_t capacity,
+    int64_t *fm, int64_t *fn)
+{
+    if (!h || !h->factorized || !h->debug_capture || f < 0 || f >= h->nf)
+        return fail (h, STMQR_ERR_INVALID, "get_front: needs debug capture and a factorization") ;
+    cudaSetDevice (h->device) ;
+    I32 hm = 0 ;
+    CK (cudaMemcpy (&hm, h->N.Hm + f, sizeof (I32), cudaMemcpyDeviceToHost)) ;
+    const I64 n = h->h_Rp [f+1] - h->h_Rp [f] ;
+    if (fm) *fm = hm ;
+    if (fn) *fn = n ;
+    const I64 cnt = (I64) hm * n ;
+    if (cnt > capacity) return fail (h, STMQR_ERR_INVALID, "get_front: buffer too small") ;
+    if (cnt > 0)
+        CK (cudaMemcpy (F, (which ? h->d_capF : h->d_capA) + h->h_capOff [f], cnt * sizeof (double),
+            cudaMemcpyDeviceToHost)) ;
+    return STMQR_OK ;
+}
+
+} // extern "C"

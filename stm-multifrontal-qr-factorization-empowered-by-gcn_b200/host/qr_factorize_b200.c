@@ -1,0 +1,196 @@
+/* qr_factorize_b200.c -- the drop-in replacement of the reference's numeric phase.
+ *
+ * Exports
+ *     qr_numeric *qr_factorize (sparse_csc **Ahandle, Long freeA, double tol, Long ntol,
+ *                               qr_symbolic *QRsym, sparse_common *cc)
+ * with the prototype of STMMQR/include/SparseQR.h:127-135 and the contract of the reference
+ * definition (STMMQR/src/qr/SparseQR_factorize.c:222-749):
+ *   - QRsym == NULL            -> free A if freeA, return NULL                       (:247-254)
+ *   - freeA                    -> SparseCore_free_sparse (Ahandle) always            (:324-327)
+ *   - tol < 0 / !do_rank_detection -> no rank detection                              (:285-289)
+ *   - every member of the returned qr_numeric is allocated with SparseCore_malloc/calloc with
+ *     exactly the sizes qr_freenum (STMMQR/src/qr/SparseQR.c:1245-1270) frees
+ *   - failure: return NULL with cc->status < SPARSE_OK                               (:329-333)
+ * It is compiled against the reference's own headers (it is host code of the reference's
+ * library: link it instead of -- or LD_PRELOAD it in front of -- SparseQR_factorize.o's
+ * qr_factorize).  All numeric work goes through the C ABI of include/stmqr_b200.h to the
+ * CUDA engine; there is no CPU path here.
+ *
+ * ns = 1: one exactly-sized host stack holds all packed R+H blocks (any front->stack
+ * placement is legal for the consumers, which only use Rblock[f]).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include "SparseQR.h"
+#include "stmqr_b200.h"
+
+/* One engine handle per process, re-planned when the symbolic object changes. */
+static stmqr_handle g_handle = NULL ;
+static qr_symbolic *g_planned_for = NULL ;
+static Long g_planned_sig [6] ;
+
+static int map_status (int s)
+{
+    switch (s)
+    {
+        case STMQR_OK:                return SPARSE_OK ;
+        case STMQR_ERR_OUT_OF_MEMORY: return SPARSE_OUT_OF_MEMORY ;
+        case STMQR_ERR_TOO_LARGE:     return SPARSE_TOO_LARGE ;
+        default:                      return SPARSE_INVALID ;
+    }
+}
+
+static void report (sparse_common *cc, int s, const char *where)
+{
+    int st = map_status (s) ;
+    fprintf (stderr, "stmqr_b200 %s: %s\n", where, g_handle ? stmqr_b200_last_error (g_handle) : "no device") ;
+    SparseCore_error (st, __FILE__, __LINE__, "B200 numeric factorization failed", cc) ;
+    if (cc->status >= SPARSE_OK) cc->status = st ;
+}
+
+qr_numeric *stmqr_b200_qr_factorize (sparse_csc **Ahandle, Long freeA, double tol, Long ntol,
+    qr_symbolic *QRsym, sparse_common *cc)
+{
+    if (QRsym == NULL)
+    {
+        if (freeA) SparseCore_free_sparse (Ahandle, cc) ;
+        return (NULL) ;
+    }
+    sparse_csc *A = *Ahandle ;
+    Long nf = QRsym->nf, m = QRsym->m, n = QRsym->n, rjsize = QRsym->rjsize,
+        hisize = QRsym->hisize ;
+    int s ;
+
+    if (g_handle == NULL)
+    {
+        int dev = 0 ;
+        const char *e = getenv ("STMQR_B200_DEVICE") ;
+        if (e) dev = atoi (e) ;
+        s = stmqr_b200_create (dev, &g_handle) ;
+        if (s != STMQR_OK)
+        {
+            g_handle = NULL ;
+            if (freeA) SparseCore_free_sparse (Ahandle, cc) ;
+            report (cc, s, "create") ;
+            return (NULL) ;
+        }
+    }
+
+    /* plan (level sets, maps, arenas): depends only on the symbolic object */
+    Long sig [6] = { m, n, nf, rjsize, hisize, QRsym->anz } ;
+    int same = (g_planned_for == QRsym) ;
+    for (int i = 0 ; same && i < 6 ; i++) same = (sig [i] == g_planned_sig [i]) ;
+    /* Re-planning is the safe default (a new qr_symbolic can be malloc'ed at the address of a
+     * freed one); STMQR_B200_CACHE_PLAN=1 keeps the plan across calls with the same object,
+     * which is what a refactorization loop over same-pattern matrices wants. */
+    if (!(same && getenv ("STMQR_B200_CACHE_PLAN")))
+    {
+        stmqr_symbolic_view v ;
+        v.m = m ; v.n = n ; v.anz = QRsym->anz ; v.nf = nf ; v.maxfn = QRsym->maxfn ;
+        v.rjsize = rjsize ; v.hisize = hisize ;
+        v.do_rank_detection = QRsym->do_rank_detection ; v.keepH = QRsym->keepH ;
+        v.Sp = QRsym->Sp ; v.Sj = QRsym->Sj ; v.Qfill = QRsym->Qfill ; v.PLinv = QRsym->PLinv ;
+        v.Sleft = QRsym->Sleft ; v.Parent = QRsym->Parent ; v.Child = QRsym->Child ;
+        v.Childp = QRsym->Childp ; v.Super = QRsym->Super ; v.Rp = QRsym->Rp ; v.Rj = QRsym->Rj ;
+        v.Post = QRsym->Post ; v.Hip = QRsym->Hip ; v.Fm = QRsym->Fm ; v.Cm = QRsym->Cm ;
+        s = stmqr_b200_analyze (g_handle, &v) ;
+        if (s != STMQR_OK)
+        {
+            g_planned_for = NULL ;
+            if (freeA) SparseCore_free_sparse (Ahandle, cc) ;
+            report (cc, s, "analyze") ;
+            return (NULL) ;
+        }
+        g_planned_for = QRsym ;
+        for (int i = 0 ; i < 6 ; i++) g_planned_sig [i] = sig [i] ;
+    }
+
+    /* the reference uses cc->Iwork (size max(m,nf)) as scratch and callers rely on it existing */
+    SparseCore_allocate_work (0, (m > nf) ? m : nf, 0, cc) ;
+
+    stmqr_csc_view Av ;
+    Av.nrow = A->nrow ; Av.ncol = A->ncol ; Av.nzmax = A->nzmax ;
+    Av.p = (const int64_t *) A->p ; Av.i = (const int64_t *) A->i ; Av.x = (const double *) A->x ;
+    stmqr_numeric_info info ;
+    s = stmqr_b200_factorize (g_handle, &Av, tol, ntol, &info) ;
+
+    if (freeA) SparseCore_free_sparse (Ahandle, cc) ;           /* A is no longer needed (:324) */
+    if (s != STMQR_OK || cc->status < SPARSE_OK)
+    {
+        if (s != STMQR_OK) report (cc, s, "factorize") ;
+        return (NULL) ;
+    }
+
+    /* ---- allocate the numeric object exactly as qr_freenum expects (:339-375) ---- */
+    qr_numeric *QRnum = (qr_numeric *) SparseCore_malloc (1, sizeof (qr_numeric), cc) ;
+    if (cc->status < SPARSE_OK) return (NULL) ;
+    Long ns = 1 ;
+    QRnum->Rblock     = (double **) SparseCore_malloc (nf, sizeof (double *), cc) ;
+    QRnum->Rdead      = (char *)    SparseCore_calloc (n,  sizeof (char), cc) ;
+    QRnum->Stacks     = (double **) SparseCore_calloc (ns, sizeof (double *), cc) ;
+    QRnum->Stack_size = (Long *)    SparseCore_calloc (ns, sizeof (Long), cc) ;
+    QRnum->HStair = (Long *)   SparseCore_malloc (rjsize, sizeof (Long), cc) ;
+    QRnum->HTau   = (double *) SparseCore_malloc (rjsize, sizeof (double), cc) ;
+    QRnum->Hii    = (Long *)   SparseCore_malloc (hisize, sizeof (Long), cc) ;
+    QRnum->Hm     = (Long *)   SparseCore_malloc (nf, sizeof (Long), cc) ;
+    QRnum->Hr     = (Long *)   SparseCore_malloc (nf, sizeof (Long), cc) ;
+    QRnum->HPinv  = (Long *)   SparseCore_malloc (m, sizeof (Long), cc) ;
+    QRnum->n = n ; QRnum->m = m ; QRnum->nf = nf ;
+    QRnum->rjsize = rjsize ; QRnum->hisize = hisize ; QRnum->keepH = QRsym->keepH ;
+    QRnum->maxstack = QRsym->maxstack ;
+    QRnum->ns = ns ; QRnum->ntasks = 1 ;
+    QRnum->maxfm = EMPTY ;
+    QRnum->norm_E_fro = 0 ;
+    Long *Roff = (Long *) SparseCore_malloc (nf, sizeof (Long), cc) ;
+    if (cc->status == SPARSE_OK)
+    {
+        Long stacksize = (info.rh_size > 0) ? info.rh_size : 1 ;
+        QRnum->Stack_size [0] = stacksize ;
+        QRnum->Stacks [0] = (double *) SparseCore_malloc (stacksize, sizeof (double), cc) ;
+    }
+    if (cc->status < SPARSE_OK)
+    {
+        SparseCore_free (nf, sizeof (Long), Roff, cc) ;
+        qr_freenum (&QRnum, cc) ;
+        return (NULL) ;
+    }
+
+    stmqr_numeric_view out ;
+    out.stack = QRnum->Stacks [0] ; out.Roff = (int64_t *) Roff ; out.Rdead = QRnum->Rdead ;
+    out.HStair = (int64_t *) QRnum->HStair ; out.HTau = QRnum->HTau ;
+    out.Hii = (int64_t *) QRnum->Hii ; out.Hm = (int64_t *) QRnum->Hm ;
+    out.Hr = (int64_t *) QRnum->Hr ; out.HPinv = (int64_t *) QRnum->HPinv ;
+    s = stmqr_b200_download (g_handle, &out) ;
+    if (s != STMQR_OK)
+    {
+        SparseCore_free (nf, sizeof (Long), Roff, cc) ;
+        qr_freenum (&QRnum, cc) ;
+        report (cc, s, "download") ;
+        return (NULL) ;
+    }
+    for (Long f = 0 ; f < nf ; f++) QRnum->Rblock [f] = QRnum->Stacks [0] + Roff [f] ;
+    SparseCore_free (nf, sizeof (Long), Roff, cc) ;
+
+    QRnum->rank = info.rank ;
+    QRnum->rank1 = info.rank1 ;
+    QRnum->maxfrank = info.maxfrank ;
+    QRnum->maxfm = info.maxfm ;
+    cc->SPQR_flopcount = info.flops ;           /* the reference's count (:504,:1571) */
+    return (QRnum) ;
+}
+
+/* The reference's symbol.  When this library is linked (or preloaded) in front of the reference's
+ * SparseQR_factorize.o, SparseQR() (SparseQR.c:349,371) and SparseLQ() call the B200 engine. */
+qr_numeric *qr_factorize (sparse_csc **Ahandle, Long freeA, double tol, Long ntol,
+    qr_symbolic *QRsym, sparse_common *cc)
+{
+    return stmqr_b200_qr_factorize (Ahandle, freeA, tol, ntol, QRsym, cc) ;
+}
+
+/* Release the device (optional; for drivers that want a clean exit). */
+void stmqr_b200_dropin_shutdown (void)
+{
+    if (g_handle) stmqr_b200_destroy (g_handle) ;
+    g_handle = NULL ;
+    g_planned_for = NULL ;
+}

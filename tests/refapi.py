@@ -388,3 +388,60 @@ def structural_equal(a: sq.Numeric, b: sq.Numeric, sym=None):
         if x.shape != y.shape or not np.array_equal(x, y):
             bad.append((k, int(np.sum(x != y)) if x.shape == y.shape else "shape"))
     return bad
+
+
+# --------------------------------------------------------------------------------------------
+# golden fixtures (tests/golden/*.npz, made by tests/golden/make_golden.py from the reference)
+# --------------------------------------------------------------------------------------------
+GOLDEN_CASES = ("dwt_992_metis", "dwt_992_colamd", "lap2d_24_metis", "lap3d_8_metis",
+                "tall_600x150_colamd", "lap2d_16_notol", "rankdef_120x80_colamd")
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    scal = {k[2:]: int(z[k]) for k in z.files if k.startswith("s_")}
+    arrs = {k[2:]: z[k] for k in z.files if k.startswith("a_")}
+    sym = sq.Symbolic(scal, arrs)
+    A = sq.Csc(int(z["A_m"]), int(z["A_n"]), z["A_p"], z["A_i"], z["A_x"])
+    num = sq.Numeric(int(z["ref_rank"]), int(z["ref_rank1"]), int(z["ref_maxfrank"]), int(z["ref_maxfm"]),
+                     int(z["ref_stack"].shape[0]), float(z["ref_flops"]), stack=z["ref_stack"], Roff=z["ref_Roff"],
+                     Rdead=z["ref_Rdead"], HStair=z["ref_HStair"], HTau=z["ref_HTau"], Hii=z["ref_Hii"],
+                     Hm=z["ref_Hm"], Hr=z["ref_Hr"], HPinv=z["ref_HPinv"])
+    return sym, A, float(z["tol"]), int(z["ntol"]), num
+
+
+def a_norm(A: sq.Csc) -> float:
+    """||A||_F, the scale of the R tolerance (north_star: 1e-10 scaled by ||A||)."""
+    return float(np.sqrt(np.sum(A.x * A.x))) if A.x.size else 1.0
+
+
+R_TOL = 1e-10   # relative to ||A||_F (BASELINE.json north_star)
+
+
+def assert_numeric_parity(sym, A, got: sq.Numeric, want: sq.Numeric, what=""):
+    bad = structural_equal(got, want, sym)
+    assert not bad, f"{what}: integer outputs differ: {bad}"
+    for f in range(sym.nf):
+        assert packed_front_size(sym, got, f) == packed_front_size(sym, want, f)
+    d = compare_R(sym, got, want, a_norm(A))
+    assert d <= R_TOL, f"{what}: R differs by {d:.3e} * ||A||"
+    return d
+
+
+def reference_flops(sym, num) -> float:
+    """F_alg of SURVEY.md 8(d): sum over live Householder columns of (t-g)(3+4(fn-k-1)),
+    recomputed from the outputs alone (HStair, Hm, Rp, Super)."""
+    fp, fn = front_shapes(sym)
+    tot = 0.0
+    for f in range(sym.nf):
+        st = num.HStair[int(sym.Rp[f]): int(sym.Rp[f]) + int(fn[f])]
+        fm = int(num.Hm[f]); g = 0
+        for k in range(int(fn[f])):
+            if g >= fm:
+                break
+            t = int(st[k])
+            if k < int(fp[f]) and t == 0:
+                continue
+            tot += (t - g) * (3 + 4 * (int(fn[f]) - k - 1))
+            g += 1
+    return tot

@@ -1,0 +1,68 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/stmqr_b200.h declares, and fails loudly (no CPU fallback) without a GPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import refapi as R
+import stmqr_b200 as sq
+
+HEADER = os.path.join(R.ROOT, "include", "stmqr_b200.h")
+
+
+def declared_symbols():
+    txt = open(HEADER).read()
+    return sorted(set(re.findall(r"\b(stmqr_b200_[a-z0-9_]+)\s*\(", txt)))
+
+
+@pytest.mark.skipif(not os.path.exists(sq.LIB_PATH), reason="libstmqr_b200.so not built")
+def test_library_exports_every_declared_symbol():
+    lib = C.CDLL(sq.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/stmqr_b200.h but not exported"
+    assert set(sq.EXPORTS) == set(syms)
+
+
+@pytest.mark.skipif(not os.path.exists(sq.LIB_PATH), reason="libstmqr_b200.so not built")
+def test_sass_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", sq.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert not re.search(r"sm_(?!100a)\d+", out), out
+
+
+@pytest.mark.skipif(not os.path.exists(sq.DROPIN_PATH), reason="libstmqr_dropin.so not built")
+def test_dropin_exports_reference_symbol():
+    out = subprocess.run(["nm", "-D", "--defined-only", sq.DROPIN_PATH], capture_output=True, text=True).stdout
+    names = {l.split()[-1] for l in out.splitlines() if l.strip()}
+    assert "qr_factorize" in names                 # STMMQR/include/SparseQR.h:127
+    assert "stmqr_b200_qr_factorize" in names
+    und = subprocess.run(["nm", "-D", "--undefined-only", sq.DROPIN_PATH], capture_output=True, text=True).stdout
+    # host code allocates through the reference's counted allocator and calls the C ABI only
+    assert "SparseCore_malloc" in und and "stmqr_b200_factorize" in und
+    assert "oracle" not in und.lower()
+
+
+@pytest.mark.skipif(not os.path.exists(sq.LIB_PATH), reason="libstmqr_b200.so not built")
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = sq.load_library()
+    assert lib.stmqr_b200_device_count() == 0
+    with pytest.raises(sq.EngineError):
+        sq.Engine(0)
+
+
+def test_product_does_not_reference_oracle():
+    """The product tree must not import / link / call anything under oracle/."""
+    pkg = R.PKG
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".c", ".h", ".py", ".sh")):
+                txt = open(os.path.join(root, f), errors="ignore").read()
+                assert "stmqr_oracle" not in txt and "libref_harness" not in txt, os.path.join(root, f)

