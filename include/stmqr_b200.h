@@ -119,6 +119,12 @@ typedef struct
     int64_t nlevels ;
     int64_t nf_small, nf_big ;       /* fronts that took the fused shared-memory / tiled path    */
     int64_t device_bytes ;           /* device memory held by the handle                         */
+    /* per kernel class (only filled when options.profile_phases = 1: CUDA events around every
+     * launch on the engine's stream).  Classes: 0 build_S, 1 front_setup, 2 assemble, 3 panel,
+     * 4 update (WY trailing update), 5 finish+alloc, 6 pack, 7 hpinv+misc */
+    double  ms_class [8] ;
+    int64_t launches_class [8] ;
+    double  update_flops ;           /* algorithmic flops of the trailing updates: 4*mr*nv*ncols  */
 } stmqr_stats ;
 
 /* Blocking parameters: the reference keeps them in mutable globals set by
@@ -165,6 +171,11 @@ int  stmqr_b200_factorize (stmqr_handle h, const stmqr_csc_view *A, double tol, 
                            stmqr_numeric_info *info) ;
 
 int  stmqr_b200_get_stats (stmqr_handle h, stmqr_stats *out) ;
+
+/* FP64 peak microbenchmarks on the handle's device, used as roofline denominators (the driver's
+ * MEASURED_PEAKS.json has no FP64 figure): register-resident DMMA (mma.sync f64) and DFMA loops,
+ * one CTA set per SM, timed with CUDA events.  TFLOP/s. */
+int  stmqr_b200_measure_fp64_peak (stmqr_handle h, double *dmma_tflops, double *dfma_tflops) ;
 const char *stmqr_b200_last_error (stmqr_handle h) ;
 
 /* Debug / parity taps used by the tests: copy one front's assembled F (before the QR) or

@@ -325,3 +325,29 @@ double rh_check_error (void *ccv, void *Av, void *QRv)
     free (x) ; free (b) ; free (y) ; free (xs) ;
     return res ;
 }
+
+/* ---- numeric refactorization on an existing symbolic object ------------------------------- */
+/* Calls qr_factorize (the interposed one above -> selected backend) exactly as SparseQR.c:349
+ * does (&A, FALSE, tol, n, QRsym, cc), replaces QR->QRnum by the result and returns the seconds
+ * spent inside the call (the reference's Fac_time interval).  Only for factorizations without
+ * singletons (QR->n1cols == 0).  pool > 0: a TPSM pool of that many workers is alive around the
+ * call, as the reference driver arranges (qrtest.c:150,193); its creation is not timed. */
+double rh_refactorize (void *ccv, void *Av, void *QRv, int pool)
+{
+    sparse_common *cc = (sparse_common *) ccv ;
+    sparse_csc *A = (sparse_csc *) Av ;
+    SparseQR_factorization *QR = (SparseQR_factorization *) QRv ;
+    if (QR->n1cols != 0) return -1 ;
+    if (QR->QRnum) qr_freenum (&QR->QRnum, cc) ;
+    cc->status = SPARSE_OK ;
+    if (pool > 0) TPSM_init (pool, 2000, 3000, TPSM_NODE_AFFINITY) ;
+    chunk_getSettings (32, 5000, 4, 4) ;
+    if (cc->QR_CHUNK_FLAG) { FCHUNK = 80 ; SMALL = 8000 ; }     /* as qr_analyze left it (:666-670) */
+    double t0 = now_s () ;
+    QR->QRnum = qr_factorize (&A, FALSE, QR->tol, A->ncol, QR->QRsym, cc) ;
+    double t = now_s () - t0 ;
+    if (pool > 0) TPSM_destroy (TPSM_SHUTDOWN_GENTLY) ;
+    if (!QR->QRnum) return -2 ;
+    QR->rank = QR->n1rows + QR->QRnum->rank1 ;
+    return t ;
+}

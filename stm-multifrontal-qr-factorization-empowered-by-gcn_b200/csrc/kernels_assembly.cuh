@@ -225,6 +225,24 @@ __global__ void k_front_finish (const I32 *__restrict__ fronts, DSym S, DNum N)
         N.Cm [f] = cm ;
         N.Hr [f] = (fm > 0) ? rm : 0 ;
         N.rsize [f] = rsize ;
+        {
+            // algorithmic bytes of assembly + pack for this front
+            const I32 col1 = S.Super [f] ;
+            double csz_children = 0, ids = fm ;
+            for (I32 q = S.Childp [f] ; q < S.Childp [f+1] ; q++)
+            {
+                const I32 c = S.Child [q] ;
+                const double cmc = N.Cm [c] ;
+                const double cnc = (S.Rp [c+1] - S.Rp [c]) - (S.Super [c+1] - S.Super [c]) ;
+                csz_children += cmc * (cmc + 1) / 2 + cmc * (cnc - cmc) ;
+                ids += cmc + cnc ;
+            }
+            const double snz = (double) (S.Sp [S.Sleft [col1+fp]] - S.Sp [S.Sleft [col1]]) ;
+            const double csz = (double) cm * (cm + 1) / 2 + (double) cm * (cn - cm) ;
+            const double b = 8.0 * (2.0 * (double) fm * fn + csz_children + (double) rsize + csz)
+                + 16.0 * snz + 8.0 * ids ;
+            atomicAdd (N.flops + 2, b) ;
+        }
         atomicAdd (N.sumrank, rank) ;
         atomicMax (N.maxfrank, rank) ;
     }

@@ -207,6 +207,8 @@ __global__ void __launch_bounds__ (1024) k_panel (LevelArgs L, DSym S, DNum N, I
         N.pnl_tend [slot] = (nv > 0) ? tq [nv-1] : g1 ;
         if (out_of_rows) N.done [slot] = 1 ;
         if (flops != 0) atomicAdd (N.flops, flops) ;
+        if (nv > 0 && k2 < fn)
+            atomicAdd (N.flops + 1, 4.0 * (double) (tq [nv-1] - g1) * (double) nv * (double) (fn - k2)) ;
     }
 }
 

@@ -17,6 +17,7 @@
 #include "../../include/stmqr_b200.h"
 #include "kernels_assembly.cuh"
 #include "kernels_front.cuh"
+#include "kernels_peak.cuh"
 
 using namespace stmqr ;
 
@@ -78,6 +79,10 @@ struct stmqr_handle_s
     stmqr_numeric_info info {} ;
     stmqr_stats stats {} ;
     I64 launches = 0 ;
+    // optional per-launch profiling (options.profile_phases)
+    std::vector<cudaEvent_t> evpool ;
+    std::vector<int> evclass ;
+    size_t evused = 0 ;
 } ;
 
 namespace {
@@ -143,6 +148,27 @@ bool narrow (const int64_t *src, I64 count, std::vector<I32> &dst)
     return true ;
 }
 
+inline void prof_begin (stmqr_handle h, int cls)
+{
+    if (!h->opt.profile_phases) return ;
+    if (h->evused + 2 > h->evpool.size ())
+    {
+        cudaEvent_t a, b ;
+        cudaEventCreate (&a) ; cudaEventCreate (&b) ;
+        h->evpool.push_back (a) ; h->evpool.push_back (b) ;
+    }
+    cudaEventRecord (h->evpool [h->evused], h->stream) ;
+    h->evclass.push_back (cls) ;
+}
+inline void prof_end (stmqr_handle h)
+{
+    h->launches++ ;
+    if (!h->opt.profile_phases) return ;
+    cudaEventRecord (h->evpool [h->evused + 1], h->stream) ;
+    h->evused += 2 ;
+}
+#define LAUNCH(cls, ...) do { prof_begin (h, cls) ; __VA_ARGS__ ; prof_end (h) ; } while (0)
+
 inline int grid_for (I64 n, int block, int cap = 148 * 16)
 {
     I64 g = (n + block - 1) / block ;
@@ -195,6 +221,7 @@ void stmqr_b200_destroy (stmqr_handle h)
     if (h->ev1) cudaEventDestroy (h->ev1) ;
     if (h->ev2) cudaEventDestroy (h->ev2) ;
     if (h->ev3) cudaEventDestroy (h->ev3) ;
+    for (cudaEvent_t e : h->evpool) cudaEventDestroy (e) ;
     if (h->stream) cudaStreamDestroy (h->stream) ;
     delete h ;
 }
@@ -409,7 +436,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     ALLOC (N.pnl_cols, (I64) h->maxLevelWidth * PANEL_MAX) ;
     ALLOC (N.rcursor, 1) ;
     ALLOC (N.sumrank, 4) ; N.maxfrank = N.sumrank + 1 ; N.maxfm = N.sumrank + 2 ; N.rank1 = N.sumrank + 3 ;
-    ALLOC (N.flops, 1) ;
+    ALLOC (N.flops, 4) ;
     ALLOC (N.W, m) ;
     ALLOC (N.base1, nf) ; ALLOC (N.base2, nf) ;
     ALLOC (h->d_err, 1) ;
@@ -481,23 +508,22 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
     CK (cudaMemsetAsync (N.Rdead, 0, std::max<I64> (h->n, 1), st)) ;
     CK (cudaMemsetAsync (N.rcursor, 0, sizeof (unsigned long long), st)) ;
     CK (cudaMemsetAsync (N.sumrank, 0, 4 * sizeof (I32), st)) ;
-    CK (cudaMemsetAsync (N.flops, 0, sizeof (double), st)) ;
+    CK (cudaMemsetAsync (N.flops, 0, 4 * sizeof (double), st)) ;
+    h->evused = 0 ; h->evclass.clear () ;
     CK (cudaMemsetAsync (h->d_err, 0, sizeof (I32), st)) ;
     CK (cudaMemsetAsync (N.HTau, 0, std::max<I64> (h->rjsize, 1) * sizeof (double), st)) ;
 
     if (h->anz > 0)
     {
-        k_build_S<<<grid_for (h->n * 32, 256), 256, 0, st>>> ((I32) h->n, h->d_Ap, h->d_Ai, h->d_Ax, S, N.Sx, h->d_err) ;
-        h->launches++ ;
+        LAUNCH (0, k_build_S<<<grid_for (h->n * 32, 256), 256, 0, st>>> ((I32) h->n, h->d_Ap, h->d_Ai, h->d_Ax, S, N.Sx, h->d_err)) ;
     }
 
     for (const Level &Lv : h->levels)
     {
         const I32 *fr = h->d_levelFronts + Lv.first ;
-        k_front_setup<<<Lv.count, 128, 0, st>>> (fr, S, N) ;
+        LAUNCH (1, k_front_setup<<<Lv.count, 128, 0, st>>> (fr, S, N)) ;
         int nsl = (int) std::min<I64> (148, std::max<I64> (1, Lv.maxFelems / 8192)) ;
-        k_assemble<<<dim3 (Lv.count, nsl), 256, 0, st>>> (fr, S, N) ;
-        h->launches += 2 ;
+        LAUNCH (2, k_assemble<<<dim3 (Lv.count, nsl), 256, 0, st>>> (fr, S, N)) ;
         if (h->debug_capture)
         {
             CK (cudaStreamSynchronize (st)) ;
@@ -525,8 +551,7 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
             }
             const I32 active = lo ;
             if (active == 0) break ;
-            k_panel<<<active, pthreads, 0, st>>> (L, S, N, k1, PB) ;
-            h->launches++ ;
+            LAUNCH (3, k_panel<<<active, pthreads, 0, st>>> (L, S, N, k1, PB)) ;
             const I32 k2 = k1 + PB ;
             if (k2 < Lv.maxfn)
             {
@@ -540,8 +565,7 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
                 if (lo2 > 0)
                 {
                     const int tiles = (Lv.maxfn - k2 + UPD_TB - 1) / UPD_TB ;
-                    k_update<<<dim3 (lo2, tiles), 256, 0, st>>> (L, S, N, k2) ;
-                    h->launches++ ;
+                    LAUNCH (4, k_update<<<dim3 (lo2, tiles), 256, 0, st>>> (L, S, N, k2)) ;
                 }
             }
         }
@@ -558,36 +582,31 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
                     cnt * sizeof (double), cudaMemcpyDeviceToDevice)) ;
             }
         }
-        k_front_finish<<<Lv.count, 128, 0, st>>> (fr, S, N) ;
-        k_level_alloc<<<1, 1024, 0, st>>> (fr, Lv.count, N) ;
-        k_pack<<<dim3 (Lv.count, nsl), 256, 0, st>>> (fr, S, N) ;
-        h->launches += 3 ;
+        LAUNCH (5, k_front_finish<<<Lv.count, 128, 0, st>>> (fr, S, N)) ;
+        LAUNCH (5, k_level_alloc<<<1, 1024, 0, st>>> (fr, Lv.count, N)) ;
+        LAUNCH (6, k_pack<<<dim3 (Lv.count, nsl), 256, 0, st>>> (fr, S, N)) ;
     }
 
     // qr_hpinv (:991-1060)
     if (h->nf > 0)
     {
-        k_hpinv_counts<<<grid_for (h->nf, 256, 1 << 20), 256, 0, st>>> (S, N) ;
-        k_scan_i64<<<1, 1024, 0, st>>> (N.base1, N.base2, (I32) h->nf) ;
-        k_hpinv_rows<<<grid_for (h->nf * 32, 256, 1 << 22), 256, 0, st>>> (S, N) ;
-        h->launches += 3 ;
+        LAUNCH (7, k_hpinv_counts<<<grid_for (h->nf, 256, 1 << 20), 256, 0, st>>> (S, N)) ;
+        LAUNCH (7, k_scan_i64<<<1, 1024, 0, st>>> (N.base1, N.base2, (I32) h->nf)) ;
+        LAUNCH (7, k_hpinv_rows<<<grid_for (h->nf * 32, 256, 1 << 22), 256, 0, st>>> (S, N)) ;
     }
     {
-        I64 nempty = 0 ;    // rows Sleft[n]..m-1; count is symbolic but lives on the device: launch by bound
-        (void) nempty ;
-        k_hpinv_empty<<<grid_for (std::max<I64> (h->m, 1), 256, 1 << 22), 256, 0, st>>> (S, N) ;
-        k_hpinv_apply<<<grid_for (std::max<I64> (std::max (h->m, h->nf * 32), 1), 256), 256, 0, st>>> (S, N, h->d_HPinv64, h->d_Hii64) ;
+        LAUNCH (7, k_hpinv_empty<<<grid_for (std::max<I64> (h->m, 1), 256, 1 << 22), 256, 0, st>>> (S, N)) ;
+        LAUNCH (7, k_hpinv_apply<<<grid_for (std::max<I64> (std::max (h->m, h->nf * 32), 1), 256), 256, 0, st>>> (S, N, h->d_HPinv64, h->d_Hii64)) ;
         const I64 nt = std::min<I64> (std::max<I64> (ntol, 0), h->n) ;
-        if (nt > 0) { k_rank1<<<(unsigned) ((nt + 255) / 256), 256, 0, st>>> (N.Rdead, nt, N.rank1) ; h->launches++ ; }
-        h->launches += 2 ;
+        if (nt > 0) LAUNCH (7, k_rank1<<<(unsigned) ((nt + 255) / 256), 256, 0, st>>> (N.Rdead, nt, N.rank1)) ;
     }
     CK (cudaEventRecord (h->ev1, st)) ;
 
     // scalars back
-    unsigned long long rcur = 0 ; I32 sc [4] = {0, 0, 0, 0} ; double fl = 0 ; I32 err = 0 ;
+    unsigned long long rcur = 0 ; I32 sc [4] = {0, 0, 0, 0} ; double fl3 [4] = {0, 0, 0, 0} ; I32 err = 0 ;
     CK (cudaMemcpyAsync (&rcur, N.rcursor, sizeof (rcur), cudaMemcpyDeviceToHost, st)) ;
     CK (cudaMemcpyAsync (sc, N.sumrank, sizeof (sc), cudaMemcpyDeviceToHost, st)) ;
-    CK (cudaMemcpyAsync (&fl, N.flops, sizeof (fl), cudaMemcpyDeviceToHost, st)) ;
+    CK (cudaMemcpyAsync (fl3, N.flops, sizeof (fl3), cudaMemcpyDeviceToHost, st)) ;
     CK (cudaMemcpyAsync (&err, h->d_err, sizeof (err), cudaMemcpyDeviceToHost, st)) ;
     CK (cudaStreamSynchronize (st)) ;
     CK (cudaGetLastError ()) ;
@@ -596,8 +615,24 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
     float ms = 0 ;
     cudaEventElapsedTime (&ms, h->ev0, h->ev1) ;
     h->stats.ms_numeric = ms ;
+    const double fl = fl3 [0] ;
     h->stats.launches = h->launches ;
     h->stats.flops = fl ;
+    h->stats.update_flops = fl3 [1] ;
+    h->stats.bytes_assemble = fl3 [2] ;
+    for (int c = 0 ; c < 8 ; c++) { h->stats.ms_class [c] = 0 ; h->stats.launches_class [c] = 0 ; }
+    if (h->opt.profile_phases)
+    {
+        for (size_t e = 0 ; e < h->evclass.size () ; e++)
+        {
+            float t = 0 ;
+            cudaEventElapsedTime (&t, h->evpool [2*e], h->evpool [2*e+1]) ;
+            h->stats.ms_class [h->evclass [e]] += t ;
+            h->stats.launches_class [h->evclass [e]] += 1 ;
+        }
+        h->stats.ms_assemble = h->stats.ms_class [1] + h->stats.ms_class [2] + h->stats.ms_class [5] + h->stats.ms_class [6] ;
+        h->stats.ms_front = h->stats.ms_class [3] + h->stats.ms_class [4] ;
+    }
     h->info.rank = sc [0] ;
     h->info.maxfrank = std::max<I32> (1, sc [1]) ;       // maxfrank starts at 1 (:555)
     h->info.maxfm = sc [2] ;
@@ -660,6 +695,41 @@ int stmqr_b200_get_stats (stmqr_handle h, stmqr_stats *out)
     if (!h || !out) return STMQR_ERR_INVALID ;
     h->stats.device_bytes = (I64) h->device_bytes ;
     *out = h->stats ;
+    return STMQR_OK ;
+}
+
+int stmqr_b200_measure_fp64_peak (stmqr_handle h, double *dmma_tflops, double *dfma_tflops)
+{
+    if (!h) return STMQR_ERR_INVALID ;
+    cudaSetDevice (h->device) ;
+    double *d_out = nullptr ;
+    CK (cudaMalloc ((void **) &d_out, 148 * 8 * 1024 * sizeof (double))) ;
+    const int iters = 4096 ;
+    const int grid = 148 * 4, block = 256 ;
+    double best [3] = {0, 0, 0} ;
+    for (int variant = 0 ; variant < 3 ; variant++)
+    {
+        for (int rep = 0 ; rep < 4 ; rep++)
+        {
+            CK (cudaEventRecord (h->ev0, h->stream)) ;
+            if (variant == 0) k_peak_dmma884<<<grid, block, 0, h->stream>>> (d_out, iters) ;
+            else if (variant == 1) k_peak_dmma16816<<<grid, block, 0, h->stream>>> (d_out, iters) ;
+            else k_peak_dfma<<<grid, block, 0, h->stream>>> (d_out, iters) ;
+            CK (cudaEventRecord (h->ev1, h->stream)) ;
+            CK (cudaStreamSynchronize (h->stream)) ;
+            float ms = 0 ;
+            cudaEventElapsedTime (&ms, h->ev0, h->ev1) ;
+            const double warps = (double) grid * block / 32 ;
+            double fl ;
+            if (variant == 0) fl = warps * iters * 8.0 * 512.0 ;          // 8 independent m8n8k4
+            else if (variant == 1) fl = warps * iters * 4.0 * 4096.0 ;    // 4 independent m16n8k16
+            else fl = (double) grid * block * iters * 16.0 * 2.0 ;        // 16 independent DFMA
+            if (rep > 0) best [variant] = std::max (best [variant], fl / (ms * 1e-3) * 1e-12) ;
+        }
+    }
+    cudaFree (d_out) ;
+    if (dmma_tflops) *dmma_tflops = std::max (best [0], best [1]) ;
+    if (dfma_tflops) *dfma_tflops = best [2] ;
     return STMQR_OK ;
 }
 

@@ -67,7 +67,11 @@ class Stats(C.Structure):
                 ("ms_d2h", C.c_double), ("ms_assemble", C.c_double), ("ms_front", C.c_double),
                 ("bytes_assemble", C.c_double), ("flops", C.c_double),
                 ("launches", C.c_int64), ("nlevels", C.c_int64), ("nf_small", C.c_int64),
-                ("nf_big", C.c_int64), ("device_bytes", C.c_int64)]
+                ("nf_big", C.c_int64), ("device_bytes", C.c_int64),
+                ("ms_class", C.c_double * 8), ("launches_class", C.c_int64 * 8), ("update_flops", C.c_double)]
+
+
+KERNEL_CLASSES = ("build_S", "front_setup", "assemble", "panel", "update", "finish_alloc", "pack", "hpinv_misc")
 
 
 class Options(C.Structure):
@@ -79,7 +83,7 @@ EXPORTS = (
     "stmqr_b200_device_count", "stmqr_b200_create", "stmqr_b200_destroy", "stmqr_b200_set_options",
     "stmqr_b200_analyze", "stmqr_b200_upload_matrix", "stmqr_b200_factorize_resident",
     "stmqr_b200_download", "stmqr_b200_factorize", "stmqr_b200_get_stats", "stmqr_b200_last_error",
-    "stmqr_b200_set_debug_capture", "stmqr_b200_get_front",
+    "stmqr_b200_set_debug_capture", "stmqr_b200_get_front", "stmqr_b200_measure_fp64_peak",
 )
 
 _lib = None
@@ -108,6 +112,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.stmqr_b200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     lib.stmqr_b200_last_error.argtypes = [C.c_void_p]
     lib.stmqr_b200_last_error.restype = C.c_char_p
+    lib.stmqr_b200_measure_fp64_peak.argtypes = [C.c_void_p, _f64p, _f64p]
     lib.stmqr_b200_set_debug_capture.argtypes = [C.c_void_p, C.c_int]
     lib.stmqr_b200_get_front.argtypes = [C.c_void_p, C.c_int64, C.c_int, _f64p, C.c_int64, _i64p, _i64p]
     _lib = lib
@@ -277,6 +282,11 @@ class Engine:
         s = Stats()
         self._check(self.lib.stmqr_b200_get_stats(self.h, C.byref(s)), "get_stats")
         return s
+
+    def measure_fp64_peak(self):
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.stmqr_b200_measure_fp64_peak(self.h, C.byref(a), C.byref(b)), "measure_fp64_peak")
+        return a.value, b.value
 
     def set_debug_capture(self, on=True):
         self._check(self.lib.stmqr_b200_set_debug_capture(self.h, int(on)), "set_debug_capture")

@@ -144,6 +144,8 @@ class Reference:
             L.rh_set_tap.argtypes = [C.c_int]
             L.rh_last_fac_seconds.restype = C.c_double
             L.rh_set_blas_threads.argtypes = [C.c_int]
+            L.rh_refactorize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+            L.rh_refactorize.restype = C.c_double
             cls._lib = L
         return cls._lib
 
@@ -207,6 +209,14 @@ class Reference:
         if not QR:
             raise RuntimeError(f"SparseQR failed, cc->status = {self.L.rh_status(self.cc)}")
         return C.c_void_p(QR)
+
+    def refactorize(self, A, QR, pool: int = 0, blas_threads: int = 1) -> float:
+        """seconds inside one qr_factorize call (selected backend) on QR's symbolic object"""
+        self.L.rh_set_blas_threads(blas_threads)
+        t = float(self.L.rh_refactorize(self.cc, A, QR, pool))
+        if t < 0:
+            raise RuntimeError(f"rh_refactorize failed ({t}), cc->status = {self.L.rh_status(self.cc)}")
+        return t
 
     def free_qr(self, QR):
         self.L.rh_free_qr(self.cc, QR)
