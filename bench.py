@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- numeric multifrontal-QR factorization throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--workload lap2d_1024] [--impl reference]
+
+A "step" is ONE numeric factorization (the reference's qr_factorize, SparseQR_factorize.c:222)
+of the workload matrix.  Default workload = BASELINE.json configs[1]: 2-D 5-point Laplacian on a
+1024x1024 grid (1 048 576 unknowns), METIS ordering, default tolerance.
+
+What is measured (one JSON line, printed by rank 0):
+  value   FP64 GFLOP/s of the numeric factorization with A already resident in HBM
+          (stmqr_b200_factorize_resident; CUDA events on the engine's stream; flops = the
+          reference's own FLOP_COUNT, SparseQR_factorize.c:1571, computed on the device and
+          equal to the count recomputed from HStair).
+  e2e     the same metric through the reference-facing plug-in: the reference's SparseQR
+          machinery calls qr_factorize (our drop-in, host/qr_factorize_b200.c) with a HOST
+          sparse_csc and gets a HOST qr_numeric back (H2D of A and D2H of R+H inside the timed
+          region, wall clock around the call = the reference's Fac_time interval).
+  roofline  the dominant kernel class of the step, from CUDA events around every launch
+          (options.profile_phases) in extra steps run after the timed region.
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref, compiled from /root/reference) running
+          its own CPU qr_factorize on the same matrix and symbolic object, on this box's cores.
+
+The symbolic phase (ordering, etree, fronts; qr_analyze) is the reference's own code, reused
+unchanged as north_star prescribes; it runs once, outside every timed region.  The numeric path
+of the product never touches oracle/: it is libstmqr_b200.so (CUDA) + libstmqr_dropin.so (C).
+`--impl reference` times the reference CPU path alone (rank 0), same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "stm-multifrontal-qr-factorization-empowered-by-gcn_b200")
+sys.path.insert(0, os.path.join(PKG, "py"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "numeric_qr_factorization_fp64_gflops"
+UNIT = "GFLOP/s"
+
+
+# ----------------------------------------------------------------------------------------------
+# workloads (BASELINE.json configs)
+# ----------------------------------------------------------------------------------------------
+def make_workload(name: str):
+    """-> (description, (m, n, Ap, Ai, Ax) or ('mtx', file), ordering_arg)"""
+    from stmqr_b200 import matrices as M
+    if name.startswith("lap2d_"):
+        g = int(name.split("_")[1])
+        return (f"2-D 5-point Laplacian {g}x{g} grid ({g*g} unknowns), METIS", M.laplacian_2d(g), 2)
+    if name.startswith("lap3d_"):
+        g = int(name.split("_")[1])
+        return (f"3-D 7-point Laplacian {g}^3 ({g**3} unknowns), METIS", M.laplacian_3d(g), 2)
+    if name.startswith("tall_"):
+        _, m, n = name.split("_")
+        m, n = int(m), int(n)
+        return (f"banded random tall-sparse {m}x{n} (8 draws/row, halfwidth 64, PCG64 seed 4), COLAMD",
+                M.tall_banded_random(m, n, draws=8, halfwidth=64, seed=4), 1)
+    if name.startswith("mtx:"):            # mtx:<name>:<ordering>
+        _, f, o = name.split(":")
+        return (f"bundled Data/{f}.mtx, ordering arg {o}", ("mtx", f), int(o))
+    raise SystemExit(f"unknown workload {name}")
+
+
+_JSON_FD = 1
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = [nm for k, nm in enumerate(names)
+                   if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+def host_setup(workload: str, backend: str):
+    """Matrix + the reference host library's symbolic analysis (SparseQR -> qr_1colamd ->
+    qr_analyze, reused unchanged).  The first numeric factorization inside SparseQR() goes
+    through `backend` ("b200" drop-in or "reference")."""
+    import refapi as R
+    desc, mat, order = make_workload(workload)
+    ref = R.Reference()
+    if mat[0] == "mtx":
+        A = ref.read_mtx(os.path.join(R.DATA_DIR, mat[1] + ".mtx"))
+    else:
+        m, n, p, i, x = mat
+        A = ref.csc_from_arrays(m, n, p, i, x)
+    tol = ref.default_tol(A)
+    ref.set_backend(backend)
+    t0 = time.time()
+    QR = ref.sparseqr(A, order, tol, grain=1.0, tap=True)
+    t_total = time.time() - t0
+    info = ref.qr_info(QR)
+    return R, ref, A, QR, tol, desc, {"symbolic_plus_first_factorization_s": t_total,
+                                      "first_factorize_s": info["fac_seconds"], "n1cols": info["n1cols"]}
+
+
+def run_reference_arm(args):
+    """The reference's own CPU numeric factorization: qr_factorize of oracle/_ref (compiled
+    from the unmodified sources), every host thread it can use."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import refapi as R
+    cores = os.cpu_count() or 1
+    desc, mat, order = make_workload(args.workload)
+    ref = R.Reference()
+    ref.set_backend("reference")
+    if mat[0] == "mtx":
+        A = ref.read_mtx(os.path.join(R.DATA_DIR, mat[1] + ".mtx"))
+    else:
+        A = ref.csc_from_arrays(*mat)
+    tol = ref.default_tol(A)
+    # two legal ways to use the cores: serial etree x threaded BLAS, or the
+    # reference's TPSM tree tasks (cc->SPQR_grain = 2*cores as qrtest.c:144 sets it; pool sized
+    # above ntasks) x 1 BLAS thread.  Each needs its own symbolic object (the task
+    # partition is made by qr_analyze).  Probe each once, keep the faster for the timed steps.
+    QRs = ref.sparseqr(A, order, tol, grain=1.0, blas_threads=cores)
+    info = ref.qr_info(QRs)
+    if info["n1cols"] != 0:
+        raise SystemExit("reference arm needs a workload without column singletons")
+    flops = info["flopcount"]                      # cc->SPQR_flopcount (counted when grain <= 1)
+    sym = ref.symbolic(QRs)
+    QRt = ref.sparseqr(A, order, tol, grain=2.0 * cores, pool=128, blas_threads=1)
+    modes = {"threaded_blas": (QRs, dict(pool=0, blas_threads=cores)),
+             "tree_tasks": (QRt, dict(pool=128, blas_threads=1))}
+    probe = {k: ref.refactorize(A, q, **kw) for k, (q, kw) in modes.items()}
+    best = min(probe, key=probe.get)
+    q, kw = modes[best]
+    times = []
+    for s in range(args.warmup + args.steps):
+        t = ref.refactorize(A, q, **kw)
+        if s >= args.warmup:
+            times.append(t)
+    sec = float(np.mean(times))
+    val = flops / sec * 1e-9
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc, "m": sym.m, "n": sym.n, "nnz": sym.anz,
+                       "fronts": sym.nf, "flops_per_step": flops},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference",
+                             "sample": f"whole workload, {args.steps} full qr_factorize calls, mode {best} "
+                                       f"(ntasks {int(ref.qr_info(q)['ntasks'])}); probe seconds {probe}"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    emit(line)
+
+
+def run_b200_arm(args):
+    import torch
+    import stmqr_b200 as sq
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 engine has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    os.environ["STMQR_B200_DEVICE"] = str(local)
+    os.environ["STMQR_B200_CACHE_PLAN"] = "1"
+    R, ref, A, QR, tol, desc, setup = host_setup(args.workload, "b200")
+    sym = ref.symbolic(QR)
+    At, ttol, ntol = ref.tapped()
+
+    eng = sq.Engine(local)
+    eng.set_options(panel=args.panel)
+    eng.analyze(sym)
+    eng.upload_matrix(At)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    # ---------------- value: A resident in HBM, device time ----------------------------------
+    for _ in range(args.warmup):
+        info = eng.factorize_resident(ttol, ntol)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    dev_ms = []
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        info = eng.factorize_resident(ttol, ntol)
+        dev_ms.append(eng.stats().ms_numeric)
+    barrier()
+    st = eng.stats()
+    launches = int(st.launches)
+    flops = float(info.flops)
+    t_dev = float(np.sum(dev_ms)) * 1e-3
+    if dist is not None:
+        tt = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev = float(tt.item())
+
+    # ---------------- e2e: host sparse_csc in, host qr_numeric out, through qr_factorize -------
+    e2e_s = []
+    can_e2e = setup["n1cols"] == 0
+    if can_e2e:
+        for s in range(min(args.warmup, 2) + args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t = ref.refactorize(A, QR)
+            if s >= min(args.warmup, 2):
+                e2e_s.append(t)
+    clocks = sampler.stop()
+    t_e2e = float(np.sum(e2e_s)) if e2e_s else None
+    if dist is not None and t_e2e is not None:
+        tt = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_e2e = float(tt.item())
+    rh_bytes = int(info.rh_size) * 8
+    h2d = (sym.n + 1) * 8 + sym.anz * 16
+    d2h = rh_bytes + 8 * (2 * sym.rjsize + sym.hisize + 3 * sym.nf + sym.m) + sym.n
+
+    # ---------------- roofline of the dominant kernel class (extra, untimed steps) ------------
+    eng.set_options(panel=args.panel, profile_phases=1)
+    cls_ms = np.zeros(8)
+    cls_n = np.zeros(8)
+    nprof = max(1, min(args.steps, 3))
+    for _ in range(nprof):
+        flush.zero_()
+        torch.cuda.synchronize()
+        eng.factorize_resident(ttol, ntol)
+        s2 = eng.stats()
+        cls_ms += np.array(list(s2.ms_class))
+        cls_n += np.array(list(s2.launches_class))
+    cls_ms /= nprof
+    cls_n /= nprof
+    s2 = eng.stats()
+    peaks, peak_src = measured_peaks()
+    dmma_tf, dfma_tf = eng.measure_fp64_peak()
+    asm_ms = float(cls_ms[1] + cls_ms[2] + cls_ms[5] + cls_ms[6])
+    front_ms = float(cls_ms[3] + cls_ms[4])
+    classes = dict(zip(sq.KERNEL_CLASSES, [round(float(x), 4) for x in cls_ms]))
+    dom = int(np.argmax(cls_ms))
+    if dom in (3, 4):
+        # front QR: panel + WY update kernels; algorithmic flops = the reference's count
+        ach = flops / (front_ms * 1e-3) * 1e-12
+        roof = {"bound": "tensor", "kernel": "front QR (k_panel + k_update)", "achieved": ach, "peak": dmma_tf,
+                "unit": "TFLOP/s", "frac": ach / dmma_tf if dmma_tf else None, "traffic": None,
+                "peak_source": "FP64 mma.sync (DMMA) register-loop microbenchmark run in this process "
+                               "(stmqr_b200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
+                "avg_launch_ms": front_ms / max(1.0, float(cls_n[3] + cls_n[4]))}
+    else:
+        ach = float(s2.bytes_assemble) / (asm_ms * 1e-3) * 1e-9
+        roof = {"bound": "hbm", "kernel": "assembly+pack (k_front_setup, k_assemble, k_front_finish, k_pack)",
+                "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": asm_ms / max(1.0, float(cls_n[1] + cls_n[2] + cls_n[5] + cls_n[6]))}
+    roof["class_ms"] = classes
+    roof["assembly_gbs"] = float(s2.bytes_assemble) / (asm_ms * 1e-3) * 1e-9 if asm_ms > 0 else None
+    roof["assembly_frac_of_hbm"] = roof["assembly_gbs"] / peaks["hbm_gbs"] if asm_ms > 0 else None
+    roof["front_qr_tflops"] = flops / (front_ms * 1e-3) * 1e-12 if front_ms > 0 else None
+    roof["fp64_dmma_peak_tflops"] = dmma_tf
+    roof["fp64_dfma_peak_tflops"] = dfma_tf
+    eng.set_options(panel=args.panel, profile_phases=0)
+
+    # ---------------- CPU baseline: the reference's own qr_factorize on this box's cores --------
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline and can_e2e:
+        # bounded sample: the whole workload, once per way of using the cores (serial etree x
+        # threaded BLAS on this run's symbolic object; the reference's TPSM tree tasks with
+        # cc->SPQR_grain = 2*cores need their own qr_analyze because it makes the task partition)
+        cores = os.cpu_count() or 1
+        ref.set_backend("reference")
+        probe = {"threaded_blas": ref.refactorize(A, QR, pool=0, blas_threads=cores)}
+        ntasks = 1
+        if not args.no_cpu_tree_tasks:
+            _, _, order = make_workload(args.workload)
+            QRt = ref.sparseqr(A, order, tol, grain=2.0 * cores, pool=128, blas_threads=1)
+            ntasks = int(ref.qr_info(QRt)["ntasks"])
+            probe["tree_tasks"] = min(ref.qr_info(QRt)["fac_seconds"],
+                                      ref.refactorize(A, QRt, pool=128, blas_threads=1))
+            ref.free_qr(QRt)
+        best = min(probe, key=probe.get)
+        cpu = {"value": flops / probe[best] * 1e-9, "unit": UNIT, "cores": cores, "kind": "reference",
+               "seconds": probe[best],
+               "sample": f"whole workload, one qr_factorize call per mode, seconds {probe} "
+                         f"(tree_tasks: ntasks {ntasks}, TPSM pool 128, 1 BLAS thread; threaded_blas: serial "
+                         f"etree, {cores} OpenBLAS threads); best = {best}"}
+        ref.set_backend("b200")
+
+    if rank == 0:
+        total_flops = flops * args.steps * world      # replicas: every rank factorizes the workload
+        line = {"metric": METRIC, "value": total_flops / t_dev * 1e-9, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": args.workload, "description": desc, "m": sym.m, "n": sym.n,
+                           "nnz": sym.anz, "fronts": sym.nf, "etree_levels": int(st.nlevels),
+                           "rank": int(info.rank), "flops_per_step": flops,
+                           "rh_doubles": int(info.rh_size), "tol": ttol,
+                           "l2": "256 MiB device buffer written between timed steps (L2 flush)",
+                           "multi_gpu": "replicas" if world > 1 else "single",
+                           "device_bytes": int(st.device_bytes)},
+                "e2e": ({"value": flops * len(e2e_s) * world / t_e2e * 1e-9, "unit": UNIT,
+                         "ms_per_step": t_e2e / len(e2e_s) * 1e3, "h2d_bytes_per_step": h2d,
+                         "d2h_bytes_per_step": d2h,
+                         "how": "wall clock around qr_factorize (drop-in) called by the reference host "
+                                "library with a host sparse_csc; host qr_numeric out; plan cached "
+                                "(STMQR_B200_CACHE_PLAN=1)",
+                         "first_call_with_plan_s": setup["first_factorize_s"],
+                         "plan_ms": float(st.ms_plan)} if t_e2e else None),
+                "gpu_launches": launches * args.steps,
+                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "stats": {"ms_h2d": float(st.ms_h2d), "ms_d2h": float(st.ms_d2h),
+                          "launches_per_step": launches}}
+        emit(line)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="lap2d_1024")
+    ap.add_argument("--panel", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-tree-tasks", action="store_true",
+                    help="skip the reference's TPSM tree-task mode in the CPU baseline probe")
+    args = ap.parse_args()
+    # the reference library printf()s its own progress on fd 1: keep fd 1 for the ONE JSON line
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

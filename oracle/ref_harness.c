@@ -160,6 +160,21 @@ double rh_default_tol (void *ccv, void *Av)
     return 20 * ((double) A->nrow + (double) A->ncol) * DBL_EPSILON * mx ;
 }
 
+/* The reference's TPSM pool cannot be re-initialised after TPSM_destroy (its distribution tables
+ * are not reset: initializeThreadsDistribution, tpsm_distribution.c:37-38, fails the second
+ * time), so the harness creates it once per process, as the reference driver does
+ * (qrtest.c:150), and leaves it alive; idle workers sleep on a condition variable. */
+static int g_pool_size = 0 ;
+void rh_pool_ensure (int pool)
+{
+    if (g_pool_size == 0)
+    {
+        TPSM_init (pool, 2000, 3000, TPSM_NODE_AFFINITY) ;
+        g_pool_size = pool ;
+    }
+}
+int rh_pool_size (void) { return g_pool_size ; }
+
 /* ---- the reference driver preamble + SparseQR (qrtest.c:144-180) ------------------------- */
 /* ordering_arg: qrtest's third argument (0 AMD, 1 COLAMD, 2 METIS, 3 NESDIS, else DEFAULT).
  * grain <= 1: serial tree (no TPSM tasks).  grain > 1: TPSM pool of `pool` workers. */
@@ -179,13 +194,12 @@ void *rh_sparseqr (void *ccv, void *Av, int ordering_arg, double tol, double gra
     cc->SPQR_grain = grain ;
     cc->status = SPARSE_OK ;
     int pooled = (grain > 1 && pool > 0) ;
-    if (pooled) TPSM_init (pool, 2000, 3000, TPSM_NODE_AFFINITY) ;
+    if (pooled) rh_pool_ensure (pool) ;
     chunk_getSettings (32, 5000, 4, 4) ;
     cc->QR_CHUNK_FLAG = 0 ;
     Relaxfactor_setting (A->ncol, SparseCore_nnz (A, cc), RELAX_FOR_QR, cc) ;
     char name [8] = "rh" ;
     SparseQR_factorization *QR = SparseQR (ordering, tol, A, cc, name) ;
-    if (pooled) TPSM_destroy (TPSM_SHUTDOWN_GENTLY) ;
     return QR ;
 }
 
@@ -340,13 +354,12 @@ double rh_refactorize (void *ccv, void *Av, void *QRv, int pool)
     if (QR->n1cols != 0) return -1 ;
     if (QR->QRnum) qr_freenum (&QR->QRnum, cc) ;
     cc->status = SPARSE_OK ;
-    if (pool > 0) TPSM_init (pool, 2000, 3000, TPSM_NODE_AFFINITY) ;
+    if (pool > 0) rh_pool_ensure (pool) ;
     chunk_getSettings (32, 5000, 4, 4) ;
     if (cc->QR_CHUNK_FLAG) { FCHUNK = 80 ; SMALL = 8000 ; }     /* as qr_analyze left it (:666-670) */
     double t0 = now_s () ;
     QR->QRnum = qr_factorize (&A, FALSE, QR->tol, A->ncol, QR->QRsym, cc) ;
     double t = now_s () - t0 ;
-    if (pool > 0) TPSM_destroy (TPSM_SHUTDOWN_GENTLY) ;
     if (!QR->QRnum) return -2 ;
     QR->rank = QR->n1rows + QR->QRnum->rank1 ;
     return t ;
