@@ -1,0 +1,657 @@
+// kernels_panel.cuh -- panel factorization of the staircase Householder QR (qr_front,
+// SparseQR_factorize.c:1383-1618: the dlarfg / dlarf column loop, plus dlarft for the block
+// reflector of the panel) for all active fronts of one etree level.
+//
+// B200 design: one thread-block CLUSTER per front.  The rows of the panel that can still change
+// (pivot row g .. staircase end of the last panel column) are split into CS contiguous slabs, one
+// per CTA of the cluster, and each CTA keeps its slab (rows x <=32 columns) in shared memory for
+// the whole panel, so the column loop never touches L2/HBM.  Per Householder column there is
+// exactly ONE cluster-wide exchange: every CTA publishes the partial dot products of the current
+// column with all panel columns over its rows (the norm, the dlarf inner products and the
+// V'V entries that dlarft needs, all from the same pass) and the owner of the pivot row publishes
+// that row; every CTA then reads the CS records through distributed shared memory, derives the
+// same beta/tau/dead decision and updates its own rows.  Slabs that do not fit in shared memory
+// (fronts with tens of thousands of rows) run the same code in place on the front (L2 resident).
+//
+// Semantics that must match the reference bit for bit (integer outputs):
+//   t = max (g+1, Stair[k])                                                    :1460
+//   dead pivot (k < ntol, |F(g,k)| <= tol): zero F(g:m-1,k), Stair=0, Tau=0, Rdead=1   :1495-1528
+//   out of rows (g >= m): remaining pivots dead, remaining columns Stair = m   :1444-1458
+//   rank = g sampled after pivot column npiv-1                                 :1604-1608
+// Blocking (panel width, when T is applied) is performance-only.
+#pragma once
+#include <cooperative_groups.h>
+#include "engine.cuh"
+
+namespace stmqr {
+
+namespace cg = cooperative_groups ;
+
+struct LevelArgs
+{
+    const I32 *fronts ;     // fronts of the level, sorted by # columns descending
+    I32 count ;
+    double tol ;
+    I64 ntol ;
+} ;
+
+// what one CTA publishes to its cluster for one Householder column
+struct PanelXch
+{
+    double dot [PANEL_MAX] ;    // sum over my rows in (g,t) of F(i,k) * F(i,c), every panel column c
+    double rowg [PANEL_MAX] ;   // F(g,c), published by the CTA whose slab holds the pivot row g
+    double mx ;                 // max over my rows in (g,t) of |F(i,k)|
+    double ssq2 ;               // rescaled sum of squares (rare under/overflow path)
+} ;
+
+// dlarft for the panel's live reflectors from their V'V entries (Gs), and the panel's outputs for
+// the trailing update (T, live columns, row window), written by the leader CTA of the cluster.
+__device__ __forceinline__ void panel_epilogue (const LevelArgs &L, const DSym &S, const DNum &N,
+    const I32 slot, const I32 f, const I32 k2, const I32 parity, const bool leader, const I32 nv,
+    const I32 g, const I32 g1, const bool out_of_rows, const double flops, double *Gs, double *Tsh,
+    double *taus, I32 *cols, I32 *tq)
+{
+    const int tid = threadIdx.x, nt = blockDim.x ;
+    const int lane = tid & 31, w = tid >> 5 ;
+    const I32 fn = S.Rp [f+1] - S.Rp [f] ;
+    // ---- dlarft: T of the nv live reflectors of this panel (forward, columnwise) --------------
+    const I32 slotp = parity * L.count + slot ;
+    if (leader && nv > 0 && k2 < fn)
+    {
+        for (int e = tid ; e < nv * nv ; e += nt)
+        {
+            const int j = e % nv, i = e / nv ;
+            if (j < i) Tsh [j + i * (PANEL_MAX + 1)] = -taus [i] * Gs [j + i * (PANEL_MAX + 1)] ;
+        }
+        __syncthreads () ;
+        if (w == 0)
+        {
+            for (int i = 0 ; i < nv ; i++)
+            {
+                // T(0:i-1,i) = T(0:i-1,0:i-1) * T(0:i-1,i)
+                double s = 0 ;
+                if (lane < i)
+                {
+                    for (int l = lane ; l < i ; l++)
+                        s += Tsh [lane + l * (PANEL_MAX + 1)] * Tsh [l + i * (PANEL_MAX + 1)] ;
+                }
+                __syncwarp () ;
+                if (lane < i) Tsh [lane + i * (PANEL_MAX + 1)] = s ;
+                if (lane == i) Tsh [i + i * (PANEL_MAX + 1)] = taus [i] ;
+                __syncwarp () ;
+            }
+        }
+        __syncthreads () ;
+        double *Tg = N.Tws + (I64) slotp * (PANEL_MAX * PANEL_MAX) ;
+        for (int e = tid ; e < nv * nv ; e += nt)
+        {
+            const int j = e % nv, i = e / nv ;
+            Tg [j + i * PANEL_MAX] = (j <= i) ? Tsh [j + i * (PANEL_MAX + 1)] : 0.0 ;
+        }
+        for (int q = tid ; q < nv ; q += nt) N.pnl_cols [slotp * PANEL_MAX + q] = cols [q] ;
+    }
+    if (leader && tid == 0)
+    {
+        N.g [slot] = g ;
+        N.pnl_g1 [slotp] = g1 ;
+        N.pnl_nv [slotp] = (k2 < fn) ? nv : 0 ;
+        N.pnl_tend [slotp] = (nv > 0) ? tq [nv-1] : g1 ;
+        if (out_of_rows) N.done [slot] = 1 ;
+        if (flops != 0) atomicAdd (N.flops, flops) ;
+        if (nv > 0 && k2 < fn)
+            atomicAdd (N.flops + 1, 4.0 * (double) (tq [nv-1] - g1) * (double) nv * (double) (fn - k2)) ;
+    }
+}
+
+// Row-per-lane mapping (one warp per panel column): used in place on the front (global memory,
+// coalesced along the rows) when the row slabs do not fit in shared memory.
+template <bool INSMEM>
+__device__ __forceinline__ void panel_columns (cg::cluster_group &cluster, double *__restrict__ P,
+    const I64 ldp, const LevelArgs &L, const DSym &S, const DNum &N, const I32 slot, const I32 f,
+    const I32 k1, const I32 k2, const I32 parity, const I32 lrow0, const I32 nloc, const I32 rbeg,
+    const I32 RL, const I32 rend, PanelXch *xch, double *tot, double *rg, double *Gs, double *Tsh,
+    double *taus, I32 *cols, I32 *tq)
+{
+    const unsigned CS = cluster.num_blocks (), cr = cluster.block_rank () ;
+    const int tid = threadIdx.x, nt = blockDim.x ;
+    const int lane = tid & 31, w = tid >> 5, nw = nt >> 5 ;
+    const I32 col1 = S.Super [f], fp = S.Super [f+1] - col1 ;
+    const I32 p1 = S.Rp [f], fn = S.Rp [f+1] - p1 ;
+    const I32 fm = N.Hm [f] ;
+    const I64 ld = fm ;
+    double *F = N.F + S.Foff [f] ;
+    I32 *st = N.stair + p1 ;
+    double *Tau = N.HTau + p1 ;
+    char *Rdead = N.Rdead + col1 ;
+    const I32 ntol = (I32) max ((I64) 0, min (L.ntol - (I64) col1, (I64) fp)) ;
+    const double tol = L.tol ;
+    const I32 np = k2 - k1 ;
+    const bool leader = (cr == 0) ;
+
+    I32 g = rbeg ;                  // the panel starts at the front's current pivot row
+    const I32 g1 = g ;
+    I32 nv = 0 ;
+    double flops = 0 ;
+    bool out_of_rows = false ;
+    int step = 0 ;
+
+    for (I32 k = k1 ; k < k2 ; k++)
+    {
+        if (g >= fm)
+        {
+            // no rows left: qr_front early exit (:1444-1458) for ALL remaining columns
+            if (leader)
+            {
+                for (I32 kk = k + tid ; kk < fn ; kk += nt)
+                {
+                    if (kk < fp) { Rdead [kk] = 1 ; st [kk] = 0 ; }
+                    else st [kk] = fm ;
+                    Tau [kk] = 0 ;
+                }
+            }
+            out_of_rows = true ;
+            break ;
+        }
+        const I32 c = k - k1 ;
+        const I32 t = max (g + 1, st [k]) ;
+        // my rows strictly below the pivot row and inside the staircase: local [i0,i1)
+        const I32 i0 = max (g + 1, lrow0) - lrow0 ;
+        const I32 i1 = min (min (t, rend), lrow0 + nloc) - lrow0 ;
+        const unsigned owner = (unsigned) ((g - rbeg) / RL) ;
+        const I32 gi = g - lrow0 ;
+        PanelXch &X = xch [step & 1] ;
+        step++ ;
+
+        // ---- one pass: dot products of column k with every panel column over my rows ----------
+        const double *xc = P + (I64) c * ldp ;
+        for (I32 cc = w ; cc < np ; cc += nw)
+        {
+            const double *yc = P + (I64) cc * ldp ;
+            double s = 0, mx = 0 ;
+            for (I32 i = i0 + lane ; i < i1 ; i += 32)
+            {
+                const double xv = xc [i] ;
+                s += xv * yc [i] ;
+                mx = fmax (mx, fabs (xv)) ;
+            }
+            s = warp_sum (s) ;
+            if (cc == c) mx = warp_max (mx) ;
+            if (lane == 0)
+            {
+                X.dot [cc] = s ;
+                X.rowg [cc] = (cr == owner) ? yc [gi] : 0.0 ;
+                if (cc == c) X.mx = mx ;
+            }
+        }
+        cluster.sync () ;
+        // ---- gather the CS records (same order in every CTA: bitwise identical decisions) -----
+        if (tid < np)
+        {
+            double s = 0 ;
+            for (unsigned r = 0 ; r < CS ; r++) s += cluster.map_shared_rank (&X, r)->dot [tid] ;
+            tot [tid] = s ;
+            rg [tid] = cluster.map_shared_rank (&X, owner)->rowg [tid] ;
+        }
+        else if (tid == PANEL_MAX)
+        {
+            double mx = 0 ;
+            for (unsigned r = 0 ; r < CS ; r++) mx = fmax (mx, cluster.map_shared_rank (&X, r)->mx) ;
+            tot [PANEL_MAX] = mx ;
+        }
+        __syncthreads () ;
+        double ss = tot [c], mx = tot [PANEL_MAX] ;
+        const double alpha = rg [c] ;
+        if (mx > 0 && !(ss > 1e-280 && ss < 1e280))
+        {
+            // rare: rescale to avoid under/overflow of the sum of squares (dnrm2 semantics);
+            // the decision is uniform over the cluster, so one more exchange is safe
+            const double inv = 1.0 / mx ;
+            double s2 = 0 ;
+            for (I32 i = i0 + tid ; i < i1 ; i += nt) { const double v = xc [i] * inv ; s2 += v * v ; }
+            double dummy = 0 ;
+            block_sum_max (s2, dummy, tot + PANEL_MAX + 2) ;
+            if (tid == 0) X.ssq2 = s2 ;
+            cluster.sync () ;
+            s2 = 0 ;
+            for (unsigned r = 0 ; r < CS ; r++) s2 += cluster.map_shared_rank (&X, r)->ssq2 ;
+            cluster.sync () ;                // X is reused two steps later: keep the step parity
+            ss = s2 ;
+        }
+        else mx = 1.0 ;
+        const double xnorm = mx * sqrt (ss) ;
+        double beta = alpha, tau = 0, scale = 0 ;
+        if (t - g > 1 && xnorm != 0)
+        {
+            beta = -copysign (hypot (alpha, xnorm), alpha) ;
+            tau = (beta - alpha) / beta ;
+            scale = 1.0 / (alpha - beta) ;
+        }
+        const bool dead = (k < ntol) && (fabs (beta) <= tol) ;
+
+        if (dead)
+        {
+            // zero F(g:m-1,k): my rows, and (leader) whatever lies below the panel's row window
+            double *xw = P + (I64) c * ldp ;
+            for (I32 i = max (g, lrow0) - lrow0 + tid ; i < nloc ; i += nt) xw [i] = 0.0 ;
+            if (leader)
+            {
+                double *xg = F + (I64) k * ld ;
+                for (I32 i = rend + tid ; i < fm ; i += nt) xg [i] = 0.0 ;
+                if (tid == 0) { st [k] = 0 ; Tau [k] = 0 ; Rdead [k] = 1 ; }
+            }
+        }
+        else
+        {
+            // ---- dlarf: apply H_k to the remaining columns of the panel (my rows) -------------
+            if (tau != 0)
+            {
+                for (I32 cc = c + 1 + w ; cc < np ; cc += nw)
+                {
+                    double *yc = P + (I64) cc * ldp ;
+                    const double wv = tau * (rg [cc] + scale * tot [cc]) ;
+                    const double fct = scale * wv ;
+                    for (I32 i = i0 + lane ; i < i1 ; i += 32) yc [i] -= xc [i] * fct ;
+                    if (cr == owner && lane == 0) yc [gi] -= wv ;
+                }
+            }
+            // V'V entries for dlarft: v_j' v_k = scale * (v_j' x) + v_j (g), j an earlier reflector
+            if (tid < nv) Gs [tid + nv * (PANEL_MAX + 1)] = scale * tot [cols [tid] - k1] + rg [cols [tid] - k1] ;
+            __syncthreads () ;
+            // ---- finish column k: v = x * scale below the diagonal, beta on it ------------------
+            double *xw = P + (I64) c * ldp ;
+            if (tau != 0) for (I32 i = i0 + tid ; i < i1 ; i += nt) xw [i] *= scale ;
+            if (cr == owner && tid == 0) xw [gi] = beta ;
+            if (tid == 0)
+            {
+                if (leader) { Tau [k] = tau ; st [k] = t ; }
+                cols [nv] = k ; tq [nv] = t ; taus [nv] = tau ;
+            }
+            flops += (double) (t - g) * (3.0 + 4.0 * (double) (fn - k - 1)) ;
+            nv++ ;
+            g++ ;
+        }
+        if (k == fp - 1 && leader && tid == 0) N.rank [f] = g ;
+        __syncthreads () ;
+    }
+
+    panel_epilogue (L, S, N, slot, f, k2, parity, leader, nv, g, g1, out_of_rows, flops, Gs, Tsh, taus, cols, tq) ;
+}
+
+// Column-per-lane mapping for a slab in shared memory: lane = panel column, warp w owns the slab
+// rows i = w (mod NW).  A row is only ever written by its owner warp, so the whole column step
+// (partial dots -> one block barrier -> [cluster exchange] -> rank-1 update + scaling of the owned
+// rows) needs ONE __syncthreads; the per-step records are double buffered by step parity.
+// ldp is odd: the 32 lanes of a warp hit 32 distinct 8-byte banks.  Nothing in the column loop
+// touches global memory: the staircase of the panel's columns is staged in shared memory and the
+// per-column outputs (Stair, Tau, Rdead) are written once at the end.
+constexpr int PANEL_NW_MAX = 16 ;       // 512 threads
+
+// per-CTA scratch carved from dynamic shared memory after the slab (sized by the # of warps)
+__host__ __device__ constexpr int panel_scratch_doubles (int nw)
+{
+    return 2 * nw * PANEL_MAX           // part [2][nw][32]  per-warp partial dots of the current column
+        + 2 * PANEL_MAX                 // prow [2][32]      the pivot row, published by its owner warp
+        + 2 * nw                        // red  [2][nw]      block reductions of the rescale path
+        + PANEL_MAX * (PANEL_MAX + 1)   // Gs   [32][33]     V'V, then T in place (dlarft)
+        + 4 * PANEL_MAX ;               // taus, stair in, stair out, flags (as doubles/ints)
+}
+
+// all-reduce of one double over the CTA's warps and then over the cluster (rare rescale path)
+template <int NW, bool ISMAX>
+__device__ __forceinline__ double panel_allreduce (cg::cluster_group &cluster, const unsigned ECS, double v,
+    double *red, PanelXch &X)
+{
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5 ;
+    if (lane == 0) red [w] = v ;
+    __syncthreads () ;
+    v = red [0] ;
+#pragma unroll
+    for (int ww = 1 ; ww < NW ; ww++) v = ISMAX ? fmax (v, red [ww]) : (v + red [ww]) ;
+    __syncthreads () ;
+    if (ECS > 1)
+    {
+        if (tid == 0) X.ssq2 = v ;
+        cluster.sync () ;
+        v = cluster.map_shared_rank (&X, 0)->ssq2 ;
+        for (unsigned r = 1 ; r < ECS ; r++)
+        {
+            const double u = cluster.map_shared_rank (&X, r)->ssq2 ;
+            v = ISMAX ? fmax (v, u) : (v + u) ;
+        }
+        cluster.sync () ;
+    }
+    return v ;
+}
+
+template <int NW>
+__device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, const unsigned ECS,
+    const I32 slab_cap, const I32 ldp, const LevelArgs &L, const DSym &S, const DNum &N,
+    const I32 slot, const I32 f, const I32 k1, const I32 k2, const I32 parity, const I32 lrow0,
+    const I32 nloc, const I32 rbeg, const I32 RL, const I32 rend, PanelXch *xch, I32 *cols, I32 *tq)
+{
+    extern __shared__ double slab [] ;
+    double *const P = slab ;
+    double *const part = slab + slab_cap ;
+    double *const prow = part + 2 * NW * PANEL_MAX ;
+    double *const red = prow + 2 * PANEL_MAX ;
+    double *const Gs = red + 2 * NW ;
+    double *const taus = Gs + PANEL_MAX * (PANEL_MAX + 1) ;
+    I32 *const stl = (I32 *) (taus + PANEL_MAX) ;       // [32] staircase of the panel's columns (in)
+    I32 *const sto = stl + PANEL_MAX ;                  // [32] new Stair, -1 = column not processed
+    double *const tauo = taus + 2 * PANEL_MAX ;         // [32] Tau out
+
+    const unsigned cr = (ECS > 1) ? cluster.block_rank () : 0 ;
+    const int tid = threadIdx.x ;
+    constexpr int nt = NW * 32 ;
+    const int lane = tid & 31, w = tid >> 5 ;
+    const I32 col1 = S.Super [f], fp = S.Super [f+1] - col1 ;
+    const I32 p1 = S.Rp [f], fn = S.Rp [f+1] - p1 ;
+    const I32 fm = N.Hm [f] ;
+    const I64 ld = fm ;
+    double *F = N.F + S.Foff [f] ;
+    I32 *st = N.stair + p1 ;
+    double *Tau = N.HTau + p1 ;
+    char *Rdead = N.Rdead + col1 ;
+    const I32 ntol = (I32) max ((I64) 0, min (L.ntol - (I64) col1, (I64) fp)) ;
+    const double tol = L.tol ;
+    const I32 np = k2 - k1 ;
+    const bool leader = (cr == 0) ;
+    const bool mycol = (lane < np) ;
+    double *yc = P + (I64) (mycol ? lane : 0) * ldp ;       // my column of the slab
+
+    if (tid < PANEL_MAX)
+    {
+        stl [tid] = (tid < np) ? st [k1 + tid] : 0 ;
+        sto [tid] = -1 ;
+    }
+    __syncthreads () ;
+
+    I32 g = rbeg ;
+    const I32 g1 = g ;
+    I32 nv = 0 ;
+    I32 myq = -1 ;                  // index of my column among the live reflectors of this panel
+    double flops = 0 ;
+    bool out_of_rows = false ;
+    int step = 0 ;
+    I32 kstop = k2 ;
+
+    for (I32 k = k1 ; k < k2 ; k++)
+    {
+        if (g >= fm) { out_of_rows = true ; kstop = k ; break ; }
+        const I32 c = k - k1 ;
+        const I32 t = max (g + 1, stl [c]) ;
+        // slab rows strictly below the pivot row and inside the staircase: local [i0,i1)
+        const I32 i0 = max (g + 1, lrow0) - lrow0 ;
+        const I32 i1 = min (min (t, rend), lrow0 + nloc) - lrow0 ;
+        const unsigned owner = (ECS > 1) ? (unsigned) ((g - rbeg) / RL) : 0u ;
+        const I32 gi = g - lrow0 ;
+        const bool own_g = (cr == owner) && ((gi & (NW - 1)) == w) ;    // my warp owns the pivot row
+        const int par = step & 1 ;
+        step++ ;
+        const double *xc = P + (I64) c * ldp ;
+        // first row of my warp at or after i0
+        const I32 ifirst = i0 + ((w - i0) & (NW - 1)) ;
+
+        // ---- partial dots of column k with my column over my warp's rows ---------------------------
+        double s ;
+        {
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0 ;
+            I32 i = ifirst ;
+            for ( ; i + 3 * NW < i1 ; i += 4 * NW)
+            {
+                const double x0 = xc [i], x1 = xc [i + NW], x2 = xc [i + 2*NW], x3 = xc [i + 3*NW] ;
+                const double y0 = yc [i], y1 = yc [i + NW], y2 = yc [i + 2*NW], y3 = yc [i + 3*NW] ;
+                s0 = fma (x0, y0, s0) ; s1 = fma (x1, y1, s1) ; s2 = fma (x2, y2, s2) ; s3 = fma (x3, y3, s3) ;
+            }
+            for ( ; i < i1 ; i += NW) s0 = fma (xc [i], yc [i], s0) ;
+            s = (s0 + s1) + (s2 + s3) ;
+        }
+        part [(par * NW + w) * PANEL_MAX + lane] = mycol ? s : 0.0 ;
+        if (own_g) prow [par * PANEL_MAX + lane] = mycol ? yc [gi] : 0.0 ;
+        __syncthreads () ;
+        s = part [(par * NW) * PANEL_MAX + lane] ;
+#pragma unroll
+        for (int ww = 1 ; ww < NW ; ww++) s += part [(par * NW + ww) * PANEL_MAX + lane] ;
+        double rgv = (cr == owner) ? prow [par * PANEL_MAX + lane] : 0.0 ;
+        if (ECS > 1)
+        {
+            // one record per CTA through distributed shared memory; only warp 0 talks to the peers
+            // (DSMEM bandwidth is ~20 B/clk per SM) and re-publishes the totals locally
+            PanelXch &X = xch [par] ;
+            if (w == 0) { X.dot [lane] = s ; X.rowg [lane] = rgv ; }
+            cluster.sync () ;
+            if (w == 0)
+            {
+                // same order in every CTA: bitwise identical decisions
+                double dv [8] ;
+#pragma unroll
+                for (unsigned r = 0 ; r < 8 ; r++)
+                    dv [r] = cluster.map_shared_rank (&X, (r < ECS) ? r : 0)->dot [lane] ;
+                rgv = cluster.map_shared_rank (&X, owner)->rowg [lane] ;
+                s = 0 ;
+#pragma unroll
+                for (unsigned r = 0 ; r < 8 ; r++) if (r < ECS) s += dv [r] ;
+                part [(par * NW) * PANEL_MAX + lane] = s ;      // part[par] is dead after the block reduction
+                prow [par * PANEL_MAX + lane] = rgv ;
+            }
+            __syncthreads () ;
+            s = part [(par * NW) * PANEL_MAX + lane] ; rgv = prow [par * PANEL_MAX + lane] ;
+        }
+        double ss = __shfl_sync (STMQR_FULL_MASK, s, c) ;
+        const double alpha = __shfl_sync (STMQR_FULL_MASK, rgv, c) ;
+        double beta = alpha, tau = 0, scale = 0 ;
+        if (t - g > 1)
+        {
+            double nrm ;
+            if (ss > 1e-280 && ss < 1e280 && fabs (alpha) < 1e140)
+            {
+                nrm = sqrt (fma (alpha, alpha, ss)) ;           // hypot (alpha, ||x||)
+            }
+            else
+            {
+                // rare: zero or badly scaled sub-column: max |x| first, then the rescaled sum of
+                // squares (dnrm2 semantics).  The decision is uniform over the cluster.
+                double mx = 0 ;
+                for (I32 i = ifirst ; i < i1 ; i += NW) mx = fmax (mx, fabs (xc [i])) ;
+                mx = panel_allreduce<NW, true> (cluster, ECS, mx, red, xch [par]) ;
+                if (mx > 0)
+                {
+                    const double inv = 1.0 / mx ;
+                    double s2 = 0 ;
+                    for (I32 i = ifirst ; i < i1 ; i += NW) { const double v = xc [i] * inv ; s2 += v * v ; }
+                    s2 = panel_allreduce<NW, false> (cluster, ECS, s2, red + NW, xch [par]) ;
+                    nrm = hypot (alpha, mx * sqrt (s2)) ;
+                    ss = 1.0 ;
+                }
+                else { nrm = 0 ; ss = 0 ; }
+            }
+            if (ss != 0)
+            {
+                beta = -copysign (nrm, alpha) ;
+                tau = (beta - alpha) / beta ;
+                scale = 1.0 / (alpha - beta) ;
+            }
+        }
+        const bool dead = (k < ntol) && (fabs (beta) <= tol) ;
+
+        if (dead)
+        {
+            // zero F(g:m-1,k): my warp's rows, and (leader) whatever lies below the panel's window
+            if (lane == c)
+            {
+                const I32 z0 = max (g, lrow0) - lrow0 ;
+                for (I32 i = z0 + ((w - z0) & (NW - 1)) ; i < nloc ; i += NW) yc [i] = 0.0 ;
+            }
+            if (leader)
+            {
+                double *xg = F + (I64) k * ld ;
+                for (I32 i = rend + tid ; i < fm ; i += nt) xg [i] = 0.0 ;
+                if (tid == 0) { sto [c] = 0 ; tauo [c] = 0 ; }
+            }
+        }
+        else
+        {
+            // ---- dlarf on my warp's rows: columns > k get the rank-1 update, column k is scaled ----
+            const double wv = tau * (rgv + scale * s) ;
+            const double fct = (lane == c) ? 0.0 : scale * wv ;
+            if (tau != 0)
+            {
+                // lane c turns x into v = x * scale, lanes > c subtract x * fct: one formula
+                // y = y * a - x * b with (a,b) = (scale,0) on lane c and (1,fct) on the others
+                const double ya = (lane == c) ? scale : 1.0 ;
+                if (lane >= c && mycol)
+                {
+                    I32 i = ifirst ;
+                    for ( ; i + 3 * NW < i1 ; i += 4 * NW)
+                    {
+                        const double x0 = xc [i], x1 = xc [i + NW], x2 = xc [i + 2*NW], x3 = xc [i + 3*NW] ;
+                        const double y0 = yc [i], y1 = yc [i + NW], y2 = yc [i + 2*NW], y3 = yc [i + 3*NW] ;
+                        __syncwarp (__activemask ()) ;
+                        yc [i] = fma (-x0, fct, y0 * ya) ; yc [i + NW] = fma (-x1, fct, y1 * ya) ;
+                        yc [i + 2*NW] = fma (-x2, fct, y2 * ya) ; yc [i + 3*NW] = fma (-x3, fct, y3 * ya) ;
+                    }
+                    for ( ; i < i1 ; i += NW)
+                    {
+                        const double x0 = xc [i], y0 = yc [i] ;
+                        __syncwarp (__activemask ()) ;
+                        yc [i] = fma (-x0, fct, y0 * ya) ;
+                    }
+                }
+                if (own_g && lane > c && mycol) yc [gi] -= wv ;
+            }
+            if (own_g && lane == c) yc [gi] = beta ;
+            // V'V entries for dlarft: v_j' v_k = scale * (v_j' x) + v_j (g), j an earlier reflector
+            if (leader && w == 0 && myq >= 0) Gs [myq + nv * (PANEL_MAX + 1)] = scale * s + rgv ;
+            if (leader && tid == 0)
+            {
+                sto [c] = t ; tauo [c] = tau ;
+                cols [nv] = k ; tq [nv] = t ; taus [nv] = tau ;
+            }
+            if (lane == c) myq = nv ;
+            flops += (double) (t - g) * (3.0 + 4.0 * (double) (fn - k - 1)) ;
+            nv++ ;
+            g++ ;
+        }
+        if (k == fp - 1 && leader && tid == 0) N.rank [f] = g ;
+    }
+    __syncthreads () ;
+    if (leader)
+    {
+        // per-column outputs of the columns this panel processed
+        if (tid < np && sto [tid] >= 0)
+        {
+            const I32 k = k1 + tid ;
+            st [k] = sto [tid] ; Tau [k] = tauo [tid] ;
+            if (sto [tid] == 0 && k < fp) Rdead [k] = 1 ;
+        }
+        if (out_of_rows)
+        {
+            // no rows left: qr_front early exit (:1444-1458) for ALL remaining columns
+            for (I32 kk = kstop + tid ; kk < fn ; kk += nt)
+            {
+                if (kk < fp) { Rdead [kk] = 1 ; st [kk] = 0 ; }
+                else st [kk] = fm ;
+                Tau [kk] = 0 ;
+            }
+        }
+    }
+    panel_epilogue (L, S, N, slot, f, k2, parity, leader, nv, g, g1, out_of_rows, flops, Gs, Gs, taus, cols, tq) ;
+}
+
+// grid = (# active fronts) * CS CTAs, cluster dimension CS (launch attribute); dynamic shared
+// memory = slab_cap doubles (the row slab of one CTA: RL rows x np columns, column-major, odd ld)
+// followed by panel_scratch_doubles (NT/32) doubles of scratch.  NT = threads per CTA: small
+// fronts use small CTAs so that many of them are resident per SM.
+template <int NT, int MINB>
+__global__ void __launch_bounds__ (NT, MINB) k_panel_cluster (LevelArgs L, DSym S, DNum N, I32 k1, I32 PB,
+    I32 parity, I32 slab_cap)
+{
+    extern __shared__ double slab [] ;
+    __shared__ PanelXch xch [2] ;
+    __shared__ double tot [PANEL_MAX + 2 + 64] ;
+    __shared__ double rg [PANEL_MAX] ;
+    __shared__ I32 cols [PANEL_MAX], tq [PANEL_MAX] ;
+    constexpr int NW = NT / 32 ;
+    // global-mode scratch (V'V / T, taus) lives behind the slab like the shared-memory mode's
+    double *Gs = slab + slab_cap + 2 * NW * PANEL_MAX + 2 * PANEL_MAX + 2 * NW ;
+    double *Tsh = Gs ;
+    double *taus = Gs + PANEL_MAX * (PANEL_MAX + 1) ;
+
+    cg::cluster_group cluster = cg::this_cluster () ;
+    const unsigned CS = cluster.num_blocks (), cr = cluster.block_rank () ;
+    const I32 slot = blockIdx.x / CS ;
+    const I32 f = L.fronts [slot] ;
+    const I32 p1 = S.Rp [f], fn = S.Rp [f+1] - p1 ;
+    const int tid = threadIdx.x, nt = blockDim.x ;
+    const I32 slotp = parity * L.count + slot ;
+
+    // every CTA of the cluster reads the front's state before any of them may change it, and
+    // then takes the same branch (same inputs), so no CTA is left waiting in a cluster barrier
+    const I32 done0 = N.done [slot] ;
+    const I32 g1 = N.g [slot] ;
+    const I32 stlast = (k1 < fn) ? N.stair [p1 + min (fn, k1 + PB) - 1] : 0 ;
+    cluster.sync () ;
+    if (k1 >= fn || done0)
+    {
+        if (cr == 0 && tid == 0) N.pnl_nv [slotp] = 0 ;
+        return ;
+    }
+    const I32 fm = N.Hm [f] ;
+    const I32 k2 = min (fn, k1 + PB) ;
+    const I32 np = k2 - k1 ;
+    const I32 *st = N.stair + p1 ;
+    // rows that this panel can touch: [g1, rend)
+    const I32 rend = min (fm, max (stlast, g1 + np)) ;
+    const I32 nrows = max (rend - g1, 0) ;
+    // effective cluster size: a window that fits one CTA's slab is done by the leader alone (no
+    // cluster barriers at all); the other CTAs of the cluster leave
+    const unsigned ECS = ((I64) ((nrows + 3) | 1) * np <= (I64) slab_cap) ? 1u : CS ;
+    if (cr >= ECS) return ;
+    const I32 RL = max (4, (((nrows + (I32) ECS - 1) / (I32) ECS) + 3) & ~3) ;
+    const I32 lrow0 = g1 + (I32) cr * RL ;
+    const I32 nloc = max (0, min (rend - lrow0, RL)) ;
+    const I32 ldp = RL | 1 ;
+    const bool insmem = ((I64) ldp * np <= (I64) slab_cap) ;
+    double *F = N.F + S.Foff [f] ;
+    const I64 ld = fm ;
+
+    if (insmem)
+    {
+        // one warp per column, lanes along the rows (coalesced); the loads of a thread are
+        // independent, so the whole slab costs about one memory latency
+        {
+            const int lane = tid & 31, w = tid >> 5 ;
+            for (I32 c = w ; c < np ; c += NW)
+            {
+                const double *src = F + (I64) (k1 + c) * ld + lrow0 ;
+                double *dst = slab + (I64) c * ldp ;
+#pragma unroll 4
+                for (I32 i = lane ; i < nloc ; i += 32) dst [i] = __ldcg (src + i) ;
+            }
+        }
+        __syncthreads () ;
+        panel_columns_smem<NW> (cluster, ECS, slab_cap, ldp, L, S, N, slot, f, k1, k2, parity, lrow0, nloc, g1,
+            RL, rend, xch, cols, tq) ;
+        __syncthreads () ;
+        {
+            const int lane = tid & 31, w = tid >> 5 ;
+            for (I32 c = w ; c < np ; c += NW)
+            {
+                double *dst = F + (I64) (k1 + c) * ld + lrow0 ;
+                const double *src = slab + (I64) c * ldp ;
+#pragma unroll 4
+                for (I32 i = lane ; i < nloc ; i += 32) dst [i] = src [i] ;
+            }
+        }
+    }
+    else
+    {
+        panel_columns<false> (cluster, F + (I64) k1 * ld + lrow0, ld, L, S, N, slot, f, k1, k2, parity, lrow0,
+            nloc, g1, RL, rend, xch, tot, rg, Gs, Tsh, taus, cols, tq) ;
+    }
+    if (ECS == 1) return ;
+    // nobody may leave while a peer can still read its exchange records
+    cluster.sync () ;
+}
+
+} // namespace stmqr

@@ -16,12 +16,16 @@
 
 #include "../../include/stmqr_b200.h"
 #include "kernels_assembly.cuh"
-#include "kernels_front.cuh"
+#include "kernels_panel.cuh"
+#include "kernels_update.cuh"
 #include "kernels_peak.cuh"
 
 using namespace stmqr ;
 
 namespace {
+
+constexpr int PANEL_SLAB_MAX_DOUBLES = 24576 ;   // 192 KB of dynamic shared memory per panel CTA
+constexpr int PANEL_CLUSTER_MAX = 8 ;            // portable cluster size
 
 struct Level
 {
@@ -29,6 +33,7 @@ struct Level
     I32 count ;
     I32 maxfn ;         // max # columns in the level
     I64 maxFelems ;     // max bound Fm*fn in the level
+    I32 maxFm ;         // max bound Fm in the level
 } ;
 
 template <typename T> struct DevBuf
@@ -42,8 +47,10 @@ template <typename T> struct DevBuf
 struct stmqr_handle_s
 {
     int device = 0 ;
-    cudaStream_t stream = nullptr ;
+    cudaStream_t stream = nullptr ;         // main stream: set-up, assembly, panels, packing
+    cudaStream_t stream2 = nullptr ;        // trailing updates (look-ahead: overlaps the next panel)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr ;
+    cudaEvent_t evP [2] = {nullptr, nullptr}, evN [2] = {nullptr, nullptr}, evW = nullptr ;
     std::string err ;
     stmqr_options opt {32, 0, 0, 0} ;
     bool analyzed = false, have_matrix = false, factorized = false ;
@@ -82,6 +89,8 @@ struct stmqr_handle_s
     // optional per-launch profiling (options.profile_phases)
     std::vector<cudaEvent_t> evpool ;
     std::vector<int> evclass ;
+    std::vector<long long> evtag ;        // (level << 32) | first column of the panel step
+    long long curtag = 0 ;
     size_t evused = 0 ;
 } ;
 
@@ -159,6 +168,7 @@ inline void prof_begin (stmqr_handle h, int cls)
     }
     cudaEventRecord (h->evpool [h->evused], h->stream) ;
     h->evclass.push_back (cls) ;
+    h->evtag.push_back (h->curtag) ;
 }
 inline void prof_end (stmqr_handle h)
 {
@@ -200,12 +210,33 @@ int stmqr_b200_create (int device, stmqr_handle *out)
     if (prop.major < 10) return STMQR_ERR_NO_DEVICE ;       // sm_100a code only, no fallback
     stmqr_handle h = new stmqr_handle_s ;
     h->device = device ;
-    if (cudaSetDevice (device) != cudaSuccess ||
-        cudaStreamCreateWithFlags (&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate (&h->ev0) != cudaSuccess || cudaEventCreate (&h->ev1) != cudaSuccess ||
-        cudaEventCreate (&h->ev2) != cudaSuccess || cudaEventCreate (&h->ev3) != cudaSuccess)
+    int prio_lo = 0, prio_hi = 0 ;
+    bool ok = cudaSetDevice (device) == cudaSuccess &&
+        cudaDeviceGetStreamPriorityRange (&prio_lo, &prio_hi) == cudaSuccess &&
+        // panels are the critical path: their stream outranks the trailing updates
+        cudaStreamCreateWithPriority (&h->stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+        cudaStreamCreateWithPriority (&h->stream2, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
+        cudaEventCreate (&h->ev0) == cudaSuccess && cudaEventCreate (&h->ev1) == cudaSuccess &&
+        cudaEventCreate (&h->ev2) == cudaSuccess && cudaEventCreate (&h->ev3) == cudaSuccess &&
+        cudaEventCreateWithFlags (&h->evP [0], cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags (&h->evP [1], cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags (&h->evN [0], cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags (&h->evN [1], cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags (&h->evW, cudaEventDisableTiming) == cudaSuccess &&
+        cudaFuncSetAttribute (k_panel_cluster<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (4)) * (int) sizeof (double)) == cudaSuccess &&
+        cudaFuncSetAttribute (k_panel_cluster<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (8)) * (int) sizeof (double)) == cudaSuccess &&
+        cudaFuncSetAttribute (k_panel_cluster<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (16)) * (int) sizeof (double)) == cudaSuccess &&
+        cudaFuncSetAttribute (k_update_dmma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int) update_smem_bytes<32> ()) == cudaSuccess &&
+        cudaFuncSetAttribute (k_update_dmma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int) update_smem_bytes<64> ()) == cudaSuccess ;
+    if (!ok)
     {
-        delete h ;
+        cudaGetLastError () ;
+        stmqr_b200_destroy (h) ;
         return STMQR_ERR_CUDA ;
     }
     *out = h ;
@@ -222,6 +253,13 @@ void stmqr_b200_destroy (stmqr_handle h)
     if (h->ev2) cudaEventDestroy (h->ev2) ;
     if (h->ev3) cudaEventDestroy (h->ev3) ;
     for (cudaEvent_t e : h->evpool) cudaEventDestroy (e) ;
+    for (int i = 0 ; i < 2 ; i++)
+    {
+        if (h->evP [i]) cudaEventDestroy (h->evP [i]) ;
+        if (h->evN [i]) cudaEventDestroy (h->evN [i]) ;
+    }
+    if (h->evW) cudaEventDestroy (h->evW) ;
+    if (h->stream2) cudaStreamDestroy (h->stream2) ;
     if (h->stream) cudaStreamDestroy (h->stream) ;
     delete h ;
 }
@@ -311,36 +349,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
             }
         }
     }
-    I32 nlev = 0 ;
-    for (I64 f = 0 ; f < nf ; f++) nlev = std::max (nlev, level [f] + 1) ;
-    std::vector<std::vector<I32>> byLevel ((size_t) nlev) ;
-    for (I64 f = 0 ; f < nf ; f++) byLevel [level [f]].push_back ((I32) f) ;
-    h->levels.clear () ; h->h_levelFronts.clear () ;
     h->h_Foff.assign ((size_t) nf, 0) ; h->h_Coff.assign ((size_t) nf, 0) ;
-    h->Fcap = 0 ; h->maxLevelWidth = 0 ;
-    for (I32 l = 0 ; l < nlev ; l++)
-    {
-        auto &v = byLevel [l] ;
-        std::stable_sort (v.begin (), v.end (), [&] (I32 a, I32 b) {
-            return (Rp [a+1] - Rp [a]) > (Rp [b+1] - Rp [b]) ; }) ;
-        Level L ; L.first = (I32) h->h_levelFronts.size () ; L.count = (I32) v.size () ;
-        L.maxfn = 0 ; L.maxFelems = 0 ;
-        I64 off = 0 ;
-        for (I32 f : v)
-        {
-            const I64 fn = Rp [f+1] - Rp [f] ;
-            const I64 fe = (I64) FmB [f] * fn ;
-            L.maxfn = std::max<I32> (L.maxfn, (I32) fn) ;
-            L.maxFelems = std::max (L.maxFelems, fe) ;
-            h->h_Foff [f] = off ;
-            off += (fe + 1) & ~(I64) 1 ;            // keep every front 16-byte aligned
-            h->h_levelFronts.push_back (f) ;
-        }
-        h->Fcap = std::max (h->Fcap, off) ;
-        h->maxLevelWidth = std::max (h->maxLevelWidth, L.count) ;
-        h->levels.push_back (L) ;
-    }
-
     // ---- contribution-block arena (bound sizes) and R+H arena bound ------------------------------
     // csize bound: qr_analyze's Cm[f] rows by cn columns (SparseQR_analyze.c:536-550).
     // R+H bound per front: sum_j min (max (j+1, Stair_j), fm) with the bound staircase (:559-573).
@@ -379,6 +388,36 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
         }
         h->Ccap = coff ;
         h->Rcap = rcap + 16 ;
+    }
+
+    I32 nlev = 0 ;
+    for (I64 f = 0 ; f < nf ; f++) nlev = std::max (nlev, level [f] + 1) ;
+    std::vector<std::vector<I32>> byLevel ((size_t) nlev) ;
+    for (I64 f = 0 ; f < nf ; f++) byLevel [level [f]].push_back ((I32) f) ;
+    h->levels.clear () ; h->h_levelFronts.clear () ;
+    h->Fcap = 0 ; h->maxLevelWidth = 0 ;
+    for (I32 l = 0 ; l < nlev ; l++)
+    {
+        auto &v = byLevel [l] ;
+        std::stable_sort (v.begin (), v.end (), [&] (I32 a, I32 b) {
+            return (Rp [a+1] - Rp [a]) > (Rp [b+1] - Rp [b]) ; }) ;
+        Level L ; L.first = (I32) h->h_levelFronts.size () ; L.count = (I32) v.size () ;
+        L.maxfn = 0 ; L.maxFelems = 0 ; L.maxFm = 0 ;
+        I64 off = 0 ;
+        for (I32 f : v)
+        {
+            const I64 fn = Rp [f+1] - Rp [f] ;
+            const I64 fe = (I64) FmB [f] * fn ;
+            L.maxfn = std::max<I32> (L.maxfn, (I32) fn) ;
+            L.maxFelems = std::max (L.maxFelems, fe) ;
+            L.maxFm = std::max (L.maxFm, FmB [f]) ;
+            h->h_Foff [f] = off ;
+            off += (fe + 1) & ~(I64) 1 ;            // keep every front 16-byte aligned
+            h->h_levelFronts.push_back (f) ;
+        }
+        h->Fcap = std::max (h->Fcap, off) ;
+        h->maxLevelWidth = std::max (h->maxLevelWidth, L.count) ;
+        h->levels.push_back (L) ;
     }
 
     // ---- symbolic maps: Cj (child column -> parent column), Sjf (S entry -> front column) -------
@@ -421,7 +460,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     ALLOC (N.C, h->Ccap) ;
     ALLOC (N.R, h->Rcap) ;
     ALLOC (N.HTau, rjsize) ;
-    ALLOC (N.Tws, (I64) h->maxLevelWidth * PANEL_MAX * PANEL_MAX) ;
+    ALLOC (N.Tws, (I64) 2 * h->maxLevelWidth * PANEL_MAX * PANEL_MAX) ;
     ALLOC (N.stair, rjsize) ;
     ALLOC (N.Cmap, rjsize) ;
     ALLOC (N.rowpos, m) ;
@@ -431,9 +470,11 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     ALLOC (N.rsize, nf) ; ALLOC (N.Roff, nf) ;
     ALLOC (N.Rdead, n) ;
     ALLOC (N.g, h->maxLevelWidth) ; ALLOC (N.done, h->maxLevelWidth) ;
-    ALLOC (N.pnl_g1, h->maxLevelWidth) ; ALLOC (N.pnl_nv, h->maxLevelWidth) ;
-    ALLOC (N.pnl_tend, h->maxLevelWidth) ;
-    ALLOC (N.pnl_cols, (I64) h->maxLevelWidth * PANEL_MAX) ;
+    // panel outputs are double buffered (parity of the panel step): the trailing update of step j
+    // reads buffer j&1 while the panel of step j+1 fills the other one
+    ALLOC (N.pnl_g1, 2 * (I64) h->maxLevelWidth) ; ALLOC (N.pnl_nv, 2 * (I64) h->maxLevelWidth) ;
+    ALLOC (N.pnl_tend, 2 * (I64) h->maxLevelWidth) ;
+    ALLOC (N.pnl_cols, (I64) 2 * h->maxLevelWidth * PANEL_MAX) ;
     ALLOC (N.rcursor, 1) ;
     ALLOC (N.sumrank, 4) ; N.maxfrank = N.sumrank + 1 ; N.maxfm = N.sumrank + 2 ; N.rank1 = N.sumrank + 3 ;
     ALLOC (N.flops, 4) ;
@@ -498,9 +539,10 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
     if (!h || !h->analyzed || !h->have_matrix)
         return fail (h, STMQR_ERR_INVALID, "factorize: analyze and upload_matrix first") ;
     cudaSetDevice (h->device) ;
-    cudaStream_t st = h->stream ;
+    cudaStream_t st = h->stream, st2 = h->stream2 ;
     DSym &S = h->S ; DNum &N = h->N ;
     if (!h->do_rank_detection) tol = -1 ;           // SparseQR_factorize.c:285-289
+    const int nc_update = (h->opt.reserved >> 8) & 0xff ;   // 0 auto, 32 or 64: columns per update CTA
     h->launches = 0 ;
     const int PB = (h->opt.panel > 0 && h->opt.panel <= PANEL_MAX) ? h->opt.panel : PANEL_MAX ;
 
@@ -509,7 +551,7 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
     CK (cudaMemsetAsync (N.rcursor, 0, sizeof (unsigned long long), st)) ;
     CK (cudaMemsetAsync (N.sumrank, 0, 4 * sizeof (I32), st)) ;
     CK (cudaMemsetAsync (N.flops, 0, 4 * sizeof (double), st)) ;
-    h->evused = 0 ; h->evclass.clear () ;
+    h->evused = 0 ; h->evclass.clear () ; h->evtag.clear () ; h->curtag = 0 ;
     CK (cudaMemsetAsync (h->d_err, 0, sizeof (I32), st)) ;
     CK (cudaMemsetAsync (N.HTau, 0, std::max<I64> (h->rjsize, 1) * sizeof (double), st)) ;
 
@@ -518,8 +560,11 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
         LAUNCH (0, k_build_S<<<grid_for (h->n * 32, 256), 256, 0, st>>> ((I32) h->n, h->d_Ap, h->d_Ai, h->d_Ax, S, N.Sx, h->d_err)) ;
     }
 
+    long long levelno = -1 ;
     for (const Level &Lv : h->levels)
     {
+        levelno++ ;
+        h->curtag = levelno << 32 ;
         const I32 *fr = h->d_levelFronts + Lv.first ;
         LAUNCH (1, k_front_setup<<<Lv.count, 128, 0, st>>> (fr, S, N)) ;
         int nsl = (int) std::min<I64> (148, std::max<I64> (1, Lv.maxFelems / 8192)) ;
@@ -538,35 +583,84 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
             }
         }
         LevelArgs L ; L.fronts = fr ; L.count = Lv.count ; L.tol = tol ; L.ntol = ntol ;
-        const int pthreads = (Lv.maxFelems >= 64 * 1024) ? 1024 : ((Lv.maxFelems >= 4096) ? 256 : 64) ;
-        for (I32 k1 = 0 ; k1 < Lv.maxfn ; k1 += PB)
-        {
-            // fronts are sorted by # columns descending: the active ones are a prefix
-            I32 lo = 0, hi = Lv.count ;
+        // ---- front QR of the level: panel steps of PB columns over all active fronts ---------------
+        // cluster size: the row slab of one CTA (rows / CS x PB doubles) should fit in shared memory
+        int CS = 1 ;
+        while (CS < PANEL_CLUSTER_MAX && ((I64) (Lv.maxFm + CS - 1) / CS + 4) * PB > PANEL_SLAB_MAX_DOUBLES) CS *= 2 ;
+        const I64 rowsPerCta = ((I64) (Lv.maxFm + CS - 1) / CS + 7) & ~(I64) 3 ;
+        const I32 slabCap = (I32) std::min<I64> (PANEL_SLAB_MAX_DOUBLES, rowsPerCta * PB) ;
+        int pthreads = (rowsPerCta >= 256) ? 512 : ((rowsPerCta >= 64) ? 256 : 128) ;
+        if ((h->opt.reserved >> 16) & 0xff) pthreads = std::min (pthreads, 32 * ((h->opt.reserved >> 16) & 0xff)) ;   // tuning
+        // number of fronts of the level with more than k columns (sorted by # columns descending)
+        auto active_at = [&] (I32 k, I32 hi) -> I32 {
+            I32 lo = 0 ;
             while (lo < hi)
             {
                 I32 mid = (lo + hi) / 2 ;
                 I32 f = h->h_levelFronts [Lv.first + mid] ;
-                if (h->h_Rp [f+1] - h->h_Rp [f] > k1) lo = mid + 1 ; else hi = mid ;
+                if (h->h_Rp [f+1] - h->h_Rp [f] > k) lo = mid + 1 ; else hi = mid ;
             }
-            const I32 active = lo ;
-            if (active == 0) break ;
-            LAUNCH (3, k_panel<<<active, pthreads, 0, st>>> (L, S, N, k1, PB)) ;
-            const I32 k2 = k1 + PB ;
-            if (k2 < Lv.maxfn)
+            return lo ;
+        } ;
+        auto launch_panel = [&] (I32 active, I32 k1, I32 parity) -> cudaError_t {
+            cudaLaunchConfig_t cfg = {} ;
+            cfg.gridDim = dim3 ((unsigned) active * CS, 1, 1) ;
+            cfg.blockDim = dim3 (pthreads, 1, 1) ;
+            cfg.dynamicSmemBytes = (size_t) (slabCap + panel_scratch_doubles (pthreads / 32)) * sizeof (double) ;
+            cfg.stream = st ;
+            cudaLaunchAttribute at [1] ;
+            at [0].id = cudaLaunchAttributeClusterDimension ;
+            at [0].val.clusterDim.x = CS ; at [0].val.clusterDim.y = 1 ; at [0].val.clusterDim.z = 1 ;
+            cfg.attrs = at ; cfg.numAttrs = 1 ;
+            if (pthreads == 128) return cudaLaunchKernelEx (&cfg, k_panel_cluster<128, 6>, L, S, N, k1, (I32) PB, parity, slabCap) ;
+            if (pthreads == 256) return cudaLaunchKernelEx (&cfg, k_panel_cluster<256, 2>, L, S, N, k1, (I32) PB, parity, slabCap) ;
+            return cudaLaunchKernelEx (&cfg, k_panel_cluster<512, 1>, L, S, N, k1, (I32) PB, parity, slabCap) ;
+        } ;
+        auto launch_update = [&] (cudaStream_t su, I32 nfronts, I32 cbeg, I32 cend, I32 parity) {
+            if (nfronts <= 0 || cbeg >= cend) return ;
+            const I64 t64 = (I64) nfronts * ((cend - cbeg + 63) / 64) ;
+            if (nc_update == 64 || (nc_update == 0 && t64 >= 2 * 148))
+                k_update_dmma<64><<<dim3 (nfronts, (cend - cbeg + 63) / 64), 256, update_smem_bytes<64> (), su>>>
+                    (L, S, N, cbeg, cend, parity) ;
+            else
+                k_update_dmma<32><<<dim3 (nfronts, (cend - cbeg + 31) / 32), 256, update_smem_bytes<32> (), su>>>
+                    (L, S, N, cbeg, cend, parity) ;
+        } ;
+        // look-ahead pays only when the trailing update is much bigger than its first 32 columns
+        const bool lookahead = !h->opt.profile_phases && !(h->opt.reserved & 1) && Lv.maxFelems >= (I64) 8000000 ;
+        {
+            I32 active = active_at (0, Lv.count) ;
+            if (active > 0) { LAUNCH (3, CK (launch_panel (active, 0, 0))) ; }
+            for (I32 j = 0 ; active > 0 ; j++)
             {
-                I32 lo2 = 0, hi2 = active ;
-                while (lo2 < hi2)
+                const I32 k2 = (j + 1) * PB ;
+                if (k2 >= Lv.maxfn) break ;
+                h->curtag = (levelno << 32) | (long long) k2 ;
+                const I32 active2 = active_at (k2, active) ;
+                if (active2 == 0) break ;
+                const I32 par = j & 1 ;
+                if (lookahead)
                 {
-                    I32 mid = (lo2 + hi2) / 2 ;
-                    I32 f = h->h_levelFronts [Lv.first + mid] ;
-                    if (h->h_Rp [f+1] - h->h_Rp [f] > k2) lo2 = mid + 1 ; else hi2 = mid ;
+                    // update the next panel's columns first, then let the next panel (main stream,
+                    // high priority) overlap the rest of this trailing update (second stream)
+                    CK (cudaEventRecord (h->evP [par], st)) ;
+                    CK (cudaStreamWaitEvent (st2, h->evP [par], 0)) ;
+                    launch_update (st2, active2, k2, std::min<I32> (k2 + PB, Lv.maxfn), par) ; h->launches++ ;
+                    CK (cudaEventRecord (h->evN [par], st2)) ;
+                    if (k2 + PB < Lv.maxfn) { launch_update (st2, active2, k2 + PB, Lv.maxfn, par) ; h->launches++ ; }
+                    CK (cudaStreamWaitEvent (st, h->evN [par], 0)) ;
                 }
-                if (lo2 > 0)
+                else
                 {
-                    const int tiles = (Lv.maxfn - k2 + UPD_TB - 1) / UPD_TB ;
-                    LAUNCH (4, k_update<<<dim3 (lo2, tiles), 256, 0, st>>> (L, S, N, k2)) ;
+                    LAUNCH (4, launch_update (st, active2, k2, Lv.maxfn, par)) ;
                 }
+                LAUNCH (3, CK (launch_panel (active2, k2, par ^ 1))) ;
+                active = active2 ;
+            }
+            if (lookahead)
+            {
+                CK (cudaEventRecord (h->evW, st2)) ;
+                CK (cudaStreamWaitEvent (st, h->evW, 0)) ;
             }
         }
         if (h->debug_capture)
@@ -623,13 +717,20 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
     for (int c = 0 ; c < 8 ; c++) { h->stats.ms_class [c] = 0 ; h->stats.launches_class [c] = 0 ; }
     if (h->opt.profile_phases)
     {
+        // STMQR_B200_TRACE=<file>: one line per launch (class, etree level, first column, microseconds)
+        const char *tracefile = getenv ("STMQR_B200_TRACE") ;
+        FILE *trace = tracefile ? fopen (tracefile, "w") : nullptr ;
+        if (trace) fprintf (trace, "class,level,k1,us\n") ;
         for (size_t e = 0 ; e < h->evclass.size () ; e++)
         {
             float t = 0 ;
             cudaEventElapsedTime (&t, h->evpool [2*e], h->evpool [2*e+1]) ;
             h->stats.ms_class [h->evclass [e]] += t ;
             h->stats.launches_class [h->evclass [e]] += 1 ;
+            if (trace) fprintf (trace, "%d,%lld,%lld,%.4f\n", h->evclass [e], h->evtag [e] >> 32,
+                h->evtag [e] & 0xffffffffLL, t * 1e3) ;
         }
+        if (trace) fclose (trace) ;
         h->stats.ms_assemble = h->stats.ms_class [1] + h->stats.ms_class [2] + h->stats.ms_class [5] + h->stats.ms_class [6] ;
         h->stats.ms_front = h->stats.ms_class [3] + h->stats.ms_class [4] ;
     }
