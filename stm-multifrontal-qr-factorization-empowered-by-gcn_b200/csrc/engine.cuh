@@ -61,6 +61,7 @@ struct DNum
     unsigned long long *rcursor ;   // bump pointer of the R arena
     I32 *sumrank, *maxfrank, *maxfm, *rank1 ;
     double *flops ;         // [0] reference flop count, [1] trailing-update flops, [2] assembly bytes
+    unsigned long long *dbg ;   // [64] cycle counters (only written when built with -DSTMQR_PANEL_TIMING)
     I32 *W ;                // [m] row permutation workspace of qr_hpinv
     I64 *base1, *base2 ;    // [nf] scans used by qr_hpinv
 } ;

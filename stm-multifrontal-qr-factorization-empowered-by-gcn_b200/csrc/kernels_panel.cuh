@@ -27,6 +27,17 @@ namespace stmqr {
 
 namespace cg = cooperative_groups ;
 
+#ifdef STMQR_PANEL_TIMING
+#define PT_DECL long long pt_t0 = clock64 (), pt_acc [8] = {0,0,0,0,0,0,0,0}
+#define PT_MARK(j) do { long long pt_t1 = clock64 () ; pt_acc [j] += pt_t1 - pt_t0 ; pt_t0 = pt_t1 ; } while (0)
+#define PT_FLUSH(base) do { if (threadIdx.x == 0 && leader && L.count == 1) { for (int j_ = 0 ; j_ < 8 ; j_++) \
+    atomicAdd (N.dbg + (base) + j_, (unsigned long long) pt_acc [j_]) ; } } while (0)
+#else
+#define PT_DECL
+#define PT_MARK(j)
+#define PT_FLUSH(base)
+#endif
+
 struct LevelArgs
 {
     const I32 *fronts ;     // fronts of the level, sorted by # columns descending
@@ -46,6 +57,7 @@ struct PanelXch
 
 // dlarft for the panel's live reflectors from their V'V entries (Gs), and the panel's outputs for
 // the trailing update (T, live columns, row window), written by the leader CTA of the cluster.
+template <bool BUILD_T>
 __device__ __forceinline__ void panel_epilogue (const LevelArgs &L, const DSym &S, const DNum &N,
     const I32 slot, const I32 f, const I32 k2, const I32 parity, const bool leader, const I32 nv,
     const I32 g, const I32 g1, const bool out_of_rows, const double flops, double *Gs, double *Tsh,
@@ -56,7 +68,7 @@ __device__ __forceinline__ void panel_epilogue (const LevelArgs &L, const DSym &
     const I32 fn = S.Rp [f+1] - S.Rp [f] ;
     // ---- dlarft: T of the nv live reflectors of this panel (forward, columnwise) --------------
     const I32 slotp = parity * L.count + slot ;
-    if (leader && nv > 0 && k2 < fn)
+    if (BUILD_T && leader && nv > 0 && k2 < fn)
     {
         for (int e = tid ; e < nv * nv ; e += nt)
         {
@@ -274,7 +286,7 @@ __device__ __forceinline__ void panel_columns (cg::cluster_group &cluster, doubl
         __syncthreads () ;
     }
 
-    panel_epilogue (L, S, N, slot, f, k2, parity, leader, nv, g, g1, out_of_rows, flops, Gs, Tsh, taus, cols, tq) ;
+    panel_epilogue<true> (L, S, N, slot, f, k2, parity, leader, nv, g, g1, out_of_rows, flops, Gs, Tsh, taus, cols, tq) ;
 }
 
 // Column-per-lane mapping for a slab in shared memory: lane = panel column, warp w owns the slab
@@ -374,9 +386,11 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
     bool out_of_rows = false ;
     int step = 0 ;
     I32 kstop = k2 ;
+    PT_DECL ;
 
     for (I32 k = k1 ; k < k2 ; k++)
     {
+        PT_MARK (7) ;
         if (g >= fm) { out_of_rows = true ; kstop = k ; break ; }
         const I32 c = k - k1 ;
         const I32 t = max (g + 1, stl [c]) ;
@@ -395,23 +409,42 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
         // ---- partial dots of column k with my column over my warp's rows ---------------------------
         double s ;
         {
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0 ;
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0 ;
             I32 i = ifirst ;
-            for ( ; i + 3 * NW < i1 ; i += 4 * NW)
+            for ( ; i + 7 * NW < i1 ; i += 8 * NW)
             {
-                const double x0 = xc [i], x1 = xc [i + NW], x2 = xc [i + 2*NW], x3 = xc [i + 3*NW] ;
-                const double y0 = yc [i], y1 = yc [i + NW], y2 = yc [i + 2*NW], y3 = yc [i + 3*NW] ;
-                s0 = fma (x0, y0, s0) ; s1 = fma (x1, y1, s1) ; s2 = fma (x2, y2, s2) ; s3 = fma (x3, y3, s3) ;
+                a0 = fma (xc [i], yc [i], a0) ;                 a1 = fma (xc [i + NW], yc [i + NW], a1) ;
+                a2 = fma (xc [i + 2*NW], yc [i + 2*NW], a2) ;   a3 = fma (xc [i + 3*NW], yc [i + 3*NW], a3) ;
+                a4 = fma (xc [i + 4*NW], yc [i + 4*NW], a4) ;   a5 = fma (xc [i + 5*NW], yc [i + 5*NW], a5) ;
+                a6 = fma (xc [i + 6*NW], yc [i + 6*NW], a6) ;   a7 = fma (xc [i + 7*NW], yc [i + 7*NW], a7) ;
             }
-            for ( ; i < i1 ; i += NW) s0 = fma (xc [i], yc [i], s0) ;
-            s = (s0 + s1) + (s2 + s3) ;
+            if (i + 3 * NW < i1)
+            {
+                a0 = fma (xc [i], yc [i], a0) ;                 a1 = fma (xc [i + NW], yc [i + NW], a1) ;
+                a2 = fma (xc [i + 2*NW], yc [i + 2*NW], a2) ;   a3 = fma (xc [i + 3*NW], yc [i + 3*NW], a3) ;
+                i += 4 * NW ;
+            }
+            if (i < i1) a4 = fma (xc [i], yc [i], a4) ;
+            if (i + NW < i1) a5 = fma (xc [i + NW], yc [i + NW], a5) ;
+            if (i + 2 * NW < i1) a6 = fma (xc [i + 2*NW], yc [i + 2*NW], a6) ;
+            s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)) ;
         }
+        PT_MARK (0) ;
         part [(par * NW + w) * PANEL_MAX + lane] = mycol ? s : 0.0 ;
         if (own_g) prow [par * PANEL_MAX + lane] = mycol ? yc [gi] : 0.0 ;
         __syncthreads () ;
-        s = part [(par * NW) * PANEL_MAX + lane] ;
+        PT_MARK (1) ;
+        {
+            // FP64 adds have a long dependent latency: sum the NW partials as a tree
+            double pv [NW] ;
 #pragma unroll
-        for (int ww = 1 ; ww < NW ; ww++) s += part [(par * NW + ww) * PANEL_MAX + lane] ;
+            for (int ww = 0 ; ww < NW ; ww++) pv [ww] = part [(par * NW + ww) * PANEL_MAX + lane] ;
+#pragma unroll
+            for (int h = NW / 2 ; h > 0 ; h >>= 1)
+#pragma unroll
+                for (int ww = 0 ; ww < h ; ww++) pv [ww] += pv [ww + h] ;
+            s = pv [0] ;
+        }
         double rgv = (cr == owner) ? prow [par * PANEL_MAX + lane] : 0.0 ;
         if (ECS > 1)
         {
@@ -437,6 +470,7 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
             __syncthreads () ;
             s = part [(par * NW) * PANEL_MAX + lane] ; rgv = prow [par * PANEL_MAX + lane] ;
         }
+        PT_MARK (2) ;
         double ss = __shfl_sync (STMQR_FULL_MASK, s, c) ;
         const double alpha = __shfl_sync (STMQR_FULL_MASK, rgv, c) ;
         double beta = alpha, tau = 0, scale = 0 ;
@@ -473,6 +507,7 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
             }
         }
         const bool dead = (k < ntol) && (fabs (beta) <= tol) ;
+        PT_MARK (3) ;
 
         if (dead)
         {
@@ -533,8 +568,10 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
             g++ ;
         }
         if (k == fp - 1 && leader && tid == 0) N.rank [f] = g ;
+        PT_MARK (4) ;
     }
     __syncthreads () ;
+    PT_MARK (5) ;
     if (leader)
     {
         // per-column outputs of the columns this panel processed
@@ -555,7 +592,79 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
             }
         }
     }
-    panel_epilogue (L, S, N, slot, f, k2, parity, leader, nv, g, g1, out_of_rows, flops, Gs, Gs, taus, cols, tq) ;
+    // the slab goes back to the front before T is built: the leader reuses it as scratch
+    for (I32 c = w ; c < np ; c += NW)
+    {
+        double *dst = F + (I64) (k1 + c) * ld + lrow0 ;
+        const double *src = P + (I64) c * ldp ;
+#pragma unroll 4
+        for (I32 i = lane ; i < nloc ; i += 32) dst [i] = src [i] ;
+    }
+    if (NW == 16 && leader && nv > 8 && k2 < fn)
+    {
+        // dlarft without its 496-step dependent chain (FP64 latency): T^-1 = D^-1 + striu(V'V)
+        // (D = diag(tau)), so with N = -D striu(V'V) (nilpotent) T = (I - N)^-1 D and
+        // (I - N)^-1 = (I + N)(I + N^2)(I + N^4)(I + N^8)(I + N^16): a few 32x32 products that all
+        // threads share.  Column i of T is zero when tau_i = 0, as dlarft leaves it.
+        __syncthreads () ;
+        constexpr int LT = PANEL_MAX + 1 ;
+        double *Qm = P, *Pm = P + PANEL_MAX * LT ;      // host guarantees slab_cap >= 2*32*33
+        for (int e = tid ; e < PANEL_MAX * PANEL_MAX ; e += nt)
+        {
+            const int j = e & 31, i = e >> 5 ;
+            Qm [j + i * LT] = (j < i && i < nv) ? -taus [j] * Gs [j + i * LT] : 0.0 ;
+            Pm [j + i * LT] = (j == i) ? 1.0 : 0.0 ;
+        }
+        __syncthreads () ;
+        for (int span = 1 ; span < nv ; span *= 2)
+        {
+            // P <- P (I + Q), Q <- Q Q  (Q = N^span); both from the old P and Q
+            double pn [2], qn [2] ;
+#pragma unroll
+            for (int a = 0 ; a < 2 ; a++)
+            {
+                const int e = tid + a * nt ;
+                const int j = e & 31, i = e >> 5 ;
+                double p0 = 0, p1 = 0, p2 = 0, p3 = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0 ;
+#pragma unroll
+                for (int l = 0 ; l < PANEL_MAX ; l += 4)
+                {
+                    const double b0 = Qm [l + i * LT], b1 = Qm [l + 1 + i * LT], b2 = Qm [l + 2 + i * LT],
+                        b3 = Qm [l + 3 + i * LT] ;
+                    p0 = fma (Pm [j + l * LT], b0, p0) ;       p1 = fma (Pm [j + (l+1) * LT], b1, p1) ;
+                    p2 = fma (Pm [j + (l+2) * LT], b2, p2) ;   p3 = fma (Pm [j + (l+3) * LT], b3, p3) ;
+                    q0 = fma (Qm [j + l * LT], b0, q0) ;       q1 = fma (Qm [j + (l+1) * LT], b1, q1) ;
+                    q2 = fma (Qm [j + (l+2) * LT], b2, q2) ;   q3 = fma (Qm [j + (l+3) * LT], b3, q3) ;
+                }
+                pn [a] = Pm [j + i * LT] + ((p0 + p1) + (p2 + p3)) ;
+                qn [a] = (q0 + q1) + (q2 + q3) ;
+            }
+            __syncthreads () ;
+#pragma unroll
+            for (int a = 0 ; a < 2 ; a++)
+            {
+                const int e = tid + a * nt ;
+                const int j = e & 31, i = e >> 5 ;
+                Pm [j + i * LT] = pn [a] ; Qm [j + i * LT] = qn [a] ;
+            }
+            __syncthreads () ;
+        }
+        const I32 slotp = parity * L.count + slot ;
+        double *Tg = N.Tws + (I64) slotp * (PANEL_MAX * PANEL_MAX) ;
+        for (int e = tid ; e < nv * nv ; e += nt)
+        {
+            const int j = e % nv, i = e / nv ;
+            Tg [j + i * PANEL_MAX] = (j <= i) ? Pm [j + i * LT] * taus [i] : 0.0 ;
+        }
+        for (int q = tid ; q < nv ; q += nt) N.pnl_cols [slotp * PANEL_MAX + q] = cols [q] ;
+        panel_epilogue<false> (L, S, N, slot, f, k2, parity, leader, nv, g, g1, out_of_rows, flops, Gs, Gs, taus, cols, tq) ;
+    }
+    else
+    {
+        panel_epilogue<true> (L, S, N, slot, f, k2, parity, leader, nv, g, g1, out_of_rows, flops, Gs, Gs, taus, cols, tq) ;
+    }
+    PT_MARK (6) ;
+    PT_FLUSH ((NW == 16 ? 0 : (NW == 8 ? 8 : 16)) + (ECS > 1 ? 24 : 0)) ;
 }
 
 // grid = (# active fronts) * CS CTAs, cluster dimension CS (launch attribute); dynamic shared
@@ -632,17 +741,6 @@ __global__ void __launch_bounds__ (NT, MINB) k_panel_cluster (LevelArgs L, DSym 
         __syncthreads () ;
         panel_columns_smem<NW> (cluster, ECS, slab_cap, ldp, L, S, N, slot, f, k1, k2, parity, lrow0, nloc, g1,
             RL, rend, xch, cols, tq) ;
-        __syncthreads () ;
-        {
-            const int lane = tid & 31, w = tid >> 5 ;
-            for (I32 c = w ; c < np ; c += NW)
-            {
-                double *dst = F + (I64) (k1 + c) * ld + lrow0 ;
-                const double *src = slab + (I64) c * ldp ;
-#pragma unroll 4
-                for (I32 i = lane ; i < nloc ; i += 32) dst [i] = src [i] ;
-            }
-        }
     }
     else
     {

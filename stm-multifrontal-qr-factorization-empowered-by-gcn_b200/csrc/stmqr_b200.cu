@@ -11,7 +11,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/stmqr_b200.h"
@@ -44,6 +48,74 @@ template <typename T> struct DevBuf
 
 } // namespace
 
+namespace {
+
+// Host threads that move the downloaded factorization from the pinned staging ring into the
+// caller's (pageable, usually freshly malloc'ed) arrays: first-touch page faults and the memcpy
+// are spread over several cores while the DMA of the next chunk is in flight.
+class CopyPool
+{
+public:
+    explicit CopyPool (int nthreads) : stop_ (false), pending_ (0), gen_ (0)
+    {
+        for (int t = 0 ; t < nthreads ; t++) workers_.emplace_back ([this, t] { run (t) ; }) ;
+    }
+    ~CopyPool ()
+    {
+        { std::lock_guard<std::mutex> lk (mu_) ; stop_ = true ; }
+        cv_.notify_all () ;
+        for (auto &w : workers_) w.join () ;
+    }
+    int size () const { return (int) workers_.size () ; }
+    // dst[0..bytes) = src[0..bytes), split over the workers; returns when all slices are done
+    void copy (char *dst, const char *src, size_t bytes)
+    {
+        const int nt = size () ;
+        if (nt == 0 || bytes < (size_t) (1 << 20)) { memcpy (dst, src, bytes) ; return ; }
+        {
+            std::lock_guard<std::mutex> lk (mu_) ;
+            dst_ = dst ; src_ = src ; bytes_ = bytes ; pending_ = nt ; gen_++ ;
+        }
+        cv_.notify_all () ;
+        std::unique_lock<std::mutex> lk (mu_) ;
+        done_.wait (lk, [this] { return pending_ == 0 ; }) ;
+    }
+private:
+    void run (int t)
+    {
+        unsigned long seen = 0 ;
+        for ( ; ; )
+        {
+            char *dst ; const char *src ; size_t bytes ;
+            {
+                std::unique_lock<std::mutex> lk (mu_) ;
+                cv_.wait (lk, [&] { return stop_ || gen_ != seen ; }) ;
+                if (stop_) return ;
+                seen = gen_ ; dst = dst_ ; src = src_ ; bytes = bytes_ ;
+            }
+            const size_t nt = workers_.size () ;
+            const size_t slice = ((bytes / nt) + 4095) & ~(size_t) 4095 ;
+            const size_t lo = std::min (bytes, slice * t), hi = std::min (bytes, slice * (t + 1)) ;
+            if (hi > lo) memcpy (dst + lo, src + lo, hi - lo) ;
+            {
+                std::lock_guard<std::mutex> lk (mu_) ;
+                if (--pending_ == 0) done_.notify_all () ;
+            }
+        }
+    }
+    std::vector<std::thread> workers_ ;
+    std::mutex mu_ ;
+    std::condition_variable cv_, done_ ;
+    bool stop_ ;
+    int pending_ ;
+    unsigned long gen_ ;
+    char *dst_ = nullptr ; const char *src_ = nullptr ; size_t bytes_ = 0 ;
+} ;
+
+constexpr size_t D2H_CHUNK = (size_t) 32 << 20 ;     // bytes per staging buffer
+
+} // namespace
+
 struct stmqr_handle_s
 {
     int device = 0 ;
@@ -68,6 +140,11 @@ struct stmqr_handle_s
 
     std::vector<void *> allocs ;
     size_t device_bytes = 0 ;
+    // download pipeline: device -> pinned ring (DMA) -> caller's arrays (host threads)
+    char *pin [2] = {nullptr, nullptr} ;
+    cudaEvent_t evPin [2] = {nullptr, nullptr} ;
+    cudaStream_t streamCopy = nullptr ;
+    CopyPool *pool = nullptr ;
 
     DSym S {} ;
     DNum N {} ;
@@ -185,6 +262,38 @@ inline int grid_for (I64 n, int block, int cap = 148 * 16)
     return (int) std::max<I64> (1, std::min<I64> (g, cap)) ;
 }
 
+
+// dst (pageable host) <- src (device), bytes: DMA into two pinned staging buffers, host threads
+// copy each landed chunk into dst while the next chunk's DMA runs.  src must be complete on
+// h->stream when this is called (the caller synchronised or this is issued after an event).
+int d2h_pipelined (stmqr_handle h, void *dst, const void *src, size_t bytes)
+{
+    if (!dst || bytes == 0) return STMQR_OK ;
+    if (bytes < (size_t) (4 << 20))
+    {
+        CK (cudaMemcpyAsync (dst, src, bytes, cudaMemcpyDeviceToHost, h->streamCopy)) ;
+        CK (cudaStreamSynchronize (h->streamCopy)) ;
+        return STMQR_OK ;
+    }
+    const size_t n = (bytes + D2H_CHUNK - 1) / D2H_CHUNK ;
+    auto issue = [&] (size_t c) -> cudaError_t {
+        const size_t off = c * D2H_CHUNK, len = std::min (D2H_CHUNK, bytes - off) ;
+        cudaError_t e = cudaMemcpyAsync (h->pin [c & 1], (const char *) src + off, len, cudaMemcpyDeviceToHost,
+            h->streamCopy) ;
+        if (e != cudaSuccess) return e ;
+        return cudaEventRecord (h->evPin [c & 1], h->streamCopy) ;
+    } ;
+    CK (issue (0)) ;
+    for (size_t c = 0 ; c < n ; c++)
+    {
+        if (c + 1 < n) CK (issue (c + 1)) ;
+        CK (cudaEventSynchronize (h->evPin [c & 1])) ;
+        const size_t off = c * D2H_CHUNK, len = std::min (D2H_CHUNK, bytes - off) ;
+        h->pool->copy ((char *) dst + off, h->pin [c & 1], len) ;
+    }
+    return STMQR_OK ;
+}
+
 } // namespace
 
 // =================================================================================================
@@ -229,10 +338,10 @@ int stmqr_b200_create (int device, stmqr_handle *out)
             (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (8)) * (int) sizeof (double)) == cudaSuccess &&
         cudaFuncSetAttribute (k_panel_cluster<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (16)) * (int) sizeof (double)) == cudaSuccess &&
-        cudaFuncSetAttribute (k_update_dmma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            (int) update_smem_bytes<32> ()) == cudaSuccess &&
-        cudaFuncSetAttribute (k_update_dmma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            (int) update_smem_bytes<64> ()) == cudaSuccess ;
+        cudaFuncSetAttribute (k_update_dmma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int) update_smem_bytes<2> ()) == cudaSuccess &&
+        cudaFuncSetAttribute (k_update_dmma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int) update_smem_bytes<4> ()) == cudaSuccess ;
     if (!ok)
     {
         cudaGetLastError () ;
@@ -259,6 +368,13 @@ void stmqr_b200_destroy (stmqr_handle h)
         if (h->evN [i]) cudaEventDestroy (h->evN [i]) ;
     }
     if (h->evW) cudaEventDestroy (h->evW) ;
+    delete h->pool ;
+    for (int i = 0 ; i < 2 ; i++)
+    {
+        if (h->pin [i]) cudaFreeHost (h->pin [i]) ;
+        if (h->evPin [i]) cudaEventDestroy (h->evPin [i]) ;
+    }
+    if (h->streamCopy) cudaStreamDestroy (h->streamCopy) ;
     if (h->stream2) cudaStreamDestroy (h->stream2) ;
     if (h->stream) cudaStreamDestroy (h->stream) ;
     delete h ;
@@ -479,11 +595,12 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     ALLOC (N.sumrank, 4) ; N.maxfrank = N.sumrank + 1 ; N.maxfm = N.sumrank + 2 ; N.rank1 = N.sumrank + 3 ;
     ALLOC (N.flops, 4) ;
     ALLOC (N.W, m) ;
+    ALLOC (N.dbg, 64) ;
     ALLOC (N.base1, nf) ; ALLOC (N.base2, nf) ;
     ALLOC (h->d_err, 1) ;
     ALLOC (h->d_HPinv64, m) ;
     ALLOC (h->d_Hii64, hisize) ;
-    ALLOC (h->d_wide, std::max<I64> (rjsize, nf)) ;
+    ALLOC (h->d_wide, rjsize + 2 * nf + 2) ;
     if (h->debug_capture)
     {
         h->h_capOff.assign ((size_t) nf + 1, 0) ;
@@ -542,7 +659,7 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
     cudaStream_t st = h->stream, st2 = h->stream2 ;
     DSym &S = h->S ; DNum &N = h->N ;
     if (!h->do_rank_detection) tol = -1 ;           // SparseQR_factorize.c:285-289
-    const int nc_update = (h->opt.reserved >> 8) & 0xff ;   // 0 auto, 32 or 64: columns per update CTA
+    const int nc_update = (h->opt.reserved >> 8) & 0xff ;   // 0 auto, 2 or 4: ring stages of the update kernel
     h->launches = 0 ;
     const int PB = (h->opt.panel > 0 && h->opt.panel <= PANEL_MAX) ? h->opt.panel : PANEL_MAX ;
 
@@ -553,6 +670,7 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
     CK (cudaMemsetAsync (N.flops, 0, 4 * sizeof (double), st)) ;
     h->evused = 0 ; h->evclass.clear () ; h->evtag.clear () ; h->curtag = 0 ;
     CK (cudaMemsetAsync (h->d_err, 0, sizeof (I32), st)) ;
+    CK (cudaMemsetAsync (N.dbg, 0, 64 * sizeof (unsigned long long), st)) ;
     CK (cudaMemsetAsync (N.HTau, 0, std::max<I64> (h->rjsize, 1) * sizeof (double), st)) ;
 
     if (h->anz > 0)
@@ -588,7 +706,9 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
         int CS = 1 ;
         while (CS < PANEL_CLUSTER_MAX && ((I64) (Lv.maxFm + CS - 1) / CS + 4) * PB > PANEL_SLAB_MAX_DOUBLES) CS *= 2 ;
         const I64 rowsPerCta = ((I64) (Lv.maxFm + CS - 1) / CS + 7) & ~(I64) 3 ;
-        const I32 slabCap = (I32) std::min<I64> (PANEL_SLAB_MAX_DOUBLES, rowsPerCta * PB) ;
+        // (at least 2 x 32 x 33 doubles: the leader builds T in the slab after writing it back)
+        const I32 slabCap = (I32) std::max<I64> (2 * PANEL_MAX * (PANEL_MAX + 1),
+            std::min<I64> (PANEL_SLAB_MAX_DOUBLES, rowsPerCta * PB)) ;
         int pthreads = (rowsPerCta >= 256) ? 512 : ((rowsPerCta >= 64) ? 256 : 128) ;
         if ((h->opt.reserved >> 16) & 0xff) pthreads = std::min (pthreads, 32 * ((h->opt.reserved >> 16) & 0xff)) ;   // tuning
         // number of fronts of the level with more than k columns (sorted by # columns descending)
@@ -618,13 +738,13 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
         } ;
         auto launch_update = [&] (cudaStream_t su, I32 nfronts, I32 cbeg, I32 cend, I32 parity) {
             if (nfronts <= 0 || cbeg >= cend) return ;
-            const I64 t64 = (I64) nfronts * ((cend - cbeg + 63) / 64) ;
-            if (nc_update == 64 || (nc_update == 0 && t64 >= 2 * 148))
-                k_update_dmma<64><<<dim3 (nfronts, (cend - cbeg + 63) / 64), 256, update_smem_bytes<64> (), su>>>
-                    (L, S, N, cbeg, cend, parity) ;
+            // few CTAs (less than one per SM): deeper ring per CTA; many: two CTAs per SM
+            const I64 ctas = (I64) nfronts * ((cend - cbeg + UPD_NC - 1) / UPD_NC) ;
+            const dim3 grid (nfronts, (cend - cbeg + UPD_NC - 1) / UPD_NC) ;
+            if (nc_update == 4 || (nc_update == 0 && ctas <= 148))
+                k_update_dmma<4><<<grid, 256, update_smem_bytes<4> (), su>>> (L, S, N, cbeg, cend, parity) ;
             else
-                k_update_dmma<32><<<dim3 (nfronts, (cend - cbeg + 31) / 32), 256, update_smem_bytes<32> (), su>>>
-                    (L, S, N, cbeg, cend, parity) ;
+                k_update_dmma<2><<<grid, 256, update_smem_bytes<2> (), su>>> (L, S, N, cbeg, cend, parity) ;
         } ;
         // look-ahead pays only when the trailing update is much bigger than its first 32 columns
         const bool lookahead = !h->opt.profile_phases && !(h->opt.reserved & 1) && Lv.maxFelems >= (I64) 8000000 ;
@@ -705,6 +825,20 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
     CK (cudaStreamSynchronize (st)) ;
     CK (cudaGetLastError ()) ;
     if (err) return fail (h, STMQR_ERR_INVALID, "factorize: an entry of A is not in the pattern of S") ;
+#ifdef STMQR_PANEL_TIMING
+    {
+        unsigned long long dbg [64] ;
+        cudaMemcpy (dbg, N.dbg, sizeof (dbg), cudaMemcpyDeviceToHost) ;
+        const char *nm [8] = {"dots", "bar", "reduce+xchg", "scalar", "update", "endsync", "epilogue", "looptop"} ;
+        for (int b = 0 ; b < 48 ; b += 8)
+        {
+            fprintf (stderr, "panel cycles [%s, %s]:", b % 24 == 0 ? "16 warps" : (b % 24 == 8 ? "8 warps" : "4 warps"),
+                b >= 24 ? "cluster" : "single") ;
+            for (int j = 0 ; j < 8 ; j++) fprintf (stderr, " %s=%.3fM", nm [j], dbg [b+j] * 1e-6) ;
+            fprintf (stderr, "\n") ;
+        }
+    }
+#endif
     if ((I64) rcur > h->Rcap) return fail (h, STMQR_ERR_INVALID, "factorize: R+H arena bound exceeded") ;
     float ms = 0 ;
     cudaEventElapsedTime (&ms, h->ev0, h->ev1) ;
@@ -760,34 +894,39 @@ int stmqr_b200_download (stmqr_handle h, const stmqr_numeric_view *out)
     cudaSetDevice (h->device) ;
     cudaStream_t st = h->stream ;
     DNum &N = h->N ;
-    CK (cudaEventRecord (h->ev2, st)) ;
-    if (out->stack && h->info.rh_size > 0)
-        CK (cudaMemcpyAsync (out->stack, N.R, h->info.rh_size * sizeof (double), cudaMemcpyDeviceToHost, st)) ;
-    if (out->Roff && h->nf > 0)
-        CK (cudaMemcpyAsync (out->Roff, N.Roff, h->nf * sizeof (I64), cudaMemcpyDeviceToHost, st)) ;
-    if (out->Rdead && h->n > 0)
-        CK (cudaMemcpyAsync (out->Rdead, N.Rdead, h->n, cudaMemcpyDeviceToHost, st)) ;
-    if (out->HTau && h->rjsize > 0)
-        CK (cudaMemcpyAsync (out->HTau, N.HTau, h->rjsize * sizeof (double), cudaMemcpyDeviceToHost, st)) ;
-    if (out->HPinv && h->m > 0)
-        CK (cudaMemcpyAsync (out->HPinv, h->d_HPinv64, h->m * sizeof (I64), cudaMemcpyDeviceToHost, st)) ;
-    if (out->Hii && h->hisize > 0)
-        CK (cudaMemcpyAsync (out->Hii, h->d_Hii64, h->hisize * sizeof (I64), cudaMemcpyDeviceToHost, st)) ;
-    auto widen = [&] (const I32 *src, I64 *dst, I64 cnt) -> int {
-        if (!dst || cnt <= 0) return STMQR_OK ;
-        k_widen<<<grid_for (cnt, 256), 256, 0, st>>> (src, h->d_wide, cnt) ;
-        CK (cudaMemcpyAsync (dst, h->d_wide, cnt * sizeof (I64), cudaMemcpyDeviceToHost, st)) ;
-        return STMQR_OK ;
-    } ;
-    int s ;
-    if ((s = widen (N.stair, out->HStair, h->rjsize)) != STMQR_OK) return s ;
-    if ((s = widen (N.Hm, out->Hm, h->nf)) != STMQR_OK) return s ;
-    if ((s = widen (N.Hr, out->Hr, h->nf)) != STMQR_OK) return s ;
-    CK (cudaEventRecord (h->ev3, st)) ;
+    if (!h->pool)
+    {
+        int nt = (int) std::min<unsigned> (8, std::max<unsigned> (1, std::thread::hardware_concurrency () / 2)) ;
+        if (const char *e = getenv ("STMQR_B200_COPY_THREADS")) nt = std::max (0, atoi (e)) ;
+        h->pool = new CopyPool (nt) ;
+        CK (cudaStreamCreateWithFlags (&h->streamCopy, cudaStreamNonBlocking)) ;
+        for (int i = 0 ; i < 2 ; i++)
+        {
+            CK (cudaHostAlloc ((void **) &h->pin [i], D2H_CHUNK, cudaHostAllocDefault)) ;
+            CK (cudaEventCreateWithFlags (&h->evPin [i], cudaEventDisableTiming)) ;
+        }
+    }
+    auto t0 = std::chrono::steady_clock::now () ;
+    // widen the int32 device arrays once (HStair | Hm | Hr back to back in d_wide)
+    const I64 nw1 = std::max<I64> (h->rjsize, 0), nw2 = std::max<I64> (h->nf, 0) ;
+    if (nw1 > 0) k_widen<<<grid_for (nw1, 256), 256, 0, st>>> (N.stair, h->d_wide, nw1) ;
+    if (nw2 > 0)
+    {
+        k_widen<<<grid_for (nw2, 256), 256, 0, st>>> (N.Hm, h->d_wide + nw1, nw2) ;
+        k_widen<<<grid_for (nw2, 256), 256, 0, st>>> (N.Hr, h->d_wide + nw1 + nw2, nw2) ;
+    }
     CK (cudaStreamSynchronize (st)) ;
-    float ms = 0 ;
-    cudaEventElapsedTime (&ms, h->ev2, h->ev3) ;
-    h->stats.ms_d2h = ms ;
+    int s ;
+    if (h->info.rh_size > 0 && (s = d2h_pipelined (h, out->stack, N.R, h->info.rh_size * sizeof (double))) != STMQR_OK) return s ;
+    if ((s = d2h_pipelined (h, out->Roff, N.Roff, h->nf * sizeof (I64))) != STMQR_OK) return s ;
+    if ((s = d2h_pipelined (h, out->Rdead, N.Rdead, h->n)) != STMQR_OK) return s ;
+    if ((s = d2h_pipelined (h, out->HTau, N.HTau, h->rjsize * sizeof (double))) != STMQR_OK) return s ;
+    if ((s = d2h_pipelined (h, out->HPinv, h->d_HPinv64, h->m * sizeof (I64))) != STMQR_OK) return s ;
+    if ((s = d2h_pipelined (h, out->Hii, h->d_Hii64, h->hisize * sizeof (I64))) != STMQR_OK) return s ;
+    if ((s = d2h_pipelined (h, out->HStair, h->d_wide, nw1 * sizeof (I64))) != STMQR_OK) return s ;
+    if ((s = d2h_pipelined (h, out->Hm, h->d_wide + nw1, nw2 * sizeof (I64))) != STMQR_OK) return s ;
+    if ((s = d2h_pipelined (h, out->Hr, h->d_wide + nw1 + nw2, nw2 * sizeof (I64))) != STMQR_OK) return s ;
+    h->stats.ms_d2h = std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now () - t0).count () ;
     return STMQR_OK ;
 }
 
