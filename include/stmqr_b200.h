@@ -170,6 +170,48 @@ int  stmqr_b200_download (stmqr_handle h, const stmqr_numeric_view *out) ;
 int  stmqr_b200_factorize (stmqr_handle h, const stmqr_csc_view *A, double tol, int64_t ntol,
                            stmqr_numeric_info *info) ;
 
+/* ---- the numeric phase in pieces, and the etree partitioned over several GPUs ------------------
+ * One handle per GPU (one process per GPU under torchrun, or several handles in one process).
+ * Replaces the reference's task tree + TPSM scheduler (SparseQR_analyze.c:705-1161,
+ * SparseQR_multithreads.c:14-115): independent etree subtrees are factorized on different GPUs,
+ * the contribution blocks of the subtree roots move to the GPU that owns the top of the tree
+ * (NCCL send/recv or peer copies, done by the host between factorize_levels (1) and (2)), and the
+ * global row permutation (qr_hpinv) is finished after an element-wise max-merge of Hm, Hr, Cm, Rdead
+ * and W over the GPUs.  factorize_resident == begin, levels (0), hpinv_a, hpinv_b on one GPU. */
+int  stmqr_b200_factorize_begin (stmqr_handle h, double tol, int64_t ntol) ;
+int  stmqr_b200_factorize_levels (stmqr_handle h, int part /* 0 all, 1 my subtrees, 2 top of tree */) ;
+int  stmqr_b200_factorize_hpinv_a (stmqr_handle h) ;
+int  stmqr_b200_factorize_hpinv_b (stmqr_handle h, stmqr_numeric_info *info) ;
+int  stmqr_b200_sync (stmqr_handle h) ;
+
+/* Host only (no device needed), deterministic: owner[f] in [0,nparts) and is_top[f] for every front.
+ * The top of the tree (fronts above the cut, closed upwards) belongs to part 0. */
+int  stmqr_b200_partition_fronts (const stmqr_symbolic_view *sym, int nparts, int32_t *owner,
+                                  int32_t *is_top) ;
+int  stmqr_b200_set_partition (stmqr_handle h, int nparts, int mypart, const int32_t *owner,
+                               const int32_t *is_top) ;
+
+#define STMQR_ARRAY_HM    0   /* int32 [nf] */
+#define STMQR_ARRAY_HR    1   /* int32 [nf] */
+#define STMQR_ARRAY_CM    2   /* int32 [nf] */
+#define STMQR_ARRAY_RDEAD 3   /* int8  [n]  */
+#define STMQR_ARRAY_W     4   /* int32 [m]  row permutation workspace of qr_hpinv */
+/* Device address of one of the arrays that are merged (element-wise max) over the GPUs. */
+int  stmqr_b200_device_array (stmqr_handle h, int which, void **ptr, int64_t *count,
+                              int32_t *elem_bytes) ;
+
+/* Device regions of front f that its parent on another GPU needs (the packed contribution block,
+ * qr_cpack layout SparseQR_factorize.c:1639-1685, and the row ids of its rows, Hii[Hip[f]+Hr[f]..)).
+ * Owner side: cm = hr = hm = -1 (read from the device).  Receiver side: pass the owner's values. */
+typedef struct
+{
+    void   *C ;   int64_t C_doubles ;
+    void   *Hii ; int64_t Hii_ints ;        /* int32 */
+    int64_t cm, hr, hm ;
+} stmqr_front_regions ;
+int  stmqr_b200_front_regions (stmqr_handle h, int64_t f, int64_t cm, int64_t hr, int64_t hm,
+                               stmqr_front_regions *out) ;
+
 int  stmqr_b200_get_stats (stmqr_handle h, stmqr_stats *out) ;
 
 /* FP64 peak microbenchmarks on the handle's device, used as roofline denominators (the driver's

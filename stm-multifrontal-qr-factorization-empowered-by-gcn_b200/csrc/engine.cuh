@@ -63,6 +63,7 @@ struct DNum
     double *flops ;         // [0] reference flop count, [1] trailing-update flops, [2] assembly bytes
     unsigned long long *dbg ;   // [64] cycle counters (only written when built with -DSTMQR_PANEL_TIMING)
     I32 *W ;                // [m] row permutation workspace of qr_hpinv
+    const unsigned char *owned ;    // [nf] or null: fronts factorized on this GPU (tree partitioned over GPUs)
     I64 *base1, *base2 ;    // [nf] scans used by qr_hpinv
 } ;
 

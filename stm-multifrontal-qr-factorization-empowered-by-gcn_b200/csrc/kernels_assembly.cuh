@@ -367,6 +367,7 @@ __global__ void k_hpinv_rows (DSym S, DNum N)
     const int lane = threadIdx.x & 31 ;
     const I32 f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5 ;
     if (f >= S.nf) return ;
+    if (N.owned && !N.owned [f]) return ;       // another GPU holds this front's row ids
     const I32 fm = N.Hm [f], rm = N.Hr [f] ;
     const I32 cn = (S.Rp [f+1] - S.Rp [f]) - (S.Super [f+1] - S.Super [f]) ;
     const I32 cm = min (fm - rm, cn) ;
@@ -392,6 +393,7 @@ __global__ void k_hpinv_apply (DSym S, DNum N, I64 *HPinv64, I64 *Hii64)
     for (I64 i = gt ; i < S.m ; i += ntot) HPinv64 [i] = N.W [S.PLinv [i]] ;
     for (I64 f = gw ; f < S.nf ; f += nwarp)
     {
+        if (N.owned && !N.owned [f]) continue ;
         const I32 fm = N.Hm [f] ;
         const I32 *Hi = N.Hii + S.Hip [f] ;
         I64 *Ho = Hii64 + S.Hip [f] ;

@@ -40,10 +40,13 @@ struct Level
     I32 maxFm ;         // max bound Fm in the level
 } ;
 
-template <typename T> struct DevBuf
+// an ordered list of etree levels over a subset of the fronts (all of them on one GPU; the owned
+// subtrees or the top of the tree when the tree is partitioned over several GPUs)
+struct LevelSet
 {
-    T *p = nullptr ;
-    size_t n = 0 ;
+    std::vector<Level> levels ;
+    std::vector<I32> fronts ;           // level-ordered, inside a level sorted by # columns descending
+    I32 *d_fronts = nullptr ;
 } ;
 
 } // namespace
@@ -132,8 +135,11 @@ struct stmqr_handle_s
     I64 m = 0, n = 0, anz = 0, nf = 0, rjsize = 0, hisize = 0, maxfn = 0 ;
     int do_rank_detection = 1 ;
     std::vector<I32> h_Super, h_Rp, h_Hip, h_FmB ;
-    std::vector<I32> h_levelFronts ;
-    std::vector<Level> levels ;
+    LevelSet ls_all, ls_sub, ls_top ;
+    std::vector<I32> h_parent, h_owner, h_istop ;   // etree parent; GPU partition (set_partition)
+    int nparts = 1, mypart = 0 ;
+    unsigned char *d_owned = nullptr ;
+    double cur_tol = -1 ; I64 cur_ntol = 0 ;
     std::vector<I64> h_Foff, h_Coff ;
     I64 Fcap = 0, Ccap = 0, Rcap = 0 ;
     I32 maxLevelWidth = 0 ;
@@ -148,7 +154,6 @@ struct stmqr_handle_s
 
     DSym S {} ;
     DNum N {} ;
-    I32 *d_levelFronts = nullptr ;
     I32 *d_err = nullptr ;
     // matrix
     I64 *d_Ap = nullptr, *d_Ai = nullptr ;
@@ -292,6 +297,105 @@ int d2h_pipelined (stmqr_handle h, void *dst, const void *src, size_t bytes)
         h->pool->copy ((char *) dst + off, h->pin [c & 1], len) ;
     }
     return STMQR_OK ;
+}
+
+
+// Partition of the etree over `nparts` GPUs (host only, deterministic: every rank computes the same
+// answer from the same qr_symbolic).  The heaviest subtrees are opened from the roots until no
+// subtree outweighs 1/(4 nparts) of the total (the reference cuts its task tree the same way,
+// big_flops = total / SPQR_grain, SparseQR_analyze.c:705-859); the opened fronts form the top of the
+// tree (part 0), the remaining subtrees are dealt to the parts largest-first onto the lightest part.
+int partition_fronts (I64 nf, const int64_t *Childp, const int64_t *Child, const int64_t *Super,
+    const int64_t *Rp, const int64_t *Fm, int nparts, int32_t *owner, int32_t *is_top)
+{
+    if (nf < 0 || nparts < 1 || !owner || !is_top) return STMQR_ERR_INVALID ;
+    std::vector<I64> parent ((size_t) nf, -1) ;
+    for (I64 f = 0 ; f < nf ; f++)
+        for (I64 q = Childp [f] ; q < Childp [f+1] ; q++)
+        {
+            const I64 c = Child [q] ;
+            if (c < 0 || c >= nf) return STMQR_ERR_INVALID ;
+            parent [c] = f ;
+        }
+    for (I64 f = 0 ; f < nf ; f++) { owner [f] = 0 ; is_top [f] = 0 ; }
+    if (nparts == 1 || nf == 0) return STMQR_OK ;
+    // topological order: children before parents
+    std::vector<I64> order ; order.reserve ((size_t) nf) ;
+    {
+        std::vector<I64> stack ;
+        for (I64 r = nf - 1 ; r >= 0 ; r--) if (parent [r] < 0) stack.push_back (r) ;
+        while (!stack.empty ())
+        {
+            const I64 f = stack.back () ; stack.pop_back () ;
+            order.push_back (f) ;                       // parents first ...
+            for (I64 q = Childp [f] ; q < Childp [f+1] ; q++) stack.push_back (Child [q]) ;
+        }
+        std::reverse (order.begin (), order.end ()) ;   // ... reversed: children first
+    }
+    std::vector<double> sub ((size_t) nf, 0.0) ;
+    double total = 0 ;
+    for (I64 f : order)
+    {
+        const double fn = (double) (Rp [f+1] - Rp [f]), fm = (double) std::max<int64_t> (Fm [f], 1) ;
+        (void) Super ;
+        const double w = fm * fn * std::min (fm, fn) + 1.0 ;
+        sub [f] += w ; total += w ;
+        if (parent [f] >= 0) sub [parent [f]] += sub [f] ;
+    }
+    const double target = total / (4.0 * nparts) ;
+    auto heavier = [&] (I64 a, I64 b) { return sub [a] != sub [b] ? sub [a] > sub [b] : a < b ; } ;
+    std::vector<I64> cand ;
+    for (I64 f = 0 ; f < nf ; f++) if (parent [f] < 0) cand.push_back (f) ;
+    for ( ; ; )
+    {
+        std::sort (cand.begin (), cand.end (), heavier) ;
+        size_t pick = cand.size () ;
+        for (size_t i = 0 ; i < cand.size () ; i++)
+            if (sub [cand [i]] > target && Childp [cand [i] + 1] > Childp [cand [i]]) { pick = i ; break ; }
+        if (pick == cand.size () || (I64) cand.size () > 64 * (I64) nparts) break ;
+        const I64 f = cand [pick] ;
+        cand.erase (cand.begin () + (std::ptrdiff_t) pick) ;
+        is_top [f] = 1 ;
+        for (I64 q = Childp [f] ; q < Childp [f+1] ; q++) cand.push_back (Child [q]) ;
+    }
+    std::sort (cand.begin (), cand.end (), heavier) ;
+    std::vector<double> load ((size_t) nparts, 0.0) ;
+    std::vector<int32_t> root_owner ((size_t) nf, -1) ;
+    for (I64 c : cand)
+    {
+        int best = 0 ;
+        for (int p = 1 ; p < nparts ; p++) if (load [p] < load [best]) best = p ;
+        root_owner [c] = best ; load [best] += sub [c] ;
+    }
+    for (auto it = order.rbegin () ; it != order.rend () ; ++it)       // parents before children
+    {
+        const I64 f = *it ;
+        if (is_top [f]) owner [f] = 0 ;
+        else if (root_owner [f] >= 0) owner [f] = root_owner [f] ;
+        else owner [f] = owner [parent [f]] ;
+    }
+    return STMQR_OK ;
+}
+
+void filter_levels (const LevelSet &all, const std::vector<unsigned char> &keep, const std::vector<I32> &Rp,
+    const std::vector<I32> &FmB, LevelSet &out)
+{
+    out.levels.clear () ; out.fronts.clear () ;
+    for (const Level &Lv : all.levels)
+    {
+        Level L ; L.first = (I32) out.fronts.size () ; L.count = 0 ; L.maxfn = 0 ; L.maxFelems = 0 ; L.maxFm = 0 ;
+        for (I32 i = 0 ; i < Lv.count ; i++)
+        {
+            const I32 f = all.fronts [Lv.first + i] ;
+            if (!keep [f]) continue ;
+            const I64 fn = Rp [f+1] - Rp [f] ;
+            L.maxfn = std::max<I32> (L.maxfn, (I32) fn) ;
+            L.maxFelems = std::max (L.maxFelems, (I64) FmB [f] * fn) ;
+            L.maxFm = std::max (L.maxFm, FmB [f]) ;
+            out.fronts.push_back (f) ; L.count++ ;
+        }
+        if (L.count > 0) out.levels.push_back (L) ;
+    }
 }
 
 } // namespace
@@ -510,14 +614,15 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     for (I64 f = 0 ; f < nf ; f++) nlev = std::max (nlev, level [f] + 1) ;
     std::vector<std::vector<I32>> byLevel ((size_t) nlev) ;
     for (I64 f = 0 ; f < nf ; f++) byLevel [level [f]].push_back ((I32) f) ;
-    h->levels.clear () ; h->h_levelFronts.clear () ;
+    h->ls_all = LevelSet () ; h->ls_sub = LevelSet () ; h->ls_top = LevelSet () ;
+    h->h_parent = parent ; h->nparts = 1 ; h->mypart = 0 ; h->h_owner.clear () ; h->h_istop.clear () ;
     h->Fcap = 0 ; h->maxLevelWidth = 0 ;
     for (I32 l = 0 ; l < nlev ; l++)
     {
         auto &v = byLevel [l] ;
         std::stable_sort (v.begin (), v.end (), [&] (I32 a, I32 b) {
             return (Rp [a+1] - Rp [a]) > (Rp [b+1] - Rp [b]) ; }) ;
-        Level L ; L.first = (I32) h->h_levelFronts.size () ; L.count = (I32) v.size () ;
+        Level L ; L.first = (I32) h->ls_all.fronts.size () ; L.count = (I32) v.size () ;
         L.maxfn = 0 ; L.maxFelems = 0 ; L.maxFm = 0 ;
         I64 off = 0 ;
         for (I32 f : v)
@@ -529,11 +634,11 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
             L.maxFm = std::max (L.maxFm, FmB [f]) ;
             h->h_Foff [f] = off ;
             off += (fe + 1) & ~(I64) 1 ;            // keep every front 16-byte aligned
-            h->h_levelFronts.push_back (f) ;
+            h->ls_all.fronts.push_back (f) ;
         }
         h->Fcap = std::max (h->Fcap, off) ;
         h->maxLevelWidth = std::max (h->maxLevelWidth, L.count) ;
-        h->levels.push_back (L) ;
+        h->ls_all.levels.push_back (L) ;
     }
 
     // ---- symbolic maps: Cj (child column -> parent column), Sjf (S entry -> front column) -------
@@ -568,7 +673,8 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     I64 *p64 ;
     UPLOAD (p64, h->h_Foff) ; S.Foff = p64 ;
     UPLOAD (p64, h->h_Coff) ; S.Coff = p64 ;
-    UPLOAD (h->d_levelFronts, h->h_levelFronts) ;
+    UPLOAD (h->ls_all.d_fronts, h->ls_all.fronts) ;
+    h->d_owned = nullptr ; h->N.owned = nullptr ;
 
     DNum &N = h->N ;
     ALLOC (N.Sx, anz) ;
@@ -613,7 +719,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     h->analyzed = true ;
     memset (&h->stats, 0, sizeof (h->stats)) ;
     h->stats.ms_plan = std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now () - t0).count () ;
-    h->stats.nlevels = (I64) h->levels.size () ;
+    h->stats.nlevels = (I64) h->ls_all.levels.size () ;
     h->stats.device_bytes = (I64) h->device_bytes ;
     return STMQR_OK ;
 }
@@ -651,18 +757,19 @@ int stmqr_b200_upload_matrix (stmqr_handle h, const stmqr_csc_view *A)
 }
 
 // -------------------------------------------------------------------------------------------------
-int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stmqr_numeric_info *info)
+// ---- the numeric phase in pieces (one GPU: begin, all levels, hpinv_a, hpinv_b; several GPUs: the
+// host interleaves the exchange of the cut contribution blocks and the merges, see py/stmqr_b200/dist.py)
+int stmqr_b200_factorize_begin (stmqr_handle h, double tol, int64_t ntol)
 {
     if (!h || !h->analyzed || !h->have_matrix)
         return fail (h, STMQR_ERR_INVALID, "factorize: analyze and upload_matrix first") ;
     cudaSetDevice (h->device) ;
-    cudaStream_t st = h->stream, st2 = h->stream2 ;
+    cudaStream_t st = h->stream ;
     DSym &S = h->S ; DNum &N = h->N ;
     if (!h->do_rank_detection) tol = -1 ;           // SparseQR_factorize.c:285-289
-    const int nc_update = (h->opt.reserved >> 8) & 0xff ;   // 0 auto, 2 or 4: ring stages of the update kernel
+    h->cur_tol = tol ; h->cur_ntol = ntol ;
     h->launches = 0 ;
-    const int PB = (h->opt.panel > 0 && h->opt.panel <= PANEL_MAX) ? h->opt.panel : PANEL_MAX ;
-
+    h->factorized = false ;
     CK (cudaEventRecord (h->ev0, st)) ;
     CK (cudaMemsetAsync (N.Rdead, 0, std::max<I64> (h->n, 1), st)) ;
     CK (cudaMemsetAsync (N.rcursor, 0, sizeof (unsigned long long), st)) ;
@@ -672,18 +779,39 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
     CK (cudaMemsetAsync (h->d_err, 0, sizeof (I32), st)) ;
     CK (cudaMemsetAsync (N.dbg, 0, 64 * sizeof (unsigned long long), st)) ;
     CK (cudaMemsetAsync (N.HTau, 0, std::max<I64> (h->rjsize, 1) * sizeof (double), st)) ;
-
+    if (h->nparts > 1)
+    {
+        // arrays that are merged over the GPUs with an element-wise max: neutral element first
+        CK (cudaMemsetAsync (N.Hm, 0, std::max<I64> (h->nf, 1) * sizeof (I32), st)) ;
+        CK (cudaMemsetAsync (N.Hr, 0, std::max<I64> (h->nf, 1) * sizeof (I32), st)) ;
+        CK (cudaMemsetAsync (N.Cm, 0, std::max<I64> (h->nf, 1) * sizeof (I32), st)) ;
+        CK (cudaMemsetAsync (N.W, 0xff, std::max<I64> (h->m, 1) * sizeof (I32), st)) ;
+    }
     if (h->anz > 0)
     {
         LAUNCH (0, k_build_S<<<grid_for (h->n * 32, 256), 256, 0, st>>> ((I32) h->n, h->d_Ap, h->d_Ai, h->d_Ax, S, N.Sx, h->d_err)) ;
     }
+    return STMQR_OK ;
+}
 
+// part: 0 = every front (one GPU), 1 = the etree subtrees this GPU owns, 2 = the top of the tree
+int stmqr_b200_factorize_levels (stmqr_handle h, int part)
+{
+    if (!h || !h->analyzed || !h->have_matrix) return fail (h, STMQR_ERR_INVALID, "factorize_levels: not ready") ;
+    if (part != 0 && h->nparts <= 1) return fail (h, STMQR_ERR_INVALID, "factorize_levels: no partition set") ;
+    cudaSetDevice (h->device) ;
+    cudaStream_t st = h->stream, st2 = h->stream2 ;
+    DSym &S = h->S ; DNum &N = h->N ;
+    const LevelSet &LS = (part == 0) ? h->ls_all : ((part == 1) ? h->ls_sub : h->ls_top) ;
+    const double tol = h->cur_tol ; const I64 ntol = h->cur_ntol ;
+    const int nc_update = (h->opt.reserved >> 8) & 0xff ;   // 0 auto, 2 or 4: ring stages of the update kernel
+    const int PB = (h->opt.panel > 0 && h->opt.panel <= PANEL_MAX) ? h->opt.panel : PANEL_MAX ;
     long long levelno = -1 ;
-    for (const Level &Lv : h->levels)
+    for (const Level &Lv : LS.levels)
     {
         levelno++ ;
         h->curtag = levelno << 32 ;
-        const I32 *fr = h->d_levelFronts + Lv.first ;
+        const I32 *fr = LS.d_fronts + Lv.first ;
         LAUNCH (1, k_front_setup<<<Lv.count, 128, 0, st>>> (fr, S, N)) ;
         int nsl = (int) std::min<I64> (148, std::max<I64> (1, Lv.maxFelems / 8192)) ;
         LAUNCH (2, k_assemble<<<dim3 (Lv.count, nsl), 256, 0, st>>> (fr, S, N)) ;
@@ -694,7 +822,7 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
             CK (cudaMemcpy (hm.data (), N.Hm, h->nf * sizeof (I32), cudaMemcpyDeviceToHost)) ;
             for (I32 i = 0 ; i < Lv.count ; i++)
             {
-                I32 f = h->h_levelFronts [Lv.first + i] ;
+                I32 f = LS.fronts [Lv.first + i] ;
                 I64 cnt = (I64) hm [f] * (h->h_Rp [f+1] - h->h_Rp [f]) ;
                 if (cnt > 0) CK (cudaMemcpy (h->d_capA + h->h_capOff [f], N.F + h->h_Foff [f],
                     cnt * sizeof (double), cudaMemcpyDeviceToDevice)) ;
@@ -717,7 +845,7 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
             while (lo < hi)
             {
                 I32 mid = (lo + hi) / 2 ;
-                I32 f = h->h_levelFronts [Lv.first + mid] ;
+                I32 f = LS.fronts [Lv.first + mid] ;
                 if (h->h_Rp [f+1] - h->h_Rp [f] > k) lo = mid + 1 ; else hi = mid ;
             }
             return lo ;
@@ -790,7 +918,7 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
             CK (cudaMemcpy (hm.data (), N.Hm, h->nf * sizeof (I32), cudaMemcpyDeviceToHost)) ;
             for (I32 i = 0 ; i < Lv.count ; i++)
             {
-                I32 f = h->h_levelFronts [Lv.first + i] ;
+                I32 f = LS.fronts [Lv.first + i] ;
                 I64 cnt = (I64) hm [f] * (h->h_Rp [f+1] - h->h_Rp [f]) ;
                 if (cnt > 0) CK (cudaMemcpy (h->d_capF + h->h_capOff [f], N.F + h->h_Foff [f],
                     cnt * sizeof (double), cudaMemcpyDeviceToDevice)) ;
@@ -801,15 +929,35 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
         LAUNCH (6, k_pack<<<dim3 (Lv.count, nsl), 256, 0, st>>> (fr, S, N)) ;
     }
 
-    // qr_hpinv (:991-1060)
+    return STMQR_OK ;
+}
+
+// qr_hpinv part 1: needs Hm, Hr, Cm of EVERY front on this device (merged over the GPUs)
+int stmqr_b200_factorize_hpinv_a (stmqr_handle h)
+{
+    if (!h || !h->analyzed) return STMQR_ERR_INVALID ;
+    cudaSetDevice (h->device) ;
+    cudaStream_t st = h->stream ;
+    DSym &S = h->S ; DNum &N = h->N ;
     if (h->nf > 0)
     {
         LAUNCH (7, k_hpinv_counts<<<grid_for (h->nf, 256, 1 << 20), 256, 0, st>>> (S, N)) ;
         LAUNCH (7, k_scan_i64<<<1, 1024, 0, st>>> (N.base1, N.base2, (I32) h->nf)) ;
         LAUNCH (7, k_hpinv_rows<<<grid_for (h->nf * 32, 256, 1 << 22), 256, 0, st>>> (S, N)) ;
     }
+    LAUNCH (7, k_hpinv_empty<<<grid_for (std::max<I64> (h->m, 1), 256, 1 << 22), 256, 0, st>>> (S, N)) ;
+    return STMQR_OK ;
+}
+
+// qr_hpinv part 2 (needs the row permutation W merged over the GPUs, and Rdead) + the scalars
+int stmqr_b200_factorize_hpinv_b (stmqr_handle h, stmqr_numeric_info *info)
+{
+    if (!h || !h->analyzed) return STMQR_ERR_INVALID ;
+    cudaSetDevice (h->device) ;
+    cudaStream_t st = h->stream ;
+    DSym &S = h->S ; DNum &N = h->N ;
+    const I64 ntol = h->cur_ntol ;
     {
-        LAUNCH (7, k_hpinv_empty<<<grid_for (std::max<I64> (h->m, 1), 256, 1 << 22), 256, 0, st>>> (S, N)) ;
         LAUNCH (7, k_hpinv_apply<<<grid_for (std::max<I64> (std::max (h->m, h->nf * 32), 1), 256), 256, 0, st>>> (S, N, h->d_HPinv64, h->d_Hii64)) ;
         const I64 nt = std::min<I64> (std::max<I64> (ntol, 0), h->n) ;
         if (nt > 0) LAUNCH (7, k_rank1<<<(unsigned) ((nt + 255) / 256), 256, 0, st>>> (N.Rdead, nt, N.rank1)) ;
@@ -879,6 +1027,24 @@ int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stm
     return STMQR_OK ;
 }
 
+int stmqr_b200_factorize_resident (stmqr_handle h, double tol, int64_t ntol, stmqr_numeric_info *info)
+{
+    int s ;
+    if ((s = stmqr_b200_factorize_begin (h, tol, ntol)) != STMQR_OK) return s ;
+    if ((s = stmqr_b200_factorize_levels (h, 0)) != STMQR_OK) return s ;
+    if ((s = stmqr_b200_factorize_hpinv_a (h)) != STMQR_OK) return s ;
+    return stmqr_b200_factorize_hpinv_b (h, info) ;
+}
+
+int stmqr_b200_sync (stmqr_handle h)
+{
+    if (!h) return STMQR_ERR_INVALID ;
+    cudaSetDevice (h->device) ;
+    CK (cudaStreamSynchronize (h->stream)) ;
+    CK (cudaStreamSynchronize (h->stream2)) ;
+    return STMQR_OK ;
+}
+
 int stmqr_b200_factorize (stmqr_handle h, const stmqr_csc_view *A, double tol, int64_t ntol,
     stmqr_numeric_info *info)
 {
@@ -927,6 +1093,93 @@ int stmqr_b200_download (stmqr_handle h, const stmqr_numeric_view *out)
     if ((s = d2h_pipelined (h, out->Hm, h->d_wide + nw1, nw2 * sizeof (I64))) != STMQR_OK) return s ;
     if ((s = d2h_pipelined (h, out->Hr, h->d_wide + nw1 + nw2, nw2 * sizeof (I64))) != STMQR_OK) return s ;
     h->stats.ms_d2h = std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now () - t0).count () ;
+    return STMQR_OK ;
+}
+
+// -------------------------------------------------------------------------------------------------
+// multi-GPU: one handle per GPU, the etree partitioned over the handles
+// -------------------------------------------------------------------------------------------------
+int stmqr_b200_partition_fronts (const stmqr_symbolic_view *sym, int nparts, int32_t *owner, int32_t *is_top)
+{
+    if (!sym || !sym->Childp || !sym->Child || !sym->Rp || !sym->Fm) return STMQR_ERR_INVALID ;
+    return partition_fronts (sym->nf, sym->Childp, sym->Child, sym->Super, sym->Rp, sym->Fm, nparts, owner, is_top) ;
+}
+
+int stmqr_b200_set_partition (stmqr_handle h, int nparts, int mypart, const int32_t *owner, const int32_t *is_top)
+{
+    if (!h || !h->analyzed || nparts < 1 || mypart < 0 || mypart >= nparts || !owner || !is_top)
+        return fail (h, STMQR_ERR_INVALID, "set_partition: analyze first; 0 <= mypart < nparts") ;
+    cudaSetDevice (h->device) ;
+    const I64 nf = h->nf ;
+    h->nparts = nparts ; h->mypart = mypart ;
+    h->h_owner.assign (owner, owner + nf) ; h->h_istop.assign (is_top, is_top + nf) ;
+    std::vector<unsigned char> owned ((size_t) std::max<I64> (nf, 1), 0), sub ((size_t) std::max<I64> (nf, 1), 0),
+        top ((size_t) std::max<I64> (nf, 1), 0) ;
+    for (I64 f = 0 ; f < nf ; f++)
+    {
+        if (is_top [f] && owner [f] != 0) return fail (h, STMQR_ERR_INVALID, "set_partition: top fronts belong to part 0") ;
+        if (is_top [f] && h->h_parent [f] >= 0 && !is_top [h->h_parent [f]])
+            return fail (h, STMQR_ERR_INVALID, "set_partition: the top of the tree must be closed upwards") ;
+        owned [f] = (owner [f] == mypart) ;
+        sub [f] = owned [f] && !is_top [f] ;
+        top [f] = owned [f] && is_top [f] ;
+    }
+    filter_levels (h->ls_all, sub, h->h_Rp, h->h_FmB, h->ls_sub) ;
+    filter_levels (h->ls_all, top, h->h_Rp, h->h_FmB, h->ls_top) ;
+    UPLOAD (h->ls_sub.d_fronts, h->ls_sub.fronts) ;
+    UPLOAD (h->ls_top.d_fronts, h->ls_top.fronts) ;
+    if (nparts > 1) { UPLOAD (h->d_owned, owned) ; h->N.owned = h->d_owned ; }
+    else { h->d_owned = nullptr ; h->N.owned = nullptr ; }
+    CK (cudaStreamSynchronize (h->stream)) ;
+    return STMQR_OK ;
+}
+
+int stmqr_b200_device_array (stmqr_handle h, int which, void **ptr, int64_t *count, int32_t *elem_bytes)
+{
+    if (!h || !h->analyzed || !ptr || !count || !elem_bytes) return STMQR_ERR_INVALID ;
+    DNum &N = h->N ;
+    switch (which)
+    {
+        case STMQR_ARRAY_HM:    *ptr = N.Hm ;    *count = h->nf ; *elem_bytes = 4 ; break ;
+        case STMQR_ARRAY_HR:    *ptr = N.Hr ;    *count = h->nf ; *elem_bytes = 4 ; break ;
+        case STMQR_ARRAY_CM:    *ptr = N.Cm ;    *count = h->nf ; *elem_bytes = 4 ; break ;
+        case STMQR_ARRAY_RDEAD: *ptr = N.Rdead ; *count = h->n ;  *elem_bytes = 1 ; break ;
+        case STMQR_ARRAY_W:     *ptr = N.W ;     *count = h->m ;  *elem_bytes = 4 ; break ;
+        default: return fail (h, STMQR_ERR_INVALID, "device_array: unknown array") ;
+    }
+    return STMQR_OK ;
+}
+
+// what a parent on another GPU needs of front f: its packed contribution block and the row ids
+// of the block's rows.  cm, hr < 0: read Cm[f], Hr[f] from this device (the owner, after a sync);
+// otherwise they are the owner's values and are stored on this device (the receiver).
+int stmqr_b200_front_regions (stmqr_handle h, int64_t f, int64_t cm, int64_t hr, int64_t hm,
+    stmqr_front_regions *out)
+{
+    if (!h || !h->analyzed || !out || f < 0 || f >= h->nf) return STMQR_ERR_INVALID ;
+    cudaSetDevice (h->device) ;
+    DNum &N = h->N ;
+    I32 v [3] ;
+    if (cm < 0 || hr < 0)
+    {
+        CK (cudaMemcpy (&v [0], N.Cm + f, sizeof (I32), cudaMemcpyDeviceToHost)) ;
+        CK (cudaMemcpy (&v [1], N.Hr + f, sizeof (I32), cudaMemcpyDeviceToHost)) ;
+        CK (cudaMemcpy (&v [2], N.Hm + f, sizeof (I32), cudaMemcpyDeviceToHost)) ;
+    }
+    else
+    {
+        v [0] = (I32) cm ; v [1] = (I32) hr ; v [2] = (I32) hm ;
+        CK (cudaMemcpy (N.Cm + f, &v [0], sizeof (I32), cudaMemcpyHostToDevice)) ;
+        CK (cudaMemcpy (N.Hr + f, &v [1], sizeof (I32), cudaMemcpyHostToDevice)) ;
+        CK (cudaMemcpy (N.Hm + f, &v [2], sizeof (I32), cudaMemcpyHostToDevice)) ;
+    }
+    const I64 fp = h->h_Super [f+1] - h->h_Super [f], fn = h->h_Rp [f+1] - h->h_Rp [f], cn = fn - fp ;
+    const I64 c = v [0] ;
+    out->cm = c ; out->hr = v [1] ; out->hm = v [2] ;
+    out->C = N.C + h->h_Coff [f] ;
+    out->C_doubles = (c * (c + 1)) / 2 + c * (cn - c) ;
+    out->Hii = N.Hii + h->h_Hip [f] + v [1] ;
+    out->Hii_ints = c ;
     return STMQR_OK ;
 }
 

@@ -79,11 +79,21 @@ class Options(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class FrontRegions(C.Structure):
+    _fields_ = [("C", C.c_void_p), ("C_doubles", C.c_int64), ("Hii", C.c_void_p), ("Hii_ints", C.c_int64),
+                ("cm", C.c_int64), ("hr", C.c_int64), ("hm", C.c_int64)]
+
+
+ARRAY_HM, ARRAY_HR, ARRAY_CM, ARRAY_RDEAD, ARRAY_W = range(5)
+
 EXPORTS = (
     "stmqr_b200_device_count", "stmqr_b200_create", "stmqr_b200_destroy", "stmqr_b200_set_options",
     "stmqr_b200_analyze", "stmqr_b200_upload_matrix", "stmqr_b200_factorize_resident",
     "stmqr_b200_download", "stmqr_b200_factorize", "stmqr_b200_get_stats", "stmqr_b200_last_error",
     "stmqr_b200_set_debug_capture", "stmqr_b200_get_front", "stmqr_b200_measure_fp64_peak",
+    "stmqr_b200_factorize_begin", "stmqr_b200_factorize_levels", "stmqr_b200_factorize_hpinv_a",
+    "stmqr_b200_factorize_hpinv_b", "stmqr_b200_sync", "stmqr_b200_partition_fronts",
+    "stmqr_b200_set_partition", "stmqr_b200_device_array", "stmqr_b200_front_regions",
 )
 
 _lib = None
@@ -115,6 +125,19 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.stmqr_b200_measure_fp64_peak.argtypes = [C.c_void_p, _f64p, _f64p]
     lib.stmqr_b200_set_debug_capture.argtypes = [C.c_void_p, C.c_int]
     lib.stmqr_b200_get_front.argtypes = [C.c_void_p, C.c_int64, C.c_int, _f64p, C.c_int64, _i64p, _i64p]
+    lib.stmqr_b200_factorize_begin.argtypes = [C.c_void_p, C.c_double, C.c_int64]
+    lib.stmqr_b200_factorize_levels.argtypes = [C.c_void_p, C.c_int]
+    lib.stmqr_b200_factorize_hpinv_a.argtypes = [C.c_void_p]
+    lib.stmqr_b200_factorize_hpinv_b.argtypes = [C.c_void_p, C.POINTER(NumericInfo)]
+    lib.stmqr_b200_sync.argtypes = [C.c_void_p]
+    lib.stmqr_b200_partition_fronts.argtypes = [C.POINTER(SymbolicView), C.c_int, C.POINTER(C.c_int32),
+                                                C.POINTER(C.c_int32)]
+    lib.stmqr_b200_set_partition.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32),
+                                             C.POINTER(C.c_int32)]
+    lib.stmqr_b200_device_array.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), _i64p,
+                                            C.POINTER(C.c_int32)]
+    lib.stmqr_b200_front_regions.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                             C.POINTER(FrontRegions)]
     _lib = lib
     return lib
 
@@ -176,6 +199,18 @@ class Symbolic:
         scal = {k[2:]: int(z[k]) for k in z.files if k.startswith("s_")}
         arrs = {k[2:]: z[k] for k in z.files if k.startswith("a_")}
         return cls(scal, arrs)
+
+
+def partition_fronts(sym: "Symbolic", nparts: int):
+    """Host-only, deterministic partition of the etree over nparts GPUs -> (owner[nf], is_top[nf])."""
+    lib = load_library()
+    owner = np.zeros(max(sym.nf, 1), np.int32)
+    top = np.zeros(max(sym.nf, 1), np.int32)
+    st = lib.stmqr_b200_partition_fronts(C.byref(sym.view), nparts, owner.ctypes.data_as(C.POINTER(C.c_int32)),
+                                         top.ctypes.data_as(C.POINTER(C.c_int32)))
+    if st != STMQR_OK:
+        raise RuntimeError(f"partition_fronts: {ERRORS.get(st, st)}")
+    return owner[:sym.nf], top[:sym.nf]
 
 
 class Csc:
@@ -277,6 +312,43 @@ class Engine:
         v.HPinv = out.HPinv.ctypes.data_as(_i64p)
         self._check(self.lib.stmqr_b200_download(self.h, C.byref(v)), "download")
         return out
+
+    # ---- the numeric phase in pieces / several GPUs (see dist.py)
+    def factorize_begin(self, tol: float, ntol: int):
+        self._check(self.lib.stmqr_b200_factorize_begin(self.h, tol, ntol), "factorize_begin")
+
+    def factorize_levels(self, part: int):
+        self._check(self.lib.stmqr_b200_factorize_levels(self.h, part), "factorize_levels")
+
+    def factorize_hpinv_a(self):
+        self._check(self.lib.stmqr_b200_factorize_hpinv_a(self.h), "factorize_hpinv_a")
+
+    def factorize_hpinv_b(self) -> NumericInfo:
+        info = NumericInfo()
+        self._check(self.lib.stmqr_b200_factorize_hpinv_b(self.h, C.byref(info)), "factorize_hpinv_b")
+        return info
+
+    def sync(self):
+        self._check(self.lib.stmqr_b200_sync(self.h), "sync")
+
+    def set_partition(self, nparts: int, mypart: int, owner, is_top):
+        owner = np.ascontiguousarray(owner, np.int32)
+        is_top = np.ascontiguousarray(is_top, np.int32)
+        self._check(self.lib.stmqr_b200_set_partition(self.h, nparts, mypart,
+                                                      owner.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                      is_top.ctypes.data_as(C.POINTER(C.c_int32))), "set_partition")
+
+    def device_array(self, which: int):
+        """(device pointer, count, element bytes) of one of the arrays merged over the GPUs"""
+        p, n, eb = C.c_void_p(), C.c_int64(), C.c_int32()
+        self._check(self.lib.stmqr_b200_device_array(self.h, which, C.byref(p), C.byref(n), C.byref(eb)),
+                    "device_array")
+        return p.value, n.value, eb.value
+
+    def front_regions(self, f: int, cm: int = -1, hr: int = -1, hm: int = -1) -> FrontRegions:
+        r = FrontRegions()
+        self._check(self.lib.stmqr_b200_front_regions(self.h, f, cm, hr, hm, C.byref(r)), "front_regions")
+        return r
 
     def stats(self) -> Stats:
         s = Stats()
