@@ -226,10 +226,27 @@ def run_b200_arm(args):
     eng.analyze(sym)
     eng.upload_matrix(At)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+    pf = None
+    if world > 1:
+        # the etree partitioned over the ranks: subtrees in parallel, cut contribution blocks to
+        # rank 0 over NCCL send/recv, top of the tree on rank 0 (stmqr_b200/dist.py)
+        from stmqr_b200 import dist as D
+        pf = D.PartitionedFactorization(D.TorchComm(torch.device("cuda", local)), {rank: eng}, sym)
+
+    def factor_step():
+        """one numeric factorization of the resident matrix -> (NumericInfo of this rank, ms)"""
+        if pf is None:
+            inf = eng.factorize_resident(ttol, ntol)
+            return inf, eng.stats().ms_numeric            # CUDA events on the engine's stream
+        barrier()
+        t0 = time.perf_counter()
+        inf = pf.factorize(ttol, ntol)[rank]
+        barrier()
+        return inf, (time.perf_counter() - t0) * 1e3      # several streams + NCCL: wall clock between syncs
 
     # ---------------- value: A resident in HBM, device time ----------------------------------
     for _ in range(args.warmup):
-        info = eng.factorize_resident(ttol, ntol)
+        info, _ = factor_step()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -237,37 +254,56 @@ def run_b200_arm(args):
     for _ in range(args.steps):
         flush.zero_()
         torch.cuda.synchronize()
-        info = eng.factorize_resident(ttol, ntol)
-        dev_ms.append(eng.stats().ms_numeric)
+        info, ms = factor_step()
+        dev_ms.append(ms)
     barrier()
     st = eng.stats()
     launches = int(st.launches)
     flops = float(info.flops)
     t_dev = float(np.sum(dev_ms)) * 1e-3
     if dist is not None:
-        tt = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([t_dev, float(launches)], device="cuda", dtype=torch.float64)
+        t2 = tt.clone()
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev = float(tt.item())
+        dist.all_reduce(t2, op=dist.ReduceOp.SUM)
+        t_dev = float(tt[0].item())
+        launches = int(t2[1].item())
 
-    # ---------------- e2e: host sparse_csc in, host qr_numeric out, through qr_factorize -------
+    # ---------------- e2e: host sparse_csc in, host qr_numeric out -----------------------------
+    # one GPU: through the reference-facing plug-in, qr_factorize (drop-in) called by the reference
+    # host library.  several GPUs: every rank uploads A from host memory, the partitioned numeric
+    # phase runs, every rank downloads the R+H blocks of its own fronts into host arrays.
     e2e_s = []
     can_e2e = setup["n1cols"] == 0
+    rh_local = int(info.rh_size)
     if can_e2e:
         for s in range(min(args.warmup, 2) + args.steps):
             flush.zero_()
-            torch.cuda.synchronize()
-            t = ref.refactorize(A, QR)
+            barrier()
+            if pf is None:
+                t = ref.refactorize(A, QR)
+            else:
+                t0 = time.perf_counter()
+                eng.upload_matrix(At)
+                inf = pf.factorize(ttol, ntol)[rank]
+                eng.download(inf)
+                barrier()
+                t = time.perf_counter() - t0
             if s >= min(args.warmup, 2):
                 e2e_s.append(t)
     clocks = sampler.stop()
     t_e2e = float(np.sum(e2e_s)) if e2e_s else None
-    if dist is not None and t_e2e is not None:
-        tt = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+    rh_total = rh_local
+    if dist is not None:
+        tt = torch.tensor([t_e2e or 0.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_e2e = float(tt.item())
-    rh_bytes = int(info.rh_size) * 8
-    h2d = (sym.n + 1) * 8 + sym.anz * 16
-    d2h = rh_bytes + 8 * (2 * sym.rjsize + sym.hisize + 3 * sym.nf + sym.m) + sym.n
+        t_e2e = float(tt.item()) if t_e2e is not None else None
+        tt = torch.tensor([float(rh_local)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        rh_total = int(tt.item())
+    rh_bytes = rh_total * 8
+    h2d = ((sym.n + 1) * 8 + sym.anz * 16) * world
+    d2h = rh_bytes + (8 * (2 * sym.rjsize + sym.hisize + 3 * sym.nf + sym.m) + sym.n) * world
 
     # ---------------- roofline of the dominant kernel class (extra, untimed steps) ------------
     eng.set_options(panel=args.panel, profile_phases=1)
@@ -277,7 +313,7 @@ def run_b200_arm(args):
     for _ in range(nprof):
         flush.zero_()
         torch.cuda.synchronize()
-        eng.factorize_resident(ttol, ntol)
+        factor_step()
         s2 = eng.stats()
         cls_ms += np.array(list(s2.ms_class))
         cls_n += np.array(list(s2.launches_class))
@@ -314,7 +350,7 @@ def run_b200_arm(args):
 
     # ---------------- CPU baseline: the reference's own qr_factorize on this box's cores --------
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline and can_e2e:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and can_e2e:
         # bounded sample: the whole workload, once per way of using the cores (serial etree x
         # threaded BLAS on this run's symbolic object; the reference's TPSM tree tasks with
         # cc->SPQR_grain = 2*cores need their own qr_analyze because it makes the task partition)
@@ -338,24 +374,31 @@ def run_b200_arm(args):
         ref.set_backend("b200")
 
     if rank == 0:
-        total_flops = flops * args.steps * world      # replicas: every rank factorizes the workload
+        total_flops = flops * args.steps              # ONE factorization per step, shared by all ranks
         line = {"metric": METRIC, "value": total_flops / t_dev * 1e-9, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": args.workload, "description": desc, "m": sym.m, "n": sym.n,
                            "nnz": sym.anz, "fronts": sym.nf, "etree_levels": int(st.nlevels),
                            "rank": int(info.rank), "flops_per_step": flops,
-                           "rh_doubles": int(info.rh_size), "tol": ttol,
+                           "rh_doubles": rh_total, "tol": ttol,
                            "l2": "256 MiB device buffer written between timed steps (L2 flush)",
-                           "multi_gpu": "replicas" if world > 1 else "single",
+                           "multi_gpu": ("single" if world == 1 else
+                                         f"etree partitioned over {world} GPUs: {int(pf.is_top.sum())} top fronts on "
+                                         f"rank 0, {len(pf.cut)} cut contribution blocks over NCCL send/recv, "
+                                         f"fronts per rank {np.bincount(pf.owner, minlength=world).tolist()}"),
+                           "timing": ("CUDA events on the engine stream" if world == 1 else
+                                      "wall clock between barrier+synchronize (engine streams + NCCL), max over ranks"),
                            "device_bytes": int(st.device_bytes)},
-                "e2e": ({"value": flops * len(e2e_s) * world / t_e2e * 1e-9, "unit": UNIT,
+                "e2e": ({"value": flops * len(e2e_s) / t_e2e * 1e-9, "unit": UNIT,
                          "ms_per_step": t_e2e / len(e2e_s) * 1e3, "h2d_bytes_per_step": h2d,
                          "d2h_bytes_per_step": d2h,
-                         "how": "wall clock around qr_factorize (drop-in) called by the reference host "
-                                "library with a host sparse_csc; host qr_numeric out; plan cached "
-                                "(STMQR_B200_CACHE_PLAN=1)",
+                         "how": ("wall clock around qr_factorize (drop-in) called by the reference host "
+                                 "library with a host sparse_csc; host qr_numeric out; plan cached "
+                                 "(STMQR_B200_CACHE_PLAN=1)") if world == 1 else
+                                ("per rank: upload A from host, partitioned numeric phase, download of the "
+                                 "rank's own R+H blocks to host arrays; max over ranks"),
                          "first_call_with_plan_s": setup["first_factorize_s"],
                          "plan_ms": float(st.ms_plan)} if t_e2e else None),
                 "gpu_launches": launches * args.steps,
