@@ -64,6 +64,10 @@ def make_workload(name: str):
         m, n = int(m), int(n)
         return (f"banded random tall-sparse {m}x{n} (8 draws/row, halfwidth 64, PCG64 seed 4), COLAMD",
                 M.tall_banded_random(m, n, draws=8, halfwidth=64, seed=4), 1)
+    if name.startswith("dense_"):
+        _, m, n = name.split("_")
+        return (f"dense random {m}x{n} as sparse_csc (one front: the large-front kernels alone), COLAMD",
+                M.dense_random(int(m), int(n)), 1)
     if name.startswith("mtx:"):            # mtx:<name>:<ordering>
         _, f, o = name.split(":")
         return (f"bundled Data/{f}.mtx, ordering arg {o}", ("mtx", f), int(o))

@@ -65,6 +65,13 @@ struct DNum
     I32 *W ;                // [m] row permutation workspace of qr_hpinv
     const unsigned char *owned ;    // [nf] or null: fronts factorized on this GPU (tree partitioned over GPUs)
     I64 *base1, *base2 ;    // [nf] scans used by qr_hpinv
+    // two-level blocked path of the large fronts (kernels_wide.cuh); sized for the widest such level
+    double *wVb ;           // [2][slots][ldv*128]   clean Householder vectors of the current outer block
+    double *wTbt ;          // [2][slots][128*128]   T of the outer block, transposed
+    I32 *wblk ;             // [2][slots][4]         g0, mr, nvtot of the outer block
+    double *wWp, *wW2 ;     // [slots][nsplit][ncmax*128] partial V'C,  [slots][ncmax*128] -T' sum
+    double *wWpi, *wW2i ;   // the same for the update inside the block (32 reflectors, <= 96 columns)
+    double *wGp ;           // [slots][nsplit][128*128] partial Gram matrices Vb'Vb
 } ;
 
 } // namespace stmqr

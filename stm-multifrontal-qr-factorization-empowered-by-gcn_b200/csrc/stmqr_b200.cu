@@ -22,6 +22,7 @@
 #include "kernels_assembly.cuh"
 #include "kernels_panel.cuh"
 #include "kernels_update.cuh"
+#include "kernels_wide.cuh"
 #include "kernels_peak.cuh"
 
 using namespace stmqr ;
@@ -38,7 +39,23 @@ struct Level
     I32 maxfn ;         // max # columns in the level
     I64 maxFelems ;     // max bound Fm*fn in the level
     I32 maxFm ;         // max bound Fm in the level
+    // two-level blocked path (kernels_wide.cuh): few, large fronts
+    bool wide ;
+    I32 ldv ;           // leading dimension of the clean V buffers
+    I32 nsplit ;        // row splits of the K = 128 contraction (WIDE_RS rows each)
+    I32 nsplit_in ;     // row splits of the K = 32 update inside an outer block (WIDE_RS_IN rows each)
 } ;
+
+constexpr I32 WIDE_RS = 1024, WIDE_RS_IN = 256 ;
+constexpr I32 WIDE_MIN_ROWS = 1024, WIDE_MIN_COLS = 384, WIDE_MAX_FRONTS = 64 ;
+
+void plan_wide (Level &L)
+{
+    L.wide = (L.maxFm >= WIDE_MIN_ROWS && L.maxfn >= WIDE_MIN_COLS && L.count <= WIDE_MAX_FRONTS) ;
+    L.ldv = ((L.maxFm + W_RT - 1) / W_RT) * W_RT + W_RT ;
+    L.nsplit = (L.ldv + WIDE_RS - 1) / WIDE_RS ;
+    L.nsplit_in = (L.ldv + WIDE_RS_IN - 1) / WIDE_RS_IN ;
+}
 
 // an ordered list of etree levels over a subset of the fronts (all of them on one GPU; the owned
 // subtrees or the top of the tree when the tree is partitioned over several GPUs)
@@ -394,7 +411,7 @@ void filter_levels (const LevelSet &all, const std::vector<unsigned char> &keep,
             L.maxFm = std::max (L.maxFm, FmB [f]) ;
             out.fronts.push_back (f) ; L.count++ ;
         }
-        if (L.count > 0) out.levels.push_back (L) ;
+        if (L.count > 0) { plan_wide (L) ; out.levels.push_back (L) ; }
     }
 }
 
@@ -423,6 +440,7 @@ int stmqr_b200_create (int device, stmqr_handle *out)
     if (prop.major < 10) return STMQR_ERR_NO_DEVICE ;       // sm_100a code only, no fallback
     stmqr_handle h = new stmqr_handle_s ;
     h->device = device ;
+    if (const char *e = getenv ("STMQR_B200_FLAGS")) h->opt.reserved = (int32_t) strtol (e, nullptr, 0) ;
     int prio_lo = 0, prio_hi = 0 ;
     bool ok = cudaSetDevice (device) == cudaSuccess &&
         cudaDeviceGetStreamPriorityRange (&prio_lo, &prio_hi) == cudaSuccess &&
@@ -445,7 +463,17 @@ int stmqr_b200_create (int device, stmqr_handle *out)
         cudaFuncSetAttribute (k_update_dmma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (int) update_smem_bytes<2> ()) == cudaSuccess &&
         cudaFuncSetAttribute (k_update_dmma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            (int) update_smem_bytes<4> ()) == cudaSuccess ;
+            (int) update_smem_bytes<4> ()) == cudaSuccess &&
+        cudaFuncSetAttribute (k_wide_vtc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int) wide_vtc_smem_bytes<1> ()) == cudaSuccess &&
+        cudaFuncSetAttribute (k_wide_vtc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int) wide_vtc_smem_bytes<4> ()) == cudaSuccess &&
+        cudaFuncSetAttribute (k_wide_apply<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int) wide_apply_smem_bytes<1> ()) == cudaSuccess &&
+        cudaFuncSetAttribute (k_wide_apply<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int) wide_apply_smem_bytes<4> ()) == cudaSuccess &&
+        cudaFuncSetAttribute (k_wide_tmerge, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int) wide_tmerge_smem_bytes ()) == cudaSuccess ;
     if (!ok)
     {
         cudaGetLastError () ;
@@ -488,6 +516,7 @@ int stmqr_b200_set_options (stmqr_handle h, const stmqr_options *opt)
 {
     if (!h || !opt) return STMQR_ERR_INVALID ;
     h->opt = *opt ;
+    if (const char *e = getenv ("STMQR_B200_FLAGS")) h->opt.reserved |= (int32_t) strtol (e, nullptr, 0) ;
     if (h->opt.panel <= 0 || h->opt.panel > PANEL_MAX) h->opt.panel = PANEL_MAX ;
     return STMQR_OK ;
 }
@@ -638,6 +667,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
         }
         h->Fcap = std::max (h->Fcap, off) ;
         h->maxLevelWidth = std::max (h->maxLevelWidth, L.count) ;
+        plan_wide (L) ;
         h->ls_all.levels.push_back (L) ;
     }
 
@@ -682,7 +712,28 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     ALLOC (N.C, h->Ccap) ;
     ALLOC (N.R, h->Rcap) ;
     ALLOC (N.HTau, rjsize) ;
-    ALLOC (N.Tws, (I64) 2 * h->maxLevelWidth * PANEL_MAX * PANEL_MAX) ;
+    // per-slot panel outputs: 2 parities (look-ahead), 4 on the levels that take the two-level path
+    I64 pslots = 2 * (I64) h->maxLevelWidth ;
+    {
+        I64 vb = 0, tb = 0, wp = 0, w2 = 0, wpi = 0, w2i = 0, gp = 0, nb = 0 ;
+        for (const Level &Lv : h->ls_all.levels)
+        {
+            if (!Lv.wide) continue ;
+            const I64 c = Lv.count ;
+            pslots = std::max (pslots, (I64) WB_PANELS * c) ;
+            vb = std::max (vb, 2 * c * (I64) Lv.ldv * WB) ;
+            tb = std::max (tb, 2 * c * (I64) (WB * WB)) ;
+            nb = std::max (nb, 2 * c * 4) ;
+            wp = std::max (wp, c * Lv.nsplit * (I64) Lv.maxfn * WB) ;
+            w2 = std::max (w2, c * (I64) Lv.maxfn * WB) ;
+            wpi = std::max (wpi, c * Lv.nsplit_in * (I64) (WB * PANEL_MAX)) ;
+            w2i = std::max (w2i, c * (I64) (WB * PANEL_MAX)) ;
+            gp = std::max (gp, c * Lv.nsplit * (I64) (WB * WB)) ;
+        }
+        ALLOC (N.wVb, vb) ; ALLOC (N.wTbt, tb) ; ALLOC (N.wblk, nb) ;
+        ALLOC (N.wWp, wp) ; ALLOC (N.wW2, w2) ; ALLOC (N.wWpi, wpi) ; ALLOC (N.wW2i, w2i) ; ALLOC (N.wGp, gp) ;
+    }
+    ALLOC (N.Tws, pslots * PANEL_MAX * PANEL_MAX) ;
     ALLOC (N.stair, rjsize) ;
     ALLOC (N.Cmap, rjsize) ;
     ALLOC (N.rowpos, m) ;
@@ -694,9 +745,9 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     ALLOC (N.g, h->maxLevelWidth) ; ALLOC (N.done, h->maxLevelWidth) ;
     // panel outputs are double buffered (parity of the panel step): the trailing update of step j
     // reads buffer j&1 while the panel of step j+1 fills the other one
-    ALLOC (N.pnl_g1, 2 * (I64) h->maxLevelWidth) ; ALLOC (N.pnl_nv, 2 * (I64) h->maxLevelWidth) ;
-    ALLOC (N.pnl_tend, 2 * (I64) h->maxLevelWidth) ;
-    ALLOC (N.pnl_cols, (I64) 2 * h->maxLevelWidth * PANEL_MAX) ;
+    ALLOC (N.pnl_g1, pslots) ; ALLOC (N.pnl_nv, pslots) ;
+    ALLOC (N.pnl_tend, pslots) ;
+    ALLOC (N.pnl_cols, pslots * PANEL_MAX) ;
     ALLOC (N.rcursor, 1) ;
     ALLOC (N.sumrank, 4) ; N.maxfrank = N.sumrank + 1 ; N.maxfm = N.sumrank + 2 ; N.rank1 = N.sumrank + 3 ;
     ALLOC (N.flops, 4) ;
@@ -876,6 +927,87 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
         } ;
         // look-ahead pays only when the trailing update is much bigger than its first 32 columns
         const bool lookahead = !h->opt.profile_phases && !(h->opt.reserved & 1) && Lv.maxFelems >= (I64) 8000000 ;
+        const bool wide = Lv.wide && !(h->opt.reserved & 2) && PB == PANEL_MAX ;
+        if (wide)
+        {
+            // ---- two-level blocking (kernels_wide.cuh): outer blocks of 128 columns = 4 panels -------
+            WideArgs WA ; WA.fronts = fr ; WA.count = Lv.count ; WA.buf = 0 ; WA.ldv = Lv.ldv ;
+            WA.rs = WIDE_RS ; WA.nsplit = Lv.nsplit ; WA.ncmax = Lv.maxfn ;
+            WideArgs WI = WA ; WI.rs = WIDE_RS_IN ; WI.nsplit = Lv.nsplit_in ;
+            const I32 nrt = Lv.ldv / W_RT ;
+            // the K = 32 update of columns [cb,ce) (inside the block) by panel p of the block
+            auto inner_update = [&] (I32 nfronts, I32 p, I32 cb, I32 ce) {
+                const I32 nct = (ce - cb + W_NC - 1) / W_NC ;
+                LAUNCH (9, k_wide_vtc<1><<<dim3 (nct * WI.nsplit, nfronts), 256, wide_vtc_smem_bytes<1> (), st>>> (WI, S, N, WIDE_INNER, p, cb, ce)) ;
+                LAUNCH (10, k_wide_wt<1><<<dim3 ((ce - cb + 15) / 16, nfronts), 256, 0, st>>> (WI, S, N, WIDE_INNER, p, cb, ce)) ;
+                LAUNCH (11, k_wide_apply<1><<<dim3 (nct * nrt, nfronts), 256, wide_apply_smem_bytes<1> (), st>>> (WI, S, N, WIDE_INNER, p, cb, ce, nct)) ;
+            } ;
+            // the K = 128 update of columns [cb,ce) (right of the block)
+            // (events of LAUNCH are recorded on the main stream: only meaningful when su == st)
+            auto outer_update = [&] (cudaStream_t su, I32 nfronts, I32 cb, I32 ce) {
+                const I32 nct = (ce - cb + W_NC - 1) / W_NC ;
+                LAUNCH (14, k_wide_vtc<4><<<dim3 (nct * WA.nsplit, nfronts), 256, wide_vtc_smem_bytes<4> (), su>>> (WA, S, N, WIDE_OUTER, 0, cb, ce)) ;
+                LAUNCH (15, k_wide_wt<4><<<dim3 ((ce - cb + 15) / 16, nfronts), 256, 0, su>>> (WA, S, N, WIDE_OUTER, 0, cb, ce)) ;
+                LAUNCH (16, k_wide_apply<4><<<dim3 (nct * nrt, nfronts), 256, wide_apply_smem_bytes<4> (), su>>> (WA, S, N, WIDE_OUTER, 0, cb, ce, nct)) ;
+            } ;
+            const I32 nblk = (Lv.maxfn + WB - 1) / WB ;
+            bool pending [2] = {false, false} ;     // a "rest of the trailing matrix" update in flight on stream2
+            for (I32 J = 0 ; J < nblk ; J++)
+            {
+                const I32 j0 = J * WB ;
+                if (active_at (j0, Lv.count) == 0) break ;
+                WA.buf = WI.buf = J & 1 ;
+                for (I32 p = 0 ; p < WB_PANELS ; p++)
+                {
+                    const I32 k1 = j0 + p * PANEL_MAX ;
+                    if (k1 >= Lv.maxfn) break ;
+                    const I32 act = active_at (k1, Lv.count) ;
+                    if (act == 0) break ;
+                    h->curtag = (levelno << 32) | (long long) k1 ;
+                    LAUNCH (3, CK (launch_panel (act, k1, p))) ;
+                    LAUNCH (8, k_wide_vextract<<<dim3 ((Lv.ldv + 255) / 256, act), 256, 0, st>>> (WI, S, N, p)) ;
+                    const I32 cb = k1 + PANEL_MAX, ce = std::min<I32> (j0 + WB, Lv.maxfn) ;
+                    if (p + 1 < WB_PANELS && cb < ce)
+                    {
+                        const I32 act2 = active_at (cb, act) ;
+                        if (act2 > 0) inner_update (act2, p, cb, ce) ;
+                    }
+                }
+                const I32 cb = j0 + WB ;
+                if (cb >= Lv.maxfn) break ;
+                const I32 act2 = active_at (cb, Lv.count) ;
+                if (act2 == 0) break ;
+                LAUNCH (12, k_wide_vtc<4><<<dim3 (2 * WA.nsplit, act2), 256, wide_vtc_smem_bytes<4> (), st>>> (WA, S, N, WIDE_GRAM, 0, 0, WB)) ;
+                LAUNCH (13, k_wide_tmerge<<<act2, 256, wide_tmerge_smem_bytes (), st>>> (WA, S, N)) ;
+                if (lookahead)
+                {
+                    // the next block's columns first (main stream), the rest of the trailing matrix on the
+                    // second stream while the next block's panels run
+                    if (pending [(J + 1) & 1]) { CK (cudaStreamWaitEvent (st, h->evN [(J + 1) & 1], 0)) ; pending [(J + 1) & 1] = false ; }
+                    const I32 cm = std::min<I32> (cb + WB, Lv.maxfn) ;
+                    outer_update (st, act2, cb, cm) ;
+                    if (cm < Lv.maxfn)
+                    {
+                        const I32 act3 = active_at (cm, act2) ;
+                        if (act3 > 0)
+                        {
+                            CK (cudaEventRecord (h->evP [J & 1], st)) ;
+                            CK (cudaStreamWaitEvent (st2, h->evP [J & 1], 0)) ;
+                            outer_update (st2, act3, cm, Lv.maxfn) ;
+                            CK (cudaEventRecord (h->evN [J & 1], st2)) ;
+                            pending [J & 1] = true ;
+                        }
+                    }
+                }
+                else
+                {
+                    outer_update (st, act2, cb, Lv.maxfn) ;
+                }
+            }
+            for (int b = 0 ; b < 2 ; b++)
+                if (pending [b]) CK (cudaStreamWaitEvent (st, h->evN [b], 0)) ;
+        }
+        else
         {
             I32 active = active_at (0, Lv.count) ;
             if (active > 0) { LAUNCH (3, CK (launch_panel (active, 0, 0))) ; }
@@ -1007,8 +1139,11 @@ int stmqr_b200_factorize_hpinv_b (stmqr_handle h, stmqr_numeric_info *info)
         {
             float t = 0 ;
             cudaEventElapsedTime (&t, h->evpool [2*e], h->evpool [2*e+1]) ;
-            h->stats.ms_class [h->evclass [e]] += t ;
-            h->stats.launches_class [h->evclass [e]] += 1 ;
+            // classes >= 8 are the kernels of the two-level path (trace detail): 8 V extract (panel
+            // class), 9-11 inner vtc/wt/apply, 12 Gram, 13 T merge, 14-16 outer vtc/wt/apply (update class)
+            const int cl = (h->evclass [e] < 8) ? h->evclass [e] : ((h->evclass [e] == 8) ? 3 : 4) ;
+            h->stats.ms_class [cl] += t ;
+            h->stats.launches_class [cl] += 1 ;
             if (trace) fprintf (trace, "%d,%lld,%lld,%.4f\n", h->evclass [e], h->evtag [e] >> 32,
                 h->evtag [e] & 0xffffffffLL, t * 1e3) ;
         }

@@ -270,8 +270,9 @@ class Engine:
             msg = self.lib.stmqr_b200_last_error(self.h)
             raise EngineError(f"{what}: {ERRORS.get(st, st)}: {msg.decode() if msg else ''}")
 
-    def set_options(self, panel=0, small_elems=0, profile_phases=0):
-        o = Options(panel, small_elems, profile_phases, 0)
+    def set_options(self, panel=0, small_elems=0, profile_phases=0, flags=0):
+        """flags (tuning / A-B tests): bit 0 no look-ahead, bit 1 no two-level (128-column) blocking"""
+        o = Options(panel, small_elems, profile_phases, flags)
         self._check(self.lib.stmqr_b200_set_options(self.h, C.byref(o)), "set_options")
 
     def analyze(self, sym: Symbolic):

@@ -76,3 +76,13 @@ def random_sparse(m: int, n: int, density: float, seed: int = 0, rank_deficient_
     A = A.tocsc()
     A.sort_indices()
     return m, n, A.indptr.astype(np.int64), A.indices.astype(np.int64), A.data.astype(np.float64)
+
+
+def dense_random(m: int, n: int, seed: int = 7):
+    """A dense m-by-n matrix stored as sparse_csc: the symbolic analysis yields ONE front of
+    m x n, so the numeric phase is exactly the dense staircase-free front QR (the large-front
+    kernels measured in isolation)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    p = np.arange(0, (n + 1) * m, m, dtype=np.int64)
+    i = np.tile(np.arange(m, dtype=np.int64), n)
+    return m, n, p, i, rng.standard_normal(m * n)

@@ -102,7 +102,43 @@ def test_engine_matches_oracle_synthetic(engine, oracle, gen, order, tolmode):
     ref.free_qr(QR); ref.free_sparse(A); ref.close()
 
 
-@pytest.mark.parametrize("name,order", [("dwt_992", 2), ("t2d_q9", 2), ("bcsstk14", 1), ("epb1", 1), ("ex18", 1)])
+@pytest.mark.parametrize("gen,order", [(("lap3d", 30), 2), (("lap2d", 300), 2), (("tall", 40000, 10000), 1)])
+def test_large_fronts_two_level_blocking(gen, order):
+    """Fronts big enough for the two-level (128-column outer block, K = 128 DMMA update) path of
+    kernels_wide.cuh: same integer structure and R (up to row signs) as the reference's CPU
+    qr_factorize, and as the engine's own single-level path (flags bit 1)."""
+    if not R.have_reference():
+        pytest.skip("needs oracle/_ref for the symbolic analysis")
+    ref = R.Reference()
+    ref.set_backend("reference")
+    if gen[0] == "lap2d":
+        m, n, p, i, x = M.laplacian_2d(gen[1])
+    elif gen[0] == "lap3d":
+        m, n, p, i, x = M.laplacian_3d(gen[1])
+    else:
+        m, n, p, i, x = M.tall_banded_random(gen[1], gen[2], draws=8, halfwidth=64, seed=4)
+    A = ref.csc_from_arrays(m, n, p, i, x)
+    tol = ref.default_tol(A)
+    QR = ref.sparseqr(A, order, tol, grain=1.0, tap=True)
+    sym = ref.symbolic(QR)
+    refnum = ref.numeric(QR, sym)
+    At, ttol, ntol = ref.tapped()
+    fm, fn = np.asarray(sym.Fm[: sym.nf]), np.diff(sym.Rp[: sym.nf + 1])
+    assert (fm >= 1024).any() and (fn >= 384).any(), "input too small to reach the two-level path"
+    e = sq.Engine(0)
+    got = {}
+    for flags in (0, 2):
+        e.set_options(flags=flags)
+        got[flags] = run_engine(e, sym, At, ttol, ntol)
+        R.assert_numeric_parity(sym, At, got[flags], refnum, f"{gen} flags {flags} vs reference")
+        assert got[flags].flops == R.reference_flops(sym, got[flags])
+    assert not R.structural_equal(got[0], got[2], sym)
+    e.close()
+    ref.free_qr(QR); ref.free_sparse(A); ref.close()
+
+
+@pytest.mark.parametrize("name,order", [("dwt_992", 2), ("t2d_q9", 2), ("bcsstk14", 1), ("epb1", 1), ("ex18", 1),
+                                        ("cvxqp3", 1)])
 def test_dropin_through_reference_api(name, order):
     """The reference's SparseQR() with the B200 qr_factorize interposed: same integer structure
     as the CPU reference, solve residual (qrtest.c check_error) and Q orthogonality through the
