@@ -61,10 +61,17 @@ struct DNum
     unsigned long long *rcursor ;   // bump pointer of the R arena
     I32 *sumrank, *maxfrank, *maxfm, *rank1 ;
     double *flops ;         // [0] reference flop count, [1] trailing-update flops, [2] assembly bytes
+    I32 *lvlstat ;          // [4] max actual # rows over the fronts of the level (k_level_maxfm)
     unsigned long long *dbg ;   // [64] cycle counters (only written when built with -DSTMQR_PANEL_TIMING)
     I32 *W ;                // [m] row permutation workspace of qr_hpinv
     const unsigned char *owned ;    // [nf] or null: fronts factorized on this GPU (tree partitioned over GPUs)
     I64 *base1, *base2 ;    // [nf] scans used by qr_hpinv
+    // exchange area of k_panel_grid (fronts too tall for a cluster of shared-memory slabs)
+    double *gridrec ;       // [slots][2][148][64]
+    int4 *gridll ;          // [slots][2][148][64] the records as {lo, tag, hi, tag} lines
+    double *gridred ;       // [slots][2][148]
+    unsigned *gridctr ;     // [slots][GRID_CTR_STRIDE] arrival counters, zero between launches
+    I32 *griderr ;
     // two-level blocked path of the large fronts (kernels_wide.cuh); sized for the widest such level
     double *wVb ;           // [2][slots][ldv*128]   clean Householder vectors of the current outer block
     double *wTbt ;          // [2][slots][128*128]   T of the outer block, transposed

@@ -109,6 +109,23 @@ __global__ void k_front_setup (const I32 *__restrict__ fronts, DSym S, DNum N)
     }
 }
 
+// max actual # rows over the fronts of one level (read back by the host for the large-front levels)
+__global__ void k_level_maxfm (const I32 *__restrict__ fronts, I32 count, DNum N)
+{
+    __shared__ I32 sh [32] ;
+    I32 m = 0 ;
+    for (I32 i = threadIdx.x ; i < count ; i += blockDim.x) m = max (m, N.Hm [fronts [i]]) ;
+    for (int o = 16 ; o > 0 ; o >>= 1) m = max (m, __shfl_xor_sync (STMQR_FULL_MASK, m, o)) ;
+    if ((threadIdx.x & 31) == 0) sh [threadIdx.x >> 5] = m ;
+    __syncthreads () ;
+    if (threadIdx.x < 32)
+    {
+        m = (threadIdx.x < (blockDim.x >> 5)) ? sh [threadIdx.x] : 0 ;
+        for (int o = 16 ; o > 0 ; o >>= 1) m = max (m, __shfl_xor_sync (STMQR_FULL_MASK, m, o)) ;
+        if (threadIdx.x == 0) N.lvlstat [0] = m ;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Numeric assembly: F <- 0, scatter the rows of S, extend-add the children's packed C blocks
 // (qr_assemble, SparseQR_factorize.c:1176-1281).  grid = (fronts of the level, column slices);

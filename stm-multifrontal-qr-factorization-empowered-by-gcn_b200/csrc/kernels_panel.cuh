@@ -308,10 +308,72 @@ __host__ __device__ constexpr int panel_scratch_doubles (int nw)
         + 4 * PANEL_MAX ;               // taus, stair in, stair out, flags (as doubles/ints)
 }
 
+// Exchange between the CTAs of one front when they are NOT a cluster (k_panel_grid: fronts too tall
+// for 8 shared-memory slabs): records in global memory (L2), a monotone arrival counter as barrier.
+// All CTAs of the front are resident at the same time (<= 1 CTA per SM, grid <= # SMs).
+struct GridComm
+{
+    double *rec ;           // [2][G][64]  per step parity and CTA: dot[32], rowg[32]
+    double *red ;           // [2][G]      rare rescale path
+    unsigned *ctr ;         // 4 arrival counters of this front, 32 words apart
+    unsigned G ;            // CTAs taking part
+    unsigned cr ;           // my rank
+    unsigned epoch ;        // barriers passed
+    int4 *ll ;              // [2][G][64] the same records as 16-byte lines {lo, tag, hi, tag}: data and
+                            // flag travel together (8-byte stores are atomic), so a step needs no
+                            // barrier: readers poll the lines until the tag of the step shows up
+    unsigned tagbase ;      // launch sequence number * 64
+} ;
+__device__ __forceinline__ void ll_store (int4 *p, const double v, const unsigned tag)
+{
+    const unsigned lo = (unsigned) __double2loint (v), hi = (unsigned) __double2hiint (v) ;
+    asm volatile ("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l" (p), "r" (lo), "r" (tag), "r" (hi), "r" (tag) : "memory") ;
+}
+__device__ __forceinline__ bool ll_load (const int4 *p, const unsigned tag, double &v)
+{
+    unsigned lo, f1, hi, f2 ;
+    asm volatile ("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r" (lo), "=r" (f1), "=r" (hi), "=r" (f2) : "l" (p) : "memory") ;
+    v = __hiloint2double ((int) hi, (int) lo) ;
+    return (f1 == tag) && (f2 == tag) ;
+}
+__device__ __forceinline__ unsigned ld_relaxed_u32 (const unsigned *p)
+{
+    unsigned v ;
+    asm volatile ("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r" (v) : "l" (p) : "memory") ;
+    return v ;
+}
+__device__ __forceinline__ void red_add_u32 (unsigned *p, unsigned v)
+{
+    asm volatile ("red.relaxed.gpu.global.add.u32 [%0], %1;" :: "l" (p), "r" (v) : "memory") ;
+}
+__device__ __forceinline__ void grid_barrier (GridComm &gc)
+{
+    __syncthreads () ;
+    gc.epoch++ ;
+    if (threadIdx.x == 0)
+    {
+        // arrivals are spread over 4 counters in different L2 sectors (atomics on one address
+        // serialise at ~27 cycles each); the waiter polls their sum
+        // (relaxed polling, one fence on each side: acquire loads would invalidate L1 every time)
+        __threadfence () ;
+        red_add_u32 (gc.ctr + 32 * (gc.cr & 3), 1u) ;
+        const unsigned target = gc.epoch * gc.G ;
+        for ( ; ; )
+        {
+            const unsigned a = ld_relaxed_u32 (gc.ctr), b = ld_relaxed_u32 (gc.ctr + 32),
+                c = ld_relaxed_u32 (gc.ctr + 64), d = ld_relaxed_u32 (gc.ctr + 96) ;
+            if (a + b + c + d >= target) break ;
+        }
+        __threadfence () ;
+    }
+    __syncthreads () ;
+}
+constexpr int GRID_CTR_STRIDE = 512 ;      // unsigned per front: start barrier [0..128), step barrier [128..256), exit [256]
+
 // all-reduce of one double over the CTA's warps and then over the cluster (rare rescale path)
-template <int NW, bool ISMAX>
-__device__ __forceinline__ double panel_allreduce (cg::cluster_group &cluster, const unsigned ECS, double v,
-    double *red, PanelXch &X)
+template <int NW, bool ISMAX, bool GRID>
+__device__ __forceinline__ double panel_allreduce (cg::cluster_group &cluster, GridComm &gc, const unsigned ECS, double v,
+    double *red, PanelXch &X, const int par)
 {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5 ;
     if (lane == 0) red [w] = v ;
@@ -320,7 +382,19 @@ __device__ __forceinline__ double panel_allreduce (cg::cluster_group &cluster, c
 #pragma unroll
     for (int ww = 1 ; ww < NW ; ww++) v = ISMAX ? fmax (v, red [ww]) : (v + red [ww]) ;
     __syncthreads () ;
-    if (ECS > 1)
+    if (ECS > 1 && GRID)
+    {
+        if (tid == 0) __stcg (gc.red + par * gc.G + gc.cr, v) ;
+        grid_barrier (gc) ;
+        v = __ldcg (gc.red + par * gc.G) ;
+        for (unsigned r = 1 ; r < ECS ; r++)
+        {
+            const double u = __ldcg (gc.red + par * gc.G + r) ;
+            v = ISMAX ? fmax (v, u) : (v + u) ;
+        }
+        grid_barrier (gc) ;
+    }
+    else if (ECS > 1)
     {
         if (tid == 0) X.ssq2 = v ;
         cluster.sync () ;
@@ -335,8 +409,8 @@ __device__ __forceinline__ double panel_allreduce (cg::cluster_group &cluster, c
     return v ;
 }
 
-template <int NW>
-__device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, const unsigned ECS,
+template <int NW, bool GRID>
+__device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, GridComm &gc, const unsigned ECS,
     const I32 slab_cap, const I32 ldp, const LevelArgs &L, const DSym &S, const DNum &N,
     const I32 slot, const I32 f, const I32 k1, const I32 k2, const I32 parity, const I32 lrow0,
     const I32 nloc, const I32 rbeg, const I32 RL, const I32 rend, PanelXch *xch, I32 *cols, I32 *tq)
@@ -352,7 +426,7 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
     I32 *const sto = stl + PANEL_MAX ;                  // [32] new Stair, -1 = column not processed
     double *const tauo = taus + 2 * PANEL_MAX ;         // [32] Tau out
 
-    const unsigned cr = (ECS > 1) ? cluster.block_rank () : 0 ;
+    const unsigned cr = (ECS > 1) ? (GRID ? gc.cr : cluster.block_rank ()) : 0 ;
     const int tid = threadIdx.x ;
     constexpr int nt = NW * 32 ;
     const int lane = tid & 31, w = tid >> 5 ;
@@ -446,7 +520,58 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
             s = pv [0] ;
         }
         double rgv = (cr == owner) ? prow [par * PANEL_MAX + lane] : 0.0 ;
-        if (ECS > 1)
+        if (ECS > 1 && GRID)
+        {
+            // one record per CTA in global memory (L2), summed in CTA order by warp 0 of every CTA:
+            // bitwise identical decisions everywhere
+            int4 *rec = gc.ll + (I64) par * gc.G * 64 ;
+            const unsigned tag = gc.tagbase + (unsigned) step ;
+            if (w == 0)
+            {
+                ll_store (rec + cr * 64 + lane, s, tag) ;
+                if (cr == owner) ll_store (rec + cr * 64 + 32 + lane, rgv, tag) ;
+            }
+            __syncthreads () ;          // part[par] is overwritten below: everybody has read its partials
+            {
+                // warp w gathers the records w, w+NW, ...: all loads in flight at once, polled until the
+                // tag of this step shows up; summed in a fixed order, the same in every CTA
+                static_assert (!GRID || NW * 10 >= 148, "records per warp") ;
+                double v [10] ;
+                bool ok ;
+                do
+                {
+                    ok = true ;
+#pragma unroll
+                    for (int j = 0 ; j < 10 ; j++)
+                    {
+                        const unsigned r = (unsigned) (w + NW * j) ;
+                        v [j] = 0.0 ;
+                        if (r < ECS) ok &= ll_load (rec + r * 64 + lane, tag, v [j]) ;
+                    }
+                } while (!__all_sync (STMQR_FULL_MASK, ok)) ;
+                if (w == 0)
+                {
+                    double rv ;
+                    while (!__all_sync (STMQR_FULL_MASK, ll_load (rec + owner * 64 + 32 + lane, tag, rv))) { }
+                    prow [par * PANEL_MAX + lane] = rv ;
+                }
+                part [(par * NW + w) * PANEL_MAX + lane] = (((v [0] + v [1]) + (v [2] + v [3])) + ((v [4] + v [5]) + (v [6] + v [7])))
+                    + (v [8] + v [9]) ;
+            }
+            __syncthreads () ;
+            {
+                double pv [NW] ;
+#pragma unroll
+                for (int ww = 0 ; ww < NW ; ww++) pv [ww] = part [(par * NW + ww) * PANEL_MAX + lane] ;
+#pragma unroll
+                for (int h = NW / 2 ; h > 0 ; h >>= 1)
+#pragma unroll
+                    for (int ww = 0 ; ww < h ; ww++) pv [ww] += pv [ww + h] ;
+                s = pv [0] ;
+            }
+            rgv = prow [par * PANEL_MAX + lane] ;
+        }
+        else if (ECS > 1)
         {
             // one record per CTA through distributed shared memory; only warp 0 talks to the peers
             // (DSMEM bandwidth is ~20 B/clk per SM) and re-publishes the totals locally
@@ -456,14 +581,14 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
             if (w == 0)
             {
                 // same order in every CTA: bitwise identical decisions
-                double dv [8] ;
+                double dv [16] ;
 #pragma unroll
-                for (unsigned r = 0 ; r < 8 ; r++)
-                    dv [r] = cluster.map_shared_rank (&X, (r < ECS) ? r : 0)->dot [lane] ;
+                for (unsigned r = 0 ; r < 16 ; r++)
+                    dv [r] = (r < 8 || ECS > 8) ? cluster.map_shared_rank (&X, (r < ECS) ? r : 0)->dot [lane] : 0.0 ;
                 rgv = cluster.map_shared_rank (&X, owner)->rowg [lane] ;
                 s = 0 ;
 #pragma unroll
-                for (unsigned r = 0 ; r < 8 ; r++) if (r < ECS) s += dv [r] ;
+                for (unsigned r = 0 ; r < 16 ; r++) if (r < ECS) s += dv [r] ;
                 part [(par * NW) * PANEL_MAX + lane] = s ;      // part[par] is dead after the block reduction
                 prow [par * PANEL_MAX + lane] = rgv ;
             }
@@ -487,13 +612,13 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
                 // squares (dnrm2 semantics).  The decision is uniform over the cluster.
                 double mx = 0 ;
                 for (I32 i = ifirst ; i < i1 ; i += NW) mx = fmax (mx, fabs (xc [i])) ;
-                mx = panel_allreduce<NW, true> (cluster, ECS, mx, red, xch [par]) ;
+                mx = panel_allreduce<NW, true, GRID> (cluster, gc, ECS, mx, red, xch [par], par) ;
                 if (mx > 0)
                 {
                     const double inv = 1.0 / mx ;
                     double s2 = 0 ;
                     for (I32 i = ifirst ; i < i1 ; i += NW) { const double v = xc [i] * inv ; s2 += v * v ; }
-                    s2 = panel_allreduce<NW, false> (cluster, ECS, s2, red + NW, xch [par]) ;
+                    s2 = panel_allreduce<NW, false, GRID> (cluster, gc, ECS, s2, red + NW, xch [par], par) ;
                     nrm = hypot (alpha, mx * sqrt (s2)) ;
                     ss = 1.0 ;
                 }
@@ -739,7 +864,8 @@ __global__ void __launch_bounds__ (NT, MINB) k_panel_cluster (LevelArgs L, DSym 
             }
         }
         __syncthreads () ;
-        panel_columns_smem<NW> (cluster, ECS, slab_cap, ldp, L, S, N, slot, f, k1, k2, parity, lrow0, nloc, g1,
+        GridComm nogrid {} ;
+        panel_columns_smem<NW, false> (cluster, nogrid, ECS, slab_cap, ldp, L, S, N, slot, f, k1, k2, parity, lrow0, nloc, g1,
             RL, rend, xch, cols, tq) ;
     }
     else
@@ -750,6 +876,96 @@ __global__ void __launch_bounds__ (NT, MINB) k_panel_cluster (LevelArgs L, DSym 
     if (ECS == 1) return ;
     // nobody may leave while a peer can still read its exchange records
     cluster.sync () ;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same panel factorization for fronts whose row window does not fit the 8 shared-memory slabs
+// of a cluster: G CTAs per front (G x fronts <= # SMs, one CTA per SM: all resident), each with its
+// slab in shared memory, exchanging through global memory with an arrival-counter barrier.
+// grid = G x nfronts, slot = slot0 + blockIdx.x / G.  ctr: 2 counters per slot, zero on entry (the
+// last CTA to leave resets them).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__ (512, 1) k_panel_grid (LevelArgs L, DSym S, DNum N, I32 k1, I32 PB, I32 parity,
+    I32 slab_cap, I32 G, I32 slot0, unsigned seq)
+{
+    extern __shared__ double slab [] ;
+    __shared__ PanelXch xch [2] ;
+    __shared__ I32 cols [PANEL_MAX], tq [PANEL_MAX] ;
+    constexpr int NW = 16 ;
+    cg::cluster_group cluster = cg::this_cluster () ;
+    const I32 slot = slot0 + blockIdx.x / G ;
+    const unsigned cr = blockIdx.x % G ;
+    const I32 f = L.fronts [slot] ;
+    const I32 p1 = S.Rp [f], fn = S.Rp [f+1] - p1 ;
+    const int tid = threadIdx.x ;
+    const I32 slotp = parity * L.count + slot ;
+    unsigned *ctr = N.gridctr + (I64) GRID_CTR_STRIDE * slot ;
+
+    // every CTA of the front reads the front's state before any of them may change it
+    const I32 done0 = N.done [slot] ;
+    const I32 g1 = N.g [slot] ;
+    const I32 stlast = (k1 < fn) ? N.stair [p1 + min (fn, k1 + PB) - 1] : 0 ;
+    const I32 fm = N.Hm [f] ;
+    GridComm g0 ; g0.rec = nullptr ; g0.red = nullptr ; g0.ctr = ctr ; g0.G = (unsigned) G ; g0.cr = cr ; g0.epoch = 0 ;
+    g0.ll = nullptr ; g0.tagbase = 0 ;
+    const I32 k2 = min (fn, k1 + PB) ;
+    const I32 np = k2 - k1 ;
+    const I32 rend = min (fm, max (stlast, g1 + np)) ;
+    const I32 nrows = max (rend - g1, 0) ;
+    // CTAs that take part: a step costs ~5.7 cycles per slab row (shared-memory sweeps) plus
+    // ~27/4 cycles per arriving CTA (L2 atomics): ECS ~ sqrt (0.84 nrows), at least what fits
+    const I32 rlcap = max (4, (slab_cap / max (np, 1) - 4) & ~3) ;
+    const I32 ecs_fit = (nrows + rlcap - 1) / rlcap ;
+    const I32 ecs_opt = (I32) sqrtf (0.84f * (float) nrows) ;
+    unsigned ECS = (unsigned) max (1, min ((I32) G, max (ecs_fit, ecs_opt))) ;
+    const bool idle = (k1 >= fn || done0) ;
+    const I32 RL = max (4, (((nrows + (I32) ECS - 1) / (I32) ECS) + 3) & ~3) ;
+    const I32 ldp = RL | 1 ;
+    const bool fits = ((I64) ldp * np <= (I64) slab_cap) ;
+    // the staircase of the panel's columns is read inside panel_columns_smem: stage it before the barrier
+    grid_barrier (g0) ;
+    if (!idle && fits && cr < ECS)
+    {
+        const I32 lrow0 = g1 + (I32) cr * RL ;
+        const I32 nloc = max (0, min (rend - lrow0, RL)) ;
+        double *F = N.F + S.Foff [f] ;
+        const I64 ld = fm ;
+        {
+            const int lane = tid & 31, w = tid >> 5 ;
+            for (I32 c = w ; c < np ; c += NW)
+            {
+                const double *src = F + (I64) (k1 + c) * ld + lrow0 ;
+                double *dst = slab + (I64) c * ldp ;
+#pragma unroll 4
+                for (I32 i = lane ; i < nloc ; i += 32) dst [i] = __ldcg (src + i) ;
+            }
+        }
+        __syncthreads () ;
+        GridComm gc ;
+        gc.rec = N.gridrec + (I64) slot * (2 * 148 * 64) ;
+        gc.red = N.gridred + (I64) slot * (2 * 148) ;
+        gc.ctr = ctr + 128 ; gc.G = ECS ; gc.cr = cr ; gc.epoch = 0 ;
+        gc.ll = N.gridll + (I64) slot * (2 * 148 * 64) ; gc.tagbase = seq * 64u ;
+        panel_columns_smem<NW, true> (cluster, gc, ECS, slab_cap, ldp, L, S, N, slot, f, k1, k2, parity, lrow0, nloc, g1,
+            RL, rend, xch, cols, tq) ;
+    }
+    else if (cr == 0 && tid == 0)
+    {
+        N.pnl_nv [slotp] = 0 ;
+        if (!idle && !fits) atomicExch (N.griderr, 1) ;      // host sized G too small: reported as an error
+    }
+    // the last CTA of the front to leave resets the counters for the next launch
+    __syncthreads () ;
+    if (tid == 0)
+    {
+        __threadfence () ;
+        if (atomicAdd (ctr + 256, 1u) == (unsigned) G - 1)
+        {
+            for (int j = 0 ; j < 8 ; j++) ctr [32 * j] = 0 ;
+            ctr [256] = 0 ;
+            __threadfence () ;
+        }
+    }
 }
 
 } // namespace stmqr

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__ (256) k_wide_vextract (WideArgs A, DSym S, DNu
 // ---------------------------------------------------------------------------------------------
 template <int KVT>
 __global__ void __launch_bounds__ (256) k_wide_vtc (WideArgs A, DSym S, DNum N, I32 mode, I32 p, I32 cbeg,
-    I32 cend)
+    I32 cend, I32 nct_in)
 {
     constexpr int KV = PANEL_MAX * KVT ;
     constexpr int STAGE = (KV + W_NC) * W_LDC ;
@@ -142,18 +142,22 @@ __global__ void __launch_bounds__ (256) k_wide_vtc (WideArgs A, DSym S, DNum N, 
     const I32 g0 = blk [0], mr = blk [1] ;
     const I32 f = A.fronts [slot] ;
     const I32 fn = S.Rp [f+1] - S.Rp [f] ;
-    const I32 nct = gridDim.x / A.nsplit ;
-    const I32 ct = blockIdx.x % nct, split = blockIdx.x / nct ;
+    const I32 nct = (KVT == 1) ? nct_in + (p * PANEL_MAX + W_NC - 1) / W_NC : nct_in ;     // column tiles per split
+    I32 ct = blockIdx.x % nct ;
+    const I32 split = blockIdx.x / nct ;
     const I32 rbeg = split * A.rs ;
     if (rbeg >= mr) return ;
     const I32 rend = min (mr, rbeg + A.rs) ;
-    const I32 clim = (mode == WIDE_GRAM) ? WB : min (cend, fn) ;
+    // WIDE_INNER launches carry extra column tiles (ct >= nct_in) that multiply V_p with the Householder
+    // vectors of the EARLIER panels of the block: the Gram blocks k_wide_tmerge needs, for free
+    if (mode == WIDE_INNER && ct >= nct_in) { mode = WIDE_GRAM ; ct -= nct_in ; cbeg = 0 ; }
+    const I32 clim = (mode == WIDE_GRAM) ? ((KVT == 1) ? p * PANEL_MAX : WB) : min (cend, fn) ;
     const I32 c0 = cbeg + ct * W_NC ;
     if (c0 >= clim) return ;
     const I32 ncol = min (W_NC, clim - c0) ;
     const I64 fm = N.Hm [f] ;
     const double *Vb = wide_vb (A, N, slot) ;
-    const double *Va = Vb + (I64) ((mode == WIDE_INNER) ? p * PANEL_MAX : 0) * A.ldv ;
+    const double *Va = Vb + (I64) ((KVT == 1) ? p * PANEL_MAX : 0) * A.ldv ;
     const double *Bp = (mode == WIDE_GRAM) ? Vb : (N.F + S.Foff [f] + g0) ;
     const I64 ldb = (mode == WIDE_GRAM) ? (I64) A.ldv : fm ;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5 ;
@@ -226,6 +230,12 @@ __global__ void __launch_bounds__ (256) k_wide_vtc (WideArgs A, DSym S, DNum N, 
     double *out ;
     I64 ldo ;
     if (mode == WIDE_OUTER) { out = N.wWp + ((I64) slot * A.nsplit + split) * ((I64) A.ncmax * WB) + (I64) c0 * WB ; ldo = WB ; }
+    else if (mode == WIDE_GRAM && KVT == 1)
+    {
+        // (V_p' V_prev)(q, c), c < 32 p:  [slot][split][p-1][c][q]
+        out = N.wGp + (((I64) slot * A.nsplit + split) * (WB_PANELS - 1) + (p - 1)) * (96 * PANEL_MAX) + (I64) c0 * PANEL_MAX ;
+        ldo = PANEL_MAX ;
+    }
     else if (mode == WIDE_GRAM) { out = N.wGp + ((I64) slot * A.nsplit + split) * (WB * WB) + (I64) c0 * WB ; ldo = WB ; }
     else { out = N.wWpi + (((I64) slot * A.nsplit + split) * WB + (c0 - cbeg)) * PANEL_MAX ; ldo = PANEL_MAX ; }
     if (KVT == 1)
@@ -297,9 +307,20 @@ __global__ void __launch_bounds__ (256) k_wide_wt (WideArgs A, DSym S, DNum N, I
     for (int e = tid ; e < NCW * KV ; e += 256)
     {
         const int cc = e / KV, q = e % KV ;
-        double s = 0 ;
-        if (cc < ncol) for (I32 sp = 0 ; sp < nsp ; sp++) s += Wp [sp * sstride + (I64) cc * KV + q] ;
-        Ws [cc * (KV + 1) + q] = s ;
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0 ;
+        if (cc < ncol)
+        {
+            const double *src = Wp + (I64) cc * KV + q ;
+            I32 sp = 0 ;
+            for ( ; sp + 3 < nsp ; sp += 4)
+            {
+                const double a = __ldcg (src + sp * sstride), b = __ldcg (src + (sp+1) * sstride),
+                    c = __ldcg (src + (sp+2) * sstride), d = __ldcg (src + (sp+3) * sstride) ;
+                s0 += a ; s1 += b ; s2 += c ; s3 += d ;
+            }
+            for ( ; sp < nsp ; sp++) s0 += __ldcg (src + sp * sstride) ;
+        }
+        Ws [cc * (KV + 1) + q] = (s0 + s1) + (s2 + s3) ;
     }
     __syncthreads () ;
     // thread (q', column group): out(q', c) = -sum_q T(q, q') Wsum(q, c)
@@ -310,13 +331,21 @@ __global__ void __launch_bounds__ (256) k_wide_wt (WideArgs A, DSym S, DNum N, I
     for (int j = 0 ; j < CPT ; j++) acc [j] = 0 ;
     if (mode == WIDE_OUTER)
     {
-        const double *Tt = N.wTbt + ((I64) A.buf * A.count + slot) * (WB * WB) ;    // Tt[q' + q*128] = T(q,q')
-#pragma unroll 4
-        for (int q = 0 ; q < KV ; q++)
+        // Tt[q' + q*128] = T(q,q'): 16 rows q at a time through shared memory (coalesced, conflict-free)
+        __shared__ double Tsm [16 * WB] ;
+        const double *Tt = N.wTbt + ((I64) A.buf * A.count + slot) * (WB * WB) ;
+        for (int q0 = 0 ; q0 < KV ; q0 += 16)
         {
-            const double t = __ldg (Tt + qp + q * WB) ;
+            for (int e = tid ; e < 16 * WB ; e += 256) Tsm [e] = __ldcg (Tt + q0 * WB + e) ;
+            __syncthreads () ;
+#pragma unroll 8
+            for (int q = 0 ; q < 16 ; q++)
+            {
+                const double t = Tsm [q * WB + (qp & (WB - 1))] ;
 #pragma unroll
-            for (int j = 0 ; j < CPT ; j++) acc [j] = fma (t, Ws [(cg * CPT + j) * (KV + 1) + q], acc [j]) ;
+                for (int j = 0 ; j < CPT ; j++) acc [j] = fma (t, Ws [(cg * CPT + j) * (KV + 1) + q0 + q], acc [j]) ;
+            }
+            __syncthreads () ;
         }
     }
     else
@@ -340,6 +369,57 @@ __global__ void __launch_bounds__ (256) k_wide_wt (WideArgs A, DSym S, DNum N, I
     }
 }
 
+// The same for the update inside the block (32 reflectors of panel p, <= 96 columns): 8 columns per
+// CTA, one thread per entry; the partial sums over the row splits are independent loads.
+__global__ void __launch_bounds__ (256) k_wide_wt_inner (WideArgs A, DSym S, DNum N, I32 p, I32 cbeg, I32 cend)
+{
+    __shared__ double Ws [8][PANEL_MAX + 1] ;
+    __shared__ double Ts [PANEL_MAX][PANEL_MAX + 1] ;
+    const I32 slot = blockIdx.y ;
+    const I32 nvp = N.pnl_nv [p * A.count + slot] ;
+    if (nvp == 0) return ;
+    const I32 *blk = wide_blk (A, N, slot) ;
+    const I32 mr = blk [1] ;
+    const I32 f = A.fronts [slot] ;
+    const I32 fn = S.Rp [f+1] - S.Rp [f] ;
+    const I32 clim = min (cend, fn) ;
+    const I32 c0 = cbeg + blockIdx.x * 8 ;
+    if (c0 >= clim) return ;
+    const I32 nsp = min (A.nsplit, (mr + A.rs - 1) / A.rs) ;
+    const int tid = threadIdx.x, cc = tid >> 5, q = tid & 31 ;
+    const double *Tg = N.Tws + (I64) (p * A.count + slot) * (PANEL_MAX * PANEL_MAX) ;   // T(j,i) at Tg[j + 32 i]
+    for (int e = tid ; e < PANEL_MAX * PANEL_MAX ; e += 256)
+    {
+        const int j = e & 31, i = e >> 5 ;
+        Ts [j][i] = (j <= i && i < nvp) ? Tg [e] : 0.0 ;
+    }
+    const bool live = (c0 + cc < clim) ;
+    const double *Wp = N.wWpi + ((I64) slot * A.nsplit * WB + (c0 - cbeg + cc)) * PANEL_MAX + q ;
+    const I64 sstride = (I64) WB * PANEL_MAX ;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0 ;
+    if (live)
+    {
+        I32 sp = 0 ;
+        for ( ; sp + 3 < nsp ; sp += 4)
+        {
+            const double a = __ldcg (Wp + sp * sstride), b = __ldcg (Wp + (sp+1) * sstride),
+                c = __ldcg (Wp + (sp+2) * sstride), d = __ldcg (Wp + (sp+3) * sstride) ;
+            s0 += a ; s1 += b ; s2 += c ; s3 += d ;
+        }
+        for ( ; sp < nsp ; sp++) s0 += __ldcg (Wp + sp * sstride) ;
+    }
+    Ws [cc][q] = (s0 + s1) + (s2 + s3) ;
+    __syncthreads () ;
+    double a0 = 0, a1 = 0 ;
+#pragma unroll
+    for (int j = 0 ; j < PANEL_MAX ; j += 2)
+    {
+        a0 = fma (Ts [j][q], Ws [cc][j], a0) ;          // T(j, q), zero for j > q
+        a1 = fma (Ts [j+1][q], Ws [cc][j+1], a1) ;
+    }
+    if (live) N.wW2i [((I64) slot * WB + (c0 - cbeg + cc)) * PANEL_MAX + q] = -(a0 + a1) ;
+}
+
 // ---------------------------------------------------------------------------------------------
 // C(rows of the block, cbeg..cend) += V W2.   grid = (column tiles of 64 x row tiles of 128, fronts).
 // ---------------------------------------------------------------------------------------------
@@ -349,7 +429,7 @@ __global__ void __launch_bounds__ (256) k_wide_apply (WideArgs A, DSym S, DNum N
 {
     constexpr int KV = PANEL_MAX * KVT ;
     constexpr int STAGE = PANEL_MAX * W_LDV + W_NC * W_LDC ;
-    constexpr int NST = (KVT == 1) ? 1 : W_NST ;
+    constexpr int NST = (KVT == 1) ? 1 : 2 ;        // 2 stages = 104 KB: two CTAs per SM overlap fill and drain
     extern __shared__ double sm [] ;
     const I32 slot = blockIdx.y ;
     const I32 *blk = wide_blk (A, N, slot) ;
@@ -401,7 +481,7 @@ __global__ void __launch_bounds__ (256) k_wide_apply (WideArgs A, DSym S, DNum N
     }
     if (NST == 1) { issue (sm, 0) ; cp_async_commit () ; }
 
-    double acc [4][4][2] ;
+    double acc [4][4][2], cold [4][4][2] ;
 #pragma unroll
     for (int mi = 0 ; mi < 4 ; mi++)
 #pragma unroll
@@ -410,7 +490,8 @@ __global__ void __launch_bounds__ (256) k_wide_apply (WideArgs A, DSym S, DNum N
             for (int e = 0 ; e < 2 ; e++)
             {
                 const int r = wr * 32 + mi * 8 + grp, c = wc * 32 + ni * 8 + tig * 2 + e ;
-                acc [mi][ni][e] = (r0 + r < mr && c < ncol) ? __ldcg (C + r + (I64) c * fm) : 0.0 ;
+                acc [mi][ni][e] = 0.0 ;
+                cold [mi][ni][e] = (r0 + r < mr && c < ncol) ? __ldcg (C + r + (I64) c * fm) : 0.0 ;
             }
 
     for (int kk = 0 ; kk < KVT ; kk++)
@@ -448,12 +529,12 @@ __global__ void __launch_bounds__ (256) k_wide_apply (WideArgs A, DSym S, DNum N
             for (int e = 0 ; e < 2 ; e++)
             {
                 const int r = wr * 32 + mi * 8 + grp, c = wc * 32 + ni * 8 + tig * 2 + e ;
-                if (r0 + r < mr && c < ncol) C [r + (I64) c * fm] = acc [mi][ni][e] ;
+                if (r0 + r < mr && c < ncol) C [r + (I64) c * fm] = cold [mi][ni][e] + acc [mi][ni][e] ;
             }
 }
 template <int KVT> constexpr size_t wide_apply_smem_bytes ()
 {
-    return sizeof (double) * (size_t) (((KVT == 1) ? 1 : W_NST) * (PANEL_MAX * W_LDV + W_NC * W_LDC)) ;
+    return sizeof (double) * (size_t) (((KVT == 1) ? 1 : 2) * (PANEL_MAX * W_LDV + W_NC * W_LDC)) ;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -461,64 +542,92 @@ template <int KVT> constexpr size_t wide_apply_smem_bytes ()
 // matrix G = Vb'Vb:  T(0:32p, p) = -T(0:32p,0:32p) G(0:32p, p) T(p,p).  One CTA per front.  Output
 // transposed (k_wide_wt reads it coalesced): Tbt[q' + 128 q] = T(q,q').
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__ (256) k_wide_tmerge (WideArgs A, DSym S, DNum N)
+__global__ void __launch_bounds__ (1024) k_wide_tmerge (WideArgs A, DSym S, DNum N)
 {
     extern __shared__ double sm [] ;
     constexpr int LT = WB + 1 ;
+    constexpr int NTH = 1024 ;
     double *T = sm ;                        // [128][129]
     double *X = T + WB * LT ;               // [96][33]
     double *G = X + 96 * 33 ;               // [96][33]
     const I32 slot = blockIdx.x ;
     const I32 *blk = wide_blk (A, N, slot) ;
     if (blk [2] == 0) return ;
-    const I32 mr = blk [1] ;
-    const I32 nsp = min (A.nsplit, (mr + A.rs - 1) / A.rs) ;
+    const I32 g0 = blk [0] ;
     const int tid = threadIdx.x ;
-    for (int e = tid ; e < WB * LT ; e += 256) T [e] = 0.0 ;
+    for (int e = tid ; e < WB * LT ; e += NTH) T [e] = 0.0 ;
     __syncthreads () ;
     for (int p = 0 ; p < WB_PANELS ; p++)
     {
         const I32 nv = N.pnl_nv [p * A.count + slot] ;
         const double *Tg = N.Tws + (I64) (p * A.count + slot) * (PANEL_MAX * PANEL_MAX) ;
-        for (int e = tid ; e < PANEL_MAX * PANEL_MAX ; e += 256)
         {
+            const int e = tid ;
             const int j = e & 31, i = e >> 5 ;          // T_pp(j,i), j <= i
             if (j <= i && i < nv) T [(p * 32 + j) * LT + p * 32 + i] = Tg [j + i * PANEL_MAX] ;
         }
     }
     __syncthreads () ;
-    const double *Gp = N.wGp + (I64) slot * A.nsplit * (WB * WB) ;
+    // Gram blocks (V_p' V_prev), partial per row split, written by the inner k_wide_vtc launches
+    const double *Gp = N.wGp + (I64) slot * A.nsplit * (WB_PANELS - 1) * (96 * PANEL_MAX) ;
+    const I64 sstride = (I64) (WB_PANELS - 1) * (96 * PANEL_MAX) ;
     for (int p = 1 ; p < WB_PANELS ; p++)
     {
         const int np = 32 * p ;
-        for (int e = tid ; e < np * 32 ; e += 256)
+        const I32 nvp = N.pnl_nv [p * A.count + slot] ;
+        if (nvp == 0) continue ;                        // uniform over the CTA: block column stays zero
+        const I32 mrp = N.pnl_tend [p * A.count + slot] - g0 ;
+        const I32 nsp = min (A.nsplit, (mrp + A.rs - 1) / A.rs) ;
+        for (int e = tid ; e < np * 32 ; e += NTH)
         {
-            const int i = e % np, l = e / np ;          // G(i, 32p + l)
-            double s = 0 ;
-            for (I32 sp = 0 ; sp < nsp ; sp++) s += Gp [(I64) sp * (WB * WB) + (np + l) * WB + i] ;
-            G [i * 33 + l] = s ;
+            const int l = e & 31, i = e >> 5 ;          // G(i, 32p + l) = (V_p' V_prev)(l, i)
+            const double *src = Gp + (I64) (p - 1) * (96 * PANEL_MAX) + i * PANEL_MAX + l ;
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0 ;
+            I32 sp = 0 ;
+            for ( ; sp + 3 < nsp ; sp += 4)
+            {
+                const double a = __ldcg (src + sp * sstride), b = __ldcg (src + (sp+1) * sstride),
+                    c = __ldcg (src + (sp+2) * sstride), d = __ldcg (src + (sp+3) * sstride) ;
+                s0 += a ; s1 += b ; s2 += c ; s3 += d ;
+            }
+            for ( ; sp < nsp ; sp++) s0 += __ldcg (src + sp * sstride) ;
+            G [i * 33 + l] = (s0 + s1) + (s2 + s3) ;
         }
         __syncthreads () ;
-        for (int e = tid ; e < np * 32 ; e += 256)
+        for (int e = tid ; e < np * 32 ; e += NTH)
         {
             const int j = e & 31, i = e >> 5 ;          // X(i,j) = sum_l G(i,l) T_pp(l,j)
-            double s = 0 ;
-#pragma unroll 8
-            for (int l = 0 ; l < 32 ; l++) s = fma (G [i * 33 + l], T [(np + l) * LT + np + j], s) ;
-            X [i * 33 + j] = s ;
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0 ;
+#pragma unroll
+            for (int l = 0 ; l < 32 ; l += 4)
+            {
+                s0 = fma (G [i * 33 + l], T [(np + l) * LT + np + j], s0) ;
+                s1 = fma (G [i * 33 + l + 1], T [(np + l + 1) * LT + np + j], s1) ;
+                s2 = fma (G [i * 33 + l + 2], T [(np + l + 2) * LT + np + j], s2) ;
+                s3 = fma (G [i * 33 + l + 3], T [(np + l + 3) * LT + np + j], s3) ;
+            }
+            X [i * 33 + j] = (s0 + s1) + (s2 + s3) ;
         }
         __syncthreads () ;
-        for (int e = tid ; e < np * 32 ; e += 256)
+        for (int e = tid ; e < np * 32 ; e += NTH)
         {
             const int j = e & 31, i = e >> 5 ;          // T(i, 32p+j) = -sum_{l>=i} T(i,l) X(l,j)
-            double s = 0 ;
-            for (int l = i ; l < np ; l++) s = fma (T [i * LT + l], X [l * 33 + j], s) ;
-            T [i * LT + np + j] = -s ;
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0 ;
+            int l = i ;
+            for ( ; l + 3 < np ; l += 4)
+            {
+                s0 = fma (T [i * LT + l], X [l * 33 + j], s0) ;
+                s1 = fma (T [i * LT + l + 1], X [(l + 1) * 33 + j], s1) ;
+                s2 = fma (T [i * LT + l + 2], X [(l + 2) * 33 + j], s2) ;
+                s3 = fma (T [i * LT + l + 3], X [(l + 3) * 33 + j], s3) ;
+            }
+            for ( ; l < np ; l++) s0 = fma (T [i * LT + l], X [l * 33 + j], s0) ;
+            T [i * LT + np + j] = -((s0 + s1) + (s2 + s3)) ;
         }
         __syncthreads () ;
     }
     double *Tt = N.wTbt + ((I64) A.buf * A.count + slot) * (WB * WB) ;
-    for (int e = tid ; e < WB * WB ; e += 256)
+    for (int e = tid ; e < WB * WB ; e += NTH)
     {
         const int qp = e & (WB - 1), q = e >> 7 ;
         Tt [qp + q * WB] = T [q * LT + qp] ;

@@ -8,6 +8,7 @@
 // all data-dependent shapes (fm, Cm, rank, R+H sizes) stay on the device.
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -47,11 +48,13 @@ struct Level
 } ;
 
 constexpr I32 WIDE_RS = 1024, WIDE_RS_IN = 256 ;
-constexpr I32 WIDE_MIN_ROWS = 1024, WIDE_MIN_COLS = 384, WIDE_MAX_FRONTS = 64 ;
-
-void plan_wide (Level &L)
+constexpr I32 WIDE_MIN_COLS = 384, WIDE_MAX_FRONTS = 64 ;
+// # rows of the tallest front from which a level takes the two-level path (tunable:
+// STMQR_B200_WIDE_ROWS): buffers are planned when the BOUND reaches it, the path is taken when the
+// ACTUAL # rows (known after k_front_setup) does
+void plan_wide (Level &L, I32 wide_rows)
 {
-    L.wide = (L.maxFm >= WIDE_MIN_ROWS && L.maxfn >= WIDE_MIN_COLS && L.count <= WIDE_MAX_FRONTS) ;
+    L.wide = (L.maxFm >= wide_rows && L.maxfn >= WIDE_MIN_COLS && L.count <= WIDE_MAX_FRONTS) ;
     L.ldv = ((L.maxFm + W_RT - 1) / W_RT) * W_RT + W_RT ;
     L.nsplit = (L.ldv + WIDE_RS - 1) / WIDE_RS ;
     L.nsplit_in = (L.ldv + WIDE_RS_IN - 1) / WIDE_RS_IN ;
@@ -155,6 +158,13 @@ struct stmqr_handle_s
     LevelSet ls_all, ls_sub, ls_top ;
     std::vector<I32> h_parent, h_owner, h_istop ;   // etree parent; GPU partition (set_partition)
     int nparts = 1, mypart = 0 ;
+    I32 *pin_lvl = nullptr ;                // pinned: actual max # rows of the level being processed
+    unsigned grid_seq = 0 ;                 // launch sequence number of k_panel_grid (tags of its exchange lines)
+    int nsm = 148 ;                         // SMs of the device (k_panel_grid: one CTA per SM)
+    int cluster_max = 8 ;                   // largest panel cluster (8 portable; 16 non-portable, no gain measured)
+    I32 cluster_rows = 160 ;                // do not split slabs below this many rows
+    I32 wide_rows = 4096 ;                  // levels whose tallest front has at least this many rows: two-level path
+    I32 grid_rows = 6100 ;                  // levels with taller fronts take k_panel_grid
     unsigned char *d_owned = nullptr ;
     double cur_tol = -1 ; I64 cur_ntol = 0 ;
     std::vector<I64> h_Foff, h_Coff ;
@@ -395,7 +405,7 @@ int partition_fronts (I64 nf, const int64_t *Childp, const int64_t *Child, const
 }
 
 void filter_levels (const LevelSet &all, const std::vector<unsigned char> &keep, const std::vector<I32> &Rp,
-    const std::vector<I32> &FmB, LevelSet &out)
+    const std::vector<I32> &FmB, I32 wide_rows, LevelSet &out)
 {
     out.levels.clear () ; out.fronts.clear () ;
     for (const Level &Lv : all.levels)
@@ -411,7 +421,7 @@ void filter_levels (const LevelSet &all, const std::vector<unsigned char> &keep,
             L.maxFm = std::max (L.maxFm, FmB [f]) ;
             out.fronts.push_back (f) ; L.count++ ;
         }
-        if (L.count > 0) { plan_wide (L) ; out.levels.push_back (L) ; }
+        if (L.count > 0) { plan_wide (L, wide_rows) ; out.levels.push_back (L) ; }
     }
 }
 
@@ -440,6 +450,11 @@ int stmqr_b200_create (int device, stmqr_handle *out)
     if (prop.major < 10) return STMQR_ERR_NO_DEVICE ;       // sm_100a code only, no fallback
     stmqr_handle h = new stmqr_handle_s ;
     h->device = device ;
+    h->nsm = std::min (148, prop.multiProcessorCount) ;
+    if (const char *e = getenv ("STMQR_B200_GRID_ROWS")) h->grid_rows = std::max (256, atoi (e)) ;
+    if (const char *e = getenv ("STMQR_B200_WIDE_ROWS")) h->wide_rows = std::max (256, atoi (e)) ;
+    if (const char *e = getenv ("STMQR_B200_CLUSTER_MAX")) h->cluster_max = std::max (1, std::min (16, atoi (e))) ;
+    if (const char *e = getenv ("STMQR_B200_CLUSTER_ROWS")) h->cluster_rows = std::max (32, atoi (e)) ;
     if (const char *e = getenv ("STMQR_B200_FLAGS")) h->opt.reserved = (int32_t) strtol (e, nullptr, 0) ;
     int prio_lo = 0, prio_hi = 0 ;
     bool ok = cudaSetDevice (device) == cudaSuccess &&
@@ -454,11 +469,17 @@ int stmqr_b200_create (int device, stmqr_handle *out)
         cudaEventCreateWithFlags (&h->evN [0], cudaEventDisableTiming) == cudaSuccess &&
         cudaEventCreateWithFlags (&h->evN [1], cudaEventDisableTiming) == cudaSuccess &&
         cudaEventCreateWithFlags (&h->evW, cudaEventDisableTiming) == cudaSuccess &&
+        cudaHostAlloc ((void **) &h->pin_lvl, 4 * sizeof (I32), cudaHostAllocDefault) == cudaSuccess &&
         cudaFuncSetAttribute (k_panel_cluster<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (4)) * (int) sizeof (double)) == cudaSuccess &&
         cudaFuncSetAttribute (k_panel_cluster<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (8)) * (int) sizeof (double)) == cudaSuccess &&
         cudaFuncSetAttribute (k_panel_cluster<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (16)) * (int) sizeof (double)) == cudaSuccess &&
+        cudaFuncSetAttribute (k_panel_cluster<128, 6>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+        cudaFuncSetAttribute (k_panel_cluster<256, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+        cudaFuncSetAttribute (k_panel_cluster<512, 1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+        cudaFuncSetAttribute (k_panel_grid, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (16)) * (int) sizeof (double)) == cudaSuccess &&
         cudaFuncSetAttribute (k_update_dmma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (int) update_smem_bytes<2> ()) == cudaSuccess &&
@@ -500,6 +521,7 @@ void stmqr_b200_destroy (stmqr_handle h)
         if (h->evN [i]) cudaEventDestroy (h->evN [i]) ;
     }
     if (h->evW) cudaEventDestroy (h->evW) ;
+    if (h->pin_lvl) cudaFreeHost (h->pin_lvl) ;
     delete h->pool ;
     for (int i = 0 ; i < 2 ; i++)
     {
@@ -667,7 +689,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
         }
         h->Fcap = std::max (h->Fcap, off) ;
         h->maxLevelWidth = std::max (h->maxLevelWidth, L.count) ;
-        plan_wide (L) ;
+        plan_wide (L, h->wide_rows) ;
         h->ls_all.levels.push_back (L) ;
     }
 
@@ -728,12 +750,24 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
             w2 = std::max (w2, c * (I64) Lv.maxfn * WB) ;
             wpi = std::max (wpi, c * Lv.nsplit_in * (I64) (WB * PANEL_MAX)) ;
             w2i = std::max (w2i, c * (I64) (WB * PANEL_MAX)) ;
-            gp = std::max (gp, c * Lv.nsplit * (I64) (WB * WB)) ;
+            gp = std::max (gp, c * Lv.nsplit_in * (I64) ((WB_PANELS - 1) * 96 * PANEL_MAX)) ;
         }
         ALLOC (N.wVb, vb) ; ALLOC (N.wTbt, tb) ; ALLOC (N.wblk, nb) ;
         ALLOC (N.wWp, wp) ; ALLOC (N.wW2, w2) ; ALLOC (N.wWpi, wpi) ; ALLOC (N.wW2i, w2i) ; ALLOC (N.wGp, gp) ;
     }
     ALLOC (N.Tws, pslots * PANEL_MAX * PANEL_MAX) ;
+    {
+        I64 gslots = 1 ;
+        for (const Level &Lv : h->ls_all.levels) if (Lv.maxFm >= h->grid_rows) gslots = std::max<I64> (gslots, Lv.count) ;
+        ALLOC (N.gridrec, gslots * 2 * 148 * 64) ;
+        ALLOC (N.gridred, gslots * 2 * 148) ;
+        ALLOC (N.gridll, gslots * 2 * 148 * 64) ;
+        CK (cudaMemsetAsync (N.gridll, 0, gslots * 2 * 148 * 64 * sizeof (int4), h->stream)) ;
+        ALLOC (N.gridctr, gslots * GRID_CTR_STRIDE) ;
+        ALLOC (N.griderr, 1) ;
+        CK (cudaMemsetAsync (N.gridctr, 0, gslots * GRID_CTR_STRIDE * sizeof (unsigned), h->stream)) ;
+        CK (cudaMemsetAsync (N.griderr, 0, sizeof (I32), h->stream)) ;
+    }
     ALLOC (N.stair, rjsize) ;
     ALLOC (N.Cmap, rjsize) ;
     ALLOC (N.rowpos, m) ;
@@ -753,6 +787,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     ALLOC (N.flops, 4) ;
     ALLOC (N.W, m) ;
     ALLOC (N.dbg, 64) ;
+    ALLOC (N.lvlstat, 4) ;
     ALLOC (N.base1, nf) ; ALLOC (N.base2, nf) ;
     ALLOC (h->d_err, 1) ;
     ALLOC (h->d_HPinv64, m) ;
@@ -864,6 +899,16 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
         h->curtag = levelno << 32 ;
         const I32 *fr = LS.d_fronts + Lv.first ;
         LAUNCH (1, k_front_setup<<<Lv.count, 128, 0, st>>> (fr, S, N)) ;
+        // levels with large fronts: the ACTUAL # rows of the tallest front decides which kernels run
+        // (the symbolic bound is ~2x too big under rank detection).  One tiny read-back per such level.
+        I32 actFm = Lv.maxFm ;
+        if (Lv.wide || Lv.maxFm >= h->grid_rows)
+        {
+            k_level_maxfm<<<1, 256, 0, st>>> (fr, Lv.count, N) ; h->launches++ ;
+            CK (cudaMemcpyAsync (h->pin_lvl, N.lvlstat, sizeof (I32), cudaMemcpyDeviceToHost, st)) ;
+            CK (cudaStreamSynchronize (st)) ;
+            actFm = std::min (Lv.maxFm, std::max (1, h->pin_lvl [0])) ;
+        }
         int nsl = (int) std::min<I64> (148, std::max<I64> (1, Lv.maxFelems / 8192)) ;
         LAUNCH (2, k_assemble<<<dim3 (Lv.count, nsl), 256, 0, st>>> (fr, S, N)) ;
         if (h->debug_capture)
@@ -883,8 +928,11 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
         // ---- front QR of the level: panel steps of PB columns over all active fronts ---------------
         // cluster size: the row slab of one CTA (rows / CS x PB doubles) should fit in shared memory
         int CS = 1 ;
-        while (CS < PANEL_CLUSTER_MAX && ((I64) (Lv.maxFm + CS - 1) / CS + 4) * PB > PANEL_SLAB_MAX_DOUBLES) CS *= 2 ;
-        const I64 rowsPerCta = ((I64) (Lv.maxFm + CS - 1) / CS + 7) & ~(I64) 3 ;
+        while (CS < PANEL_CLUSTER_MAX && ((I64) (actFm + CS - 1) / CS + 4) * PB > PANEL_SLAB_MAX_DOUBLES) CS *= 2 ;
+        // few fronts in the level: idle SMs are better spent on shorter slabs (a column step sweeps the
+        // slab three times through shared memory); up to the non-portable cluster size 16
+        while (CS < h->cluster_max && (I64) Lv.count * CS * 2 <= h->nsm && (actFm + CS - 1) / CS > h->cluster_rows) CS *= 2 ;
+        const I64 rowsPerCta = ((I64) (actFm + CS - 1) / CS + 7) & ~(I64) 3 ;
         // (at least 2 x 32 x 33 doubles: the leader builds T in the slab after writing it back)
         const I32 slabCap = (I32) std::max<I64> (2 * PANEL_MAX * (PANEL_MAX + 1),
             std::min<I64> (PANEL_SLAB_MAX_DOUBLES, rowsPerCta * PB)) ;
@@ -901,7 +949,27 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
             }
             return lo ;
         } ;
+        // fronts too tall for a cluster of 8 shared-memory slabs: G CTAs per front with a global-memory
+        // exchange (k_panel_grid), as many fronts per launch as fit one CTA per SM
+        const bool gridpanel = (actFm >= h->grid_rows) && PB == PANEL_MAX && !(h->opt.reserved & 4) ;
+        const I32 gneed = (I32) (((I64) actFm + 8 + 759) / 760) ;
         auto launch_panel = [&] (I32 active, I32 k1, I32 parity) -> cudaError_t {
+            if (gridpanel && gneed <= h->nsm)
+            {
+                const I32 per = std::max<I32> (1, h->nsm / gneed) ;
+                const size_t smem = (size_t) (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (16)) * sizeof (double) ;
+                for (I32 s0 = 0 ; s0 < active ; s0 += per)
+                {
+                    const I32 nb = std::min<I32> (per, active - s0) ;
+                    // no more CTAs than the step-cost model of k_panel_grid can use (they all have to
+                    // become resident before the panel starts)
+                    const I32 G = std::min<I32> (h->nsm / nb, std::max<I32> (gneed, (I32) std::sqrt (0.84 * (double) actFm) + 1)) ;
+                    k_panel_grid<<<(unsigned) (G * nb), 512, smem, st>>> (L, S, N, k1, (I32) PB, parity,
+                        (I32) PANEL_SLAB_MAX_DOUBLES, G, s0, ++h->grid_seq) ;
+                    if (s0 + per < active) h->launches++ ;
+                }
+                return cudaGetLastError () ;
+            }
             cudaLaunchConfig_t cfg = {} ;
             cfg.gridDim = dim3 ((unsigned) active * CS, 1, 1) ;
             cfg.blockDim = dim3 (pthreads, 1, 1) ;
@@ -927,26 +995,32 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
         } ;
         // look-ahead pays only when the trailing update is much bigger than its first 32 columns
         const bool lookahead = !h->opt.profile_phases && !(h->opt.reserved & 1) && Lv.maxFelems >= (I64) 8000000 ;
-        const bool wide = Lv.wide && !(h->opt.reserved & 2) && PB == PANEL_MAX ;
+        const bool wide = Lv.wide && actFm >= h->wide_rows && !(h->opt.reserved & 2) && PB == PANEL_MAX ;
         if (wide)
         {
             // ---- two-level blocking (kernels_wide.cuh): outer blocks of 128 columns = 4 panels -------
             WideArgs WA ; WA.fronts = fr ; WA.count = Lv.count ; WA.buf = 0 ; WA.ldv = Lv.ldv ;
             WA.rs = WIDE_RS ; WA.nsplit = Lv.nsplit ; WA.ncmax = Lv.maxfn ;
             WideArgs WI = WA ; WI.rs = WIDE_RS_IN ; WI.nsplit = Lv.nsplit_in ;
-            const I32 nrt = Lv.ldv / W_RT ;
+            const I32 nrt = std::min<I32> (Lv.ldv / W_RT, (actFm + W_RT - 1) / W_RT) ;
+            const I32 nsplA = std::min<I32> (Lv.nsplit, (actFm + WIDE_RS - 1) / WIDE_RS) ;
+            const I32 nsplI = std::min<I32> (Lv.nsplit_in, (actFm + WIDE_RS_IN - 1) / WIDE_RS_IN) ;
             // the K = 32 update of columns [cb,ce) (inside the block) by panel p of the block
+            // after panel p: Gram blocks of V_p with the earlier panels of the block (p >= 1) and the
+            // K = 32 update of the columns [cb,ce) that are left in the block (p < 3), one launch
             auto inner_update = [&] (I32 nfronts, I32 p, I32 cb, I32 ce) {
-                const I32 nct = (ce - cb + W_NC - 1) / W_NC ;
-                LAUNCH (9, k_wide_vtc<1><<<dim3 (nct * WI.nsplit, nfronts), 256, wide_vtc_smem_bytes<1> (), st>>> (WI, S, N, WIDE_INNER, p, cb, ce)) ;
-                LAUNCH (10, k_wide_wt<1><<<dim3 ((ce - cb + 15) / 16, nfronts), 256, 0, st>>> (WI, S, N, WIDE_INNER, p, cb, ce)) ;
+                const I32 nct = (ce > cb) ? (ce - cb + W_NC - 1) / W_NC : 0 ;
+                const I32 ncg = (p * PANEL_MAX + W_NC - 1) / W_NC ;
+                if (nct + ncg == 0) return ;
+                LAUNCH (9, k_wide_vtc<1><<<dim3 ((nct + ncg) * nsplI, nfronts), 256, wide_vtc_smem_bytes<1> (), st>>> (WI, S, N, WIDE_INNER, p, cb, ce, nct)) ;
+                if (nct == 0) return ;
+                LAUNCH (10, k_wide_wt_inner<<<dim3 ((ce - cb + 7) / 8, nfronts), 256, 0, st>>> (WI, S, N, p, cb, ce)) ;
                 LAUNCH (11, k_wide_apply<1><<<dim3 (nct * nrt, nfronts), 256, wide_apply_smem_bytes<1> (), st>>> (WI, S, N, WIDE_INNER, p, cb, ce, nct)) ;
             } ;
-            // the K = 128 update of columns [cb,ce) (right of the block)
             // (events of LAUNCH are recorded on the main stream: only meaningful when su == st)
             auto outer_update = [&] (cudaStream_t su, I32 nfronts, I32 cb, I32 ce) {
                 const I32 nct = (ce - cb + W_NC - 1) / W_NC ;
-                LAUNCH (14, k_wide_vtc<4><<<dim3 (nct * WA.nsplit, nfronts), 256, wide_vtc_smem_bytes<4> (), su>>> (WA, S, N, WIDE_OUTER, 0, cb, ce)) ;
+                LAUNCH (14, k_wide_vtc<4><<<dim3 (nct * nsplA, nfronts), 256, wide_vtc_smem_bytes<4> (), su>>> (WA, S, N, WIDE_OUTER, 0, cb, ce, nct)) ;
                 LAUNCH (15, k_wide_wt<4><<<dim3 ((ce - cb + 15) / 16, nfronts), 256, 0, su>>> (WA, S, N, WIDE_OUTER, 0, cb, ce)) ;
                 LAUNCH (16, k_wide_apply<4><<<dim3 (nct * nrt, nfronts), 256, wide_apply_smem_bytes<4> (), su>>> (WA, S, N, WIDE_OUTER, 0, cb, ce, nct)) ;
             } ;
@@ -965,20 +1039,16 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
                     if (act == 0) break ;
                     h->curtag = (levelno << 32) | (long long) k1 ;
                     LAUNCH (3, CK (launch_panel (act, k1, p))) ;
-                    LAUNCH (8, k_wide_vextract<<<dim3 ((Lv.ldv + 255) / 256, act), 256, 0, st>>> (WI, S, N, p)) ;
+                    LAUNCH (8, k_wide_vextract<<<dim3 ((std::min<I32> (Lv.ldv, actFm + 2 * W_RT) + 255) / 256, act), 256, 0, st>>> (WI, S, N, p)) ;
                     const I32 cb = k1 + PANEL_MAX, ce = std::min<I32> (j0 + WB, Lv.maxfn) ;
-                    if (p + 1 < WB_PANELS && cb < ce)
-                    {
-                        const I32 act2 = active_at (cb, act) ;
-                        if (act2 > 0) inner_update (act2, p, cb, ce) ;
-                    }
+                    const I32 act2 = (cb < Lv.maxfn) ? active_at (cb, act) : 0 ;      // fronts with columns right of the panel
+                    if (act2 > 0) inner_update (act2, p, cb, std::max (cb, ce)) ;
                 }
                 const I32 cb = j0 + WB ;
                 if (cb >= Lv.maxfn) break ;
                 const I32 act2 = active_at (cb, Lv.count) ;
                 if (act2 == 0) break ;
-                LAUNCH (12, k_wide_vtc<4><<<dim3 (2 * WA.nsplit, act2), 256, wide_vtc_smem_bytes<4> (), st>>> (WA, S, N, WIDE_GRAM, 0, 0, WB)) ;
-                LAUNCH (13, k_wide_tmerge<<<act2, 256, wide_tmerge_smem_bytes (), st>>> (WA, S, N)) ;
+                LAUNCH (13, k_wide_tmerge<<<act2, 1024, wide_tmerge_smem_bytes (), st>>> (WI, S, N)) ;
                 if (lookahead)
                 {
                     // the next block's columns first (main stream), the rest of the trailing matrix on the
@@ -1102,9 +1172,12 @@ int stmqr_b200_factorize_hpinv_b (stmqr_handle h, stmqr_numeric_info *info)
     CK (cudaMemcpyAsync (sc, N.sumrank, sizeof (sc), cudaMemcpyDeviceToHost, st)) ;
     CK (cudaMemcpyAsync (fl3, N.flops, sizeof (fl3), cudaMemcpyDeviceToHost, st)) ;
     CK (cudaMemcpyAsync (&err, h->d_err, sizeof (err), cudaMemcpyDeviceToHost, st)) ;
+    I32 gerr = 0 ;
+    CK (cudaMemcpyAsync (&gerr, N.griderr, sizeof (gerr), cudaMemcpyDeviceToHost, st)) ;
     CK (cudaStreamSynchronize (st)) ;
     CK (cudaGetLastError ()) ;
     if (err) return fail (h, STMQR_ERR_INVALID, "factorize: an entry of A is not in the pattern of S") ;
+    if (gerr) return fail (h, STMQR_ERR_INVALID, "factorize: a panel did not fit the shared-memory slabs of k_panel_grid") ;
 #ifdef STMQR_PANEL_TIMING
     {
         unsigned long long dbg [64] ;
@@ -1259,8 +1332,8 @@ int stmqr_b200_set_partition (stmqr_handle h, int nparts, int mypart, const int3
         sub [f] = owned [f] && !is_top [f] ;
         top [f] = owned [f] && is_top [f] ;
     }
-    filter_levels (h->ls_all, sub, h->h_Rp, h->h_FmB, h->ls_sub) ;
-    filter_levels (h->ls_all, top, h->h_Rp, h->h_FmB, h->ls_top) ;
+    filter_levels (h->ls_all, sub, h->h_Rp, h->h_FmB, h->wide_rows, h->ls_sub) ;
+    filter_levels (h->ls_all, top, h->h_Rp, h->h_FmB, h->wide_rows, h->ls_top) ;
     UPLOAD (h->ls_sub.d_fronts, h->ls_sub.fronts) ;
     UPLOAD (h->ls_top.d_fronts, h->ls_top.fronts) ;
     if (nparts > 1) { UPLOAD (h->d_owned, owned) ; h->N.owned = h->d_owned ; }

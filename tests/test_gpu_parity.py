@@ -125,15 +125,25 @@ def test_large_fronts_two_level_blocking(gen, order):
     At, ttol, ntol = ref.tapped()
     fm, fn = np.asarray(sym.Fm[: sym.nf]), np.diff(sym.Rp[: sym.nf + 1])
     assert (fm >= 1024).any() and (fn >= 384).any(), "input too small to reach the two-level path"
-    e = sq.Engine(0)
     got = {}
-    for flags in (0, 2):
+    # flags bit 1: single-level blocking; STMQR_B200_GRID_ROWS: fronts with at least that many rows
+    # take the panel kernel that exchanges through global memory (k_panel_grid)
+    # STMQR_B200_WIDE_ROWS: fronts with at least that many rows take the two-level path (default 4096)
+    for flags, grid_rows in ((0, None), (2, None), (0, "1024"), (2, "1024")):
+        os.environ["STMQR_B200_WIDE_ROWS"] = "1024"
+        if grid_rows:
+            os.environ["STMQR_B200_GRID_ROWS"] = grid_rows
+        try:
+            e = sq.Engine(0)
+        finally:
+            os.environ.pop("STMQR_B200_GRID_ROWS", None)
+            os.environ.pop("STMQR_B200_WIDE_ROWS", None)
         e.set_options(flags=flags)
-        got[flags] = run_engine(e, sym, At, ttol, ntol)
-        R.assert_numeric_parity(sym, At, got[flags], refnum, f"{gen} flags {flags} vs reference")
-        assert got[flags].flops == R.reference_flops(sym, got[flags])
-    assert not R.structural_equal(got[0], got[2], sym)
-    e.close()
+        num = got[(flags, grid_rows)] = run_engine(e, sym, At, ttol, ntol)
+        R.assert_numeric_parity(sym, At, num, refnum, f"{gen} flags {flags} grid {grid_rows} vs reference")
+        assert num.flops == R.reference_flops(sym, num)
+        assert not R.structural_equal(num, got[(0, None)], sym)
+        e.close()
     ref.free_qr(QR); ref.free_sparse(A); ref.close()
 
 
