@@ -92,7 +92,8 @@ typedef struct
  * can free them).  Layouts are the reference's qr_numeric. */
 typedef struct
 {
-    double  *stack ;                 /* [rh_size] all packed R+H blocks, one stack (ns = 1)  */
+    double  *stack ;                 /* [rh_size] all packed R+H blocks, one stack (ns = 1);
+                                        NULL: skip (already streamed)                       */
     int64_t *Roff ;                  /* [nf] Rblock[f] = stack + Roff[f]                     */
     char    *Rdead ;                 /* [n]                                                  */
     int64_t *HStair ;                /* [rjsize]                                             */
@@ -169,6 +170,16 @@ int  stmqr_b200_download (stmqr_handle h, const stmqr_numeric_view *out) ;
  * `stack` from info->rh_size first). */
 int  stmqr_b200_factorize (stmqr_handle h, const stmqr_csc_view *A, double tol, int64_t ntol,
                            stmqr_numeric_info *info) ;
+
+/* The same with the download of the packed R+H stack overlapped with the factorization: the blocks
+ * of an etree level are final as soon as the level is packed and are copied into `stack` while the next
+ * levels run (the reference's qr_factorize also allocates its stacks by the symbolic bound and shrinks
+ * them afterwards, SparseQR_factorize.c:405-410,:560-660).  `stack` must hold stmqr_b200_rh_bound()
+ * doubles; on return the first info->rh_size of them are valid.  Afterwards call stmqr_b200_download
+ * with out->stack = NULL for the remaining arrays. */
+int  stmqr_b200_rh_bound (stmqr_handle h, int64_t *doubles) ;
+int  stmqr_b200_factorize_streamed (stmqr_handle h, const stmqr_csc_view *A, double tol, int64_t ntol,
+                                    double *stack, int64_t capacity, stmqr_numeric_info *info) ;
 
 /* ---- the numeric phase in pieces, and the etree partitioned over several GPUs ------------------
  * One handle per GPU (one process per GPU under torchrun, or several handles in one process).

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <condition_variable>
+#include <deque>
 #include <functional>
 #include <mutex>
 #include <string>
@@ -136,6 +137,7 @@ private:
 } ;
 
 constexpr size_t D2H_CHUNK = (size_t) 32 << 20 ;     // bytes per staging buffer
+constexpr int STREAM_MAX_LEVELS = 8192 ;
 
 } // namespace
 
@@ -158,6 +160,18 @@ struct stmqr_handle_s
     LevelSet ls_all, ls_sub, ls_top ;
     std::vector<I32> h_parent, h_owner, h_istop ;   // etree parent; GPU partition (set_partition)
     int nparts = 1, mypart = 0 ;
+    // streamed download (stmqr_b200_factorize_streamed): the R+H blocks of a level go to the host while
+    // the next levels are factorized
+    bool streaming = false ;
+    std::vector<cudaEvent_t> evLvl ;
+    unsigned long long *pin_cursor = nullptr ;      // pinned [STREAM_MAX_LEVELS]: R arena cursor after each level
+    int stream_levels = 0 ;
+    std::mutex smu ;
+    std::condition_variable scv ;
+    std::deque<int> squeue ;
+    bool sdone = false ;
+    int serr = STMQR_OK ;
+    bool stack_streamed = false ;
     I32 *pin_lvl = nullptr ;                // pinned: actual max # rows of the level being processed
     unsigned grid_seq = 0 ;                 // launch sequence number of k_panel_grid (tags of its exchange lines)
     int nsm = 148 ;                         // SMs of the device (k_panel_grid: one CTA per SM)
@@ -326,6 +340,48 @@ int d2h_pipelined (stmqr_handle h, void *dst, const void *src, size_t bytes)
     return STMQR_OK ;
 }
 
+
+int ensure_copy_pipeline (stmqr_handle h)
+{
+    if (h->pool) return STMQR_OK ;
+    int nt = (int) std::min<unsigned> (8, std::max<unsigned> (1, std::thread::hardware_concurrency () / 2)) ;
+    if (const char *e = getenv ("STMQR_B200_COPY_THREADS")) nt = std::max (0, atoi (e)) ;
+    h->pool = new CopyPool (nt) ;
+    CK (cudaStreamCreateWithFlags (&h->streamCopy, cudaStreamNonBlocking)) ;
+    for (int i = 0 ; i < 2 ; i++)
+    {
+        CK (cudaHostAlloc ((void **) &h->pin [i], D2H_CHUNK, cudaHostAllocDefault)) ;
+        CK (cudaEventCreateWithFlags (&h->evPin [i], cudaEventDisableTiming)) ;
+    }
+    return STMQR_OK ;
+}
+
+// the downloader of stmqr_b200_factorize_streamed: per finished level, its slice of the R+H arena
+void stream_worker (stmqr_handle h, double *dst, I64 capacity)
+{
+    cudaSetDevice (h->device) ;
+    I64 begin = 0 ;
+    for ( ; ; )
+    {
+        int li ;
+        {
+            std::unique_lock<std::mutex> lk (h->smu) ;
+            h->scv.wait (lk, [&] { return !h->squeue.empty () || h->sdone ; }) ;
+            if (h->squeue.empty ()) break ;
+            li = h->squeue.front () ; h->squeue.pop_front () ;
+        }
+        if (h->serr != STMQR_OK) continue ;
+        if (cudaEventSynchronize (h->evLvl [li]) != cudaSuccess) { h->serr = STMQR_ERR_CUDA ; continue ; }
+        const I64 end = (I64) h->pin_cursor [li] ;
+        if (end > capacity) { h->serr = STMQR_ERR_INVALID ; continue ; }
+        if (end > begin)
+        {
+            const int s = d2h_pipelined (h, dst + begin, h->N.R + begin, (size_t) (end - begin) * sizeof (double)) ;
+            if (s != STMQR_OK) h->serr = s ;
+        }
+        begin = end ;
+    }
+}
 
 // Partition of the etree over `nparts` GPUs (host only, deterministic: every rank computes the same
 // answer from the same qr_symbolic).  The heaviest subtrees are opened from the roots until no
@@ -522,6 +578,8 @@ void stmqr_b200_destroy (stmqr_handle h)
     }
     if (h->evW) cudaEventDestroy (h->evW) ;
     if (h->pin_lvl) cudaFreeHost (h->pin_lvl) ;
+    if (h->pin_cursor) cudaFreeHost (h->pin_cursor) ;
+    for (cudaEvent_t e : h->evLvl) cudaEventDestroy (e) ;
     delete h->pool ;
     for (int i = 0 ; i < 2 ; i++)
     {
@@ -1129,6 +1187,21 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
         LAUNCH (5, k_front_finish<<<Lv.count, 128, 0, st>>> (fr, S, N)) ;
         LAUNCH (5, k_level_alloc<<<1, 1024, 0, st>>> (fr, Lv.count, N)) ;
         LAUNCH (6, k_pack<<<dim3 (Lv.count, nsl), 256, 0, st>>> (fr, S, N)) ;
+        if (h->streaming && h->stream_levels < STREAM_MAX_LEVELS)
+        {
+            // the level's R+H blocks are final: hand their slice of the arena to the downloader
+            const int li = h->stream_levels++ ;
+            while ((int) h->evLvl.size () <= li)
+            {
+                cudaEvent_t e ;
+                CK (cudaEventCreateWithFlags (&e, cudaEventDisableTiming)) ;
+                h->evLvl.push_back (e) ;
+            }
+            CK (cudaMemcpyAsync (h->pin_cursor + li, N.rcursor, sizeof (unsigned long long), cudaMemcpyDeviceToHost, st)) ;
+            CK (cudaEventRecord (h->evLvl [li], st)) ;
+            { std::lock_guard<std::mutex> lk (h->smu) ; h->squeue.push_back (li) ; }
+            h->scv.notify_one () ;
+        }
     }
 
     return STMQR_OK ;
@@ -1261,6 +1334,43 @@ int stmqr_b200_factorize (stmqr_handle h, const stmqr_csc_view *A, double tol, i
     return stmqr_b200_factorize_resident (h, tol, ntol, info) ;
 }
 
+int stmqr_b200_rh_bound (stmqr_handle h, int64_t *doubles)
+{
+    if (!h || !h->analyzed || !doubles) return STMQR_ERR_INVALID ;
+    *doubles = h->Rcap ;
+    return STMQR_OK ;
+}
+
+int stmqr_b200_factorize_streamed (stmqr_handle h, const stmqr_csc_view *A, double tol, int64_t ntol,
+    double *stack, int64_t capacity, stmqr_numeric_info *info)
+{
+    if (!h || !stack || capacity < 1) return fail (h, STMQR_ERR_INVALID, "factorize_streamed: no destination") ;
+    int s = stmqr_b200_upload_matrix (h, A) ;
+    if (s != STMQR_OK) return s ;
+    if ((s = ensure_copy_pipeline (h)) != STMQR_OK) return s ;
+    if (!h->pin_cursor) CK (cudaHostAlloc ((void **) &h->pin_cursor, STREAM_MAX_LEVELS * sizeof (unsigned long long), cudaHostAllocDefault)) ;
+    h->squeue.clear () ; h->sdone = false ; h->serr = STMQR_OK ; h->stream_levels = 0 ;
+    h->streaming = true ;
+    std::thread worker (stream_worker, h, stack, (I64) capacity) ;
+    if ((s = stmqr_b200_factorize_begin (h, tol, ntol)) == STMQR_OK &&
+        (s = stmqr_b200_factorize_levels (h, 0)) == STMQR_OK &&
+        (s = stmqr_b200_factorize_hpinv_a (h)) == STMQR_OK)
+        s = stmqr_b200_factorize_hpinv_b (h, info) ;
+    { std::lock_guard<std::mutex> lk (h->smu) ; h->sdone = true ; }
+    h->scv.notify_all () ;
+    worker.join () ;
+    h->streaming = false ;
+    if (s != STMQR_OK) return s ;
+    if (h->serr != STMQR_OK) return fail (h, h->serr, "factorize_streamed: download of the R+H stack failed") ;
+    if (h->info.rh_size > capacity) return fail (h, STMQR_ERR_INVALID, "factorize_streamed: stack capacity too small") ;
+    if (h->stream_levels >= STREAM_MAX_LEVELS)
+    {
+        // (more etree levels than events: the tail was not streamed) copy everything again
+        if ((s = d2h_pipelined (h, stack, h->N.R, h->info.rh_size * sizeof (double))) != STMQR_OK) return s ;
+    }
+    return STMQR_OK ;
+}
+
 // -------------------------------------------------------------------------------------------------
 int stmqr_b200_download (stmqr_handle h, const stmqr_numeric_view *out)
 {
@@ -1268,18 +1378,7 @@ int stmqr_b200_download (stmqr_handle h, const stmqr_numeric_view *out)
     cudaSetDevice (h->device) ;
     cudaStream_t st = h->stream ;
     DNum &N = h->N ;
-    if (!h->pool)
-    {
-        int nt = (int) std::min<unsigned> (8, std::max<unsigned> (1, std::thread::hardware_concurrency () / 2)) ;
-        if (const char *e = getenv ("STMQR_B200_COPY_THREADS")) nt = std::max (0, atoi (e)) ;
-        h->pool = new CopyPool (nt) ;
-        CK (cudaStreamCreateWithFlags (&h->streamCopy, cudaStreamNonBlocking)) ;
-        for (int i = 0 ; i < 2 ; i++)
-        {
-            CK (cudaHostAlloc ((void **) &h->pin [i], D2H_CHUNK, cudaHostAllocDefault)) ;
-            CK (cudaEventCreateWithFlags (&h->evPin [i], cudaEventDisableTiming)) ;
-        }
-    }
+    { int s0 = ensure_copy_pipeline (h) ; if (s0 != STMQR_OK) return s0 ; }
     auto t0 = std::chrono::steady_clock::now () ;
     // widen the int32 device arrays once (HStair | Hm | Hr back to back in d_wide)
     const I64 nw1 = std::max<I64> (h->rjsize, 0), nw2 = std::max<I64> (h->nf, 0) ;
@@ -1291,7 +1390,7 @@ int stmqr_b200_download (stmqr_handle h, const stmqr_numeric_view *out)
     }
     CK (cudaStreamSynchronize (st)) ;
     int s ;
-    if (h->info.rh_size > 0 && (s = d2h_pipelined (h, out->stack, N.R, h->info.rh_size * sizeof (double))) != STMQR_OK) return s ;
+    if (h->info.rh_size > 0 && out->stack && (s = d2h_pipelined (h, out->stack, N.R, h->info.rh_size * sizeof (double))) != STMQR_OK) return s ;
     if ((s = d2h_pipelined (h, out->Roff, N.Roff, h->nf * sizeof (I64))) != STMQR_OK) return s ;
     if ((s = d2h_pipelined (h, out->Rdead, N.Rdead, h->n)) != STMQR_OK) return s ;
     if ((s = d2h_pipelined (h, out->HTau, N.HTau, h->rjsize * sizeof (double))) != STMQR_OK) return s ;

@@ -125,19 +125,20 @@ qr_numeric *stmqr_b200_qr_factorize (sparse_csc **Ahandle, Long freeA, double to
     Av.nrow = A->nrow ; Av.ncol = A->ncol ; Av.nzmax = A->nzmax ;
     Av.p = (const int64_t *) A->p ; Av.i = (const int64_t *) A->i ; Av.x = (const double *) A->x ;
     stmqr_numeric_info info ;
-    s = stmqr_b200_factorize (g_handle, &Av, tol, ntol, &info) ;
 
-    t_fact = now_ms () ;
-    if (freeA) SparseCore_free_sparse (Ahandle, cc) ;           /* A is no longer needed (:324) */
-    if (s != STMQR_OK || cc->status < SPARSE_OK)
+    /* ---- allocate the numeric object exactly as qr_freenum expects (:339-375) ----
+     * The R+H stack is allocated by its symbolic bound and shrunk afterwards, as the reference does
+     * with its own stacks (:405-410, :560-660): the engine can then copy the blocks of every finished
+     * etree level into it while the next levels are still being factorized. */
+    const int streamed = (getenv ("STMQR_B200_NO_STREAM") == NULL) ;
+    int64_t cap = 0 ;
+    if (streamed && stmqr_b200_rh_bound (g_handle, &cap) != STMQR_OK) cap = 0 ;
+    qr_numeric *QRnum = (qr_numeric *) SparseCore_malloc (1, sizeof (qr_numeric), cc) ;
+    if (cc->status < SPARSE_OK)
     {
-        if (s != STMQR_OK) report (cc, s, "factorize") ;
+        if (freeA) SparseCore_free_sparse (Ahandle, cc) ;
         return (NULL) ;
     }
-
-    /* ---- allocate the numeric object exactly as qr_freenum expects (:339-375) ---- */
-    qr_numeric *QRnum = (qr_numeric *) SparseCore_malloc (1, sizeof (qr_numeric), cc) ;
-    if (cc->status < SPARSE_OK) return (NULL) ;
     Long ns = 1 ;
     QRnum->Rblock     = (double **) SparseCore_malloc (nf, sizeof (double *), cc) ;
     QRnum->Rdead      = (char *)    SparseCore_calloc (n,  sizeof (char), cc) ;
@@ -156,21 +157,65 @@ qr_numeric *stmqr_b200_qr_factorize (sparse_csc **Ahandle, Long freeA, double to
     QRnum->maxfm = EMPTY ;
     QRnum->norm_E_fro = 0 ;
     Long *Roff = (Long *) SparseCore_malloc (nf, sizeof (Long), cc) ;
-    if (cc->status == SPARSE_OK)
+    if (cc->status == SPARSE_OK && streamed && cap > 0)
+    {
+        QRnum->Stack_size [0] = cap ;
+        QRnum->Stacks [0] = (double *) SparseCore_malloc (cap, sizeof (double), cc) ;
+    }
+    if (cc->status < SPARSE_OK)
+    {
+        if (Roff) SparseCore_free (nf, sizeof (Long), Roff, cc) ;
+        qr_freenum (&QRnum, cc) ;
+        if (freeA) SparseCore_free_sparse (Ahandle, cc) ;
+        return (NULL) ;
+    }
+#ifdef MADV_HUGEPAGE
+#define STACK_HUGEPAGES(ptr, doubles) do { \
+        /* the stack is written exactly once, front to back, by the download: ask for huge pages on its \
+         * 2 MB-aligned interior so that the first touch takes ~500x fewer page faults */ \
+        if ((ptr) && (size_t) (doubles) * sizeof (double) >= ((size_t) 8 << 20)) \
+        { \
+            size_t a_ = ((size_t) (ptr) + ((size_t) 2 << 20) - 1) & ~(((size_t) 2 << 20) - 1) ; \
+            size_t e_ = ((size_t) (ptr) + (size_t) (doubles) * sizeof (double)) & ~(((size_t) 2 << 20) - 1) ; \
+            if (e_ > a_) madvise ((void *) a_, e_ - a_, MADV_HUGEPAGE) ; \
+        } } while (0)
+#else
+#define STACK_HUGEPAGES(ptr, doubles) do { } while (0)
+#endif
+
+    if (streamed && cap > 0)
+    {
+        STACK_HUGEPAGES (QRnum->Stacks [0], cap) ;
+        s = stmqr_b200_factorize_streamed (g_handle, &Av, tol, ntol, QRnum->Stacks [0], cap, &info) ;
+    }
+    else
+    {
+        s = stmqr_b200_factorize (g_handle, &Av, tol, ntol, &info) ;
+    }
+    t_fact = now_ms () ;
+    if (freeA) SparseCore_free_sparse (Ahandle, cc) ;           /* A is no longer needed (:324) */
+    if (s != STMQR_OK || cc->status < SPARSE_OK)
+    {
+        if (s != STMQR_OK) report (cc, s, "factorize") ;
+        SparseCore_free (nf, sizeof (Long), Roff, cc) ;
+        qr_freenum (&QRnum, cc) ;
+        return (NULL) ;
+    }
     {
         Long stacksize = (info.rh_size > 0) ? info.rh_size : 1 ;
-        QRnum->Stack_size [0] = stacksize ;
-        QRnum->Stacks [0] = (double *) SparseCore_malloc (stacksize, sizeof (double), cc) ;
-#ifdef MADV_HUGEPAGE
-        /* the stack is written exactly once, front to back, by the download: ask for huge pages
-         * on its 2 MB-aligned interior so that the first touch takes ~500x fewer page faults */
-        if (QRnum->Stacks [0] && stacksize * sizeof (double) >= ((size_t) 8 << 20))
+        if (streamed && cap > 0)
         {
-            size_t a = ((size_t) QRnum->Stacks [0] + ((size_t) 2 << 20) - 1) & ~(((size_t) 2 << 20) - 1) ;
-            size_t e = ((size_t) QRnum->Stacks [0] + stacksize * sizeof (double)) & ~(((size_t) 2 << 20) - 1) ;
-            if (e > a) madvise ((void *) a, e - a, MADV_HUGEPAGE) ;
+            /* shrink the stack to what the factorization produced (:640-657) */
+            size_t cur = (size_t) cap ;
+            QRnum->Stacks [0] = (double *) SparseCore_realloc (stacksize, sizeof (double), QRnum->Stacks [0], &cur, cc) ;
+            QRnum->Stack_size [0] = (Long) cur ;
         }
-#endif
+        else
+        {
+            QRnum->Stack_size [0] = stacksize ;
+            QRnum->Stacks [0] = (double *) SparseCore_malloc (stacksize, sizeof (double), cc) ;
+            STACK_HUGEPAGES (QRnum->Stacks [0], stacksize) ;
+        }
     }
     t_alloc = now_ms () ;
     if (cc->status < SPARSE_OK)
@@ -181,7 +226,8 @@ qr_numeric *stmqr_b200_qr_factorize (sparse_csc **Ahandle, Long freeA, double to
     }
 
     stmqr_numeric_view out ;
-    out.stack = QRnum->Stacks [0] ; out.Roff = (int64_t *) Roff ; out.Rdead = QRnum->Rdead ;
+    out.stack = (streamed && cap > 0) ? NULL : QRnum->Stacks [0] ;
+    out.Roff = (int64_t *) Roff ; out.Rdead = QRnum->Rdead ;
     out.HStair = (int64_t *) QRnum->HStair ; out.HTau = QRnum->HTau ;
     out.Hii = (int64_t *) QRnum->Hii ; out.Hm = (int64_t *) QRnum->Hm ;
     out.Hr = (int64_t *) QRnum->Hr ; out.HPinv = (int64_t *) QRnum->HPinv ;

@@ -94,6 +94,7 @@ EXPORTS = (
     "stmqr_b200_factorize_begin", "stmqr_b200_factorize_levels", "stmqr_b200_factorize_hpinv_a",
     "stmqr_b200_factorize_hpinv_b", "stmqr_b200_sync", "stmqr_b200_partition_fronts",
     "stmqr_b200_set_partition", "stmqr_b200_device_array", "stmqr_b200_front_regions",
+    "stmqr_b200_rh_bound", "stmqr_b200_factorize_streamed",
 )
 
 _lib = None
@@ -138,6 +139,9 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
                                             C.POINTER(C.c_int32)]
     lib.stmqr_b200_front_regions.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                              C.POINTER(FrontRegions)]
+    lib.stmqr_b200_rh_bound.argtypes = [C.c_void_p, _i64p]
+    lib.stmqr_b200_factorize_streamed.argtypes = [C.c_void_p, C.POINTER(CscView), C.c_double, C.c_int64, _f64p,
+                                                  C.c_int64, C.POINTER(NumericInfo)]
     _lib = lib
     return lib
 
@@ -292,17 +296,29 @@ class Engine:
         self._check(self.lib.stmqr_b200_factorize(self.h, C.byref(A.view), tol, ntol, C.byref(info)), "factorize")
         return info
 
-    def download(self, info: NumericInfo) -> Numeric:
+    def factorize_streamed(self, A: Csc, tol: float, ntol: int):
+        """upload + numeric phase with the R+H stack copied to the host level by level while the
+        next levels run -> (info, stack[:rh_size]); then download(info, stack=...) for the rest"""
+        cap = C.c_int64()
+        self._check(self.lib.stmqr_b200_rh_bound(self.h, C.byref(cap)), "rh_bound")
+        stack = np.empty(max(int(cap.value), 1), np.float64)
+        info = NumericInfo()
+        self._check(self.lib.stmqr_b200_factorize_streamed(
+            self.h, C.byref(A.view), tol, ntol, stack.ctypes.data_as(_f64p), stack.size, C.byref(info)),
+            "factorize_streamed")
+        return info, stack[: max(int(info.rh_size), 1)]
+
+    def download(self, info: NumericInfo, stack=None) -> Numeric:
         s = self.sym
         out = Numeric(int(info.rank), int(info.rank1), int(info.maxfrank), int(info.maxfm),
                       int(info.rh_size), float(info.flops),
-                      stack=np.empty(max(int(info.rh_size), 1), np.float64),
+                      stack=(stack if stack is not None else np.empty(max(int(info.rh_size), 1), np.float64)),
                       Roff=np.empty(max(s.nf, 1), np.int64), Rdead=np.zeros(max(s.n, 1), np.int8),
                       HStair=np.empty(max(s.rjsize, 1), np.int64), HTau=np.empty(max(s.rjsize, 1), np.float64),
                       Hii=np.empty(max(s.hisize, 1), np.int64), Hm=np.empty(max(s.nf, 1), np.int64),
                       Hr=np.empty(max(s.nf, 1), np.int64), HPinv=np.empty(max(s.m, 1), np.int64))
         v = NumericView()
-        v.stack = out.stack.ctypes.data_as(_f64p)
+        v.stack = out.stack.ctypes.data_as(_f64p) if stack is None else None      # NULL: already streamed
         v.Roff = out.Roff.ctypes.data_as(_i64p)
         v.Rdead = out.Rdead.ctypes.data
         v.HStair = out.HStair.ctypes.data_as(_i64p)

@@ -208,6 +208,21 @@ def test_qrtest_driver_with_ld_preload(tmp_path):
     assert "res =  2.4e+01" in out.stdout, out.stdout[-2000:]     # STM-MQR.xlsx row 700 / SURVEY.md 4
 
 
+@pytest.mark.parametrize("case", ["dwt_992_metis", "lap2d_24_metis", "tall_600x150_colamd"])
+def test_streamed_download_is_identical(engine, case):
+    """stmqr_b200_factorize_streamed (R+H blocks copied level by level while later levels run)
+    delivers bit-for-bit what factorize + download delivers."""
+    sym, A, tol, ntol, want = R.load_golden(case)
+    a = run_engine(engine, sym, A, tol, ntol)
+    engine.analyze(sym)
+    info, stack = engine.factorize_streamed(A, tol, ntol)
+    b = engine.download(info, stack=stack)
+    assert not R.structural_equal(a, b, sym)
+    assert a.rh_size == b.rh_size and np.array_equal(a.stack[: a.rh_size], b.stack[: b.rh_size])
+    assert np.array_equal(a.Roff, b.Roff) and np.array_equal(a.HTau, b.HTau)
+    R.assert_numeric_parity(sym, A, b, want, case + " streamed")
+
+
 def test_errors_and_edge_cases(engine):
     sym, A, tol, ntol, want = R.load_golden("lap2d_16_notol")
     engine.analyze(sym)
