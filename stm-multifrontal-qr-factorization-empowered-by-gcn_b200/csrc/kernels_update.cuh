@@ -75,9 +75,13 @@ __device__ __forceinline__ void issue_chunk (double *stage, const double *__rest
     }
 }
 
+// rsf > 1: the rows are split over a cluster of rsf CTAs (cluster dimension z): every CTA computes
+// the partial W of its rows, the partials are summed in rank order through distributed shared memory,
+// and every CTA updates its own rows -- mid-size fronts (a few column tiles, thousands of rows)
+// then occupy rsf times as many SMs and every CTA streams 1/rsf of the rows.
 template <int NSTAGE>
 __global__ void __launch_bounds__ (256) k_update_dmma (LevelArgs L, DSym S, DNum N, I32 cbeg, I32 cend,
-    I32 parity)
+    I32 parity, I32 rsf)
 {
     constexpr int NT = UPD_NC / 8 ;                 // accumulator tiles along the columns
     extern __shared__ double sm [] ;
@@ -101,6 +105,9 @@ __global__ void __launch_bounds__ (256) k_update_dmma (LevelArgs L, DSym S, DNum
     const I32 g1 = N.pnl_g1 [slotp], tend = N.pnl_tend [slotp] ;
     const I32 mr = tend - g1 ;
     const I32 nch = (mr + UPD_RC - 1) / UPD_RC ;
+    const I32 cpr = (nch + rsf - 1) / rsf ;                         // chunks per rank of the cluster
+    const I32 ch0 = min (nch, (I32) blockIdx.z * cpr), ch1 = min (nch, ch0 + cpr) ;
+    const I32 nmy = ch1 - ch0 ;
     const int tid = threadIdx.x ;
     const int lane = tid & 31, w = tid >> 5 ;
     const int grp = lane >> 2, tig = lane & 3 ;     // mma fragment coordinates
@@ -126,20 +133,20 @@ __global__ void __launch_bounds__ (256) k_update_dmma (LevelArgs L, DSym S, DNum
 #pragma unroll
     for (int p = 0 ; p < NSTAGE - 1 ; p++)
     {
-        if (p < nch) issue_chunk (ring + p * UPD_STAGE, F, ld, g1, mr, nv, cols, c0, ncol, p * UPD_RC, tid) ;
+        if (p < nmy) issue_chunk (ring + p * UPD_STAGE, F, ld, g1, mr, nv, cols, c0, ncol, (ch0 + p) * UPD_RC, tid) ;
         cp_async_commit () ;
     }
-    for (I32 ch = 0 ; ch < nch ; ch++)
+    for (I32 ch = 0 ; ch < nmy ; ch++)
     {
         // keep NSTAGE-1 chunks in flight; the stage refilled here was consumed in iteration ch-1
-        if (ch + NSTAGE - 1 < nch)
+        if (ch + NSTAGE - 1 < nmy)
             issue_chunk (ring + ((ch + NSTAGE - 1) % NSTAGE) * UPD_STAGE, F, ld, g1, mr, nv, cols, c0, ncol,
-                (ch + NSTAGE - 1) * UPD_RC, tid) ;
+                (ch0 + ch + NSTAGE - 1) * UPD_RC, tid) ;
         cp_async_commit () ;
         cp_async_wait<NSTAGE - 1> () ;
         __syncthreads () ;
         double *Vs = ring + (ch % NSTAGE) * UPD_STAGE, *Cs = Vs + PANEL_MAX * UPD_LDS ;
-        if (ch == 0)
+        if (ch0 + ch == 0)
         {
             if (tid < nv) Vs [tid * UPD_LDS + tid] = 1.0 ;          // unit diagonal of V
             __syncthreads () ;
@@ -192,6 +199,28 @@ __global__ void __launch_bounds__ (256) k_update_dmma (LevelArgs L, DSym S, DNum
             const int e = tid + a * 256 ;
             Ws [(e >> 5) * UPD_LDW + (e & 31)] = wsum [a] ;
         }
+        if (rsf > 1)
+        {
+            // W = sum over the ranks of the cluster (fixed order: every rank gets the same bits)
+            cg::cluster_group cluster = cg::this_cluster () ;
+            cluster.sync () ;
+#pragma unroll
+            for (int a = 0 ; a < (UPD_NC * PANEL_MAX) / 256 ; a++)
+            {
+                const int e = tid + a * 256 ;
+                double *mine = Ws + (e >> 5) * UPD_LDW + (e & 31) ;
+                double t = 0 ;
+                for (int r = 0 ; r < rsf ; r++) t += *cluster.map_shared_rank (mine, r) ;
+                wsum [a] = t ;
+            }
+            cluster.sync () ;           // all remote reads done: Ws may be overwritten, peers may leave
+#pragma unroll
+            for (int a = 0 ; a < (UPD_NC * PANEL_MAX) / 256 ; a++)
+            {
+                const int e = tid + a * 256 ;
+                Ws [(e >> 5) * UPD_LDW + (e & 31)] = wsum [a] ;
+            }
+        }
         __syncthreads () ;
         double w2 [(UPD_NC * PANEL_MAX) / 256] ;
 #pragma unroll
@@ -230,19 +259,19 @@ __global__ void __launch_bounds__ (256) k_update_dmma (LevelArgs L, DSym S, DNum
 #pragma unroll
     for (int p = 0 ; p < NSTAGE - 1 ; p++)
     {
-        if (p < nch) issue_chunk (ring + p * UPD_STAGE, F, ld, g1, mr, nv, cols, c0, ncol, p * UPD_RC, tid) ;
+        if (p < nmy) issue_chunk (ring + p * UPD_STAGE, F, ld, g1, mr, nv, cols, c0, ncol, (ch0 + p) * UPD_RC, tid) ;
         cp_async_commit () ;
     }
-    for (I32 ch = 0 ; ch < nch ; ch++)
+    for (I32 ch = 0 ; ch < nmy ; ch++)
     {
-        if (ch + NSTAGE - 1 < nch)
+        if (ch + NSTAGE - 1 < nmy)
             issue_chunk (ring + ((ch + NSTAGE - 1) % NSTAGE) * UPD_STAGE, F, ld, g1, mr, nv, cols, c0, ncol,
-                (ch + NSTAGE - 1) * UPD_RC, tid) ;
+                (ch0 + ch + NSTAGE - 1) * UPD_RC, tid) ;
         cp_async_commit () ;
         cp_async_wait<NSTAGE - 1> () ;
         __syncthreads () ;
         double *Vs = ring + (ch % NSTAGE) * UPD_STAGE, *Cs = Vs + PANEL_MAX * UPD_LDS ;
-        if (ch == 0)
+        if (ch0 + ch == 0)
         {
             if (tid < nv) Vs [tid * UPD_LDS + tid] = 1.0 ;
             __syncthreads () ;
@@ -259,7 +288,7 @@ __global__ void __launch_bounds__ (256) k_update_dmma (LevelArgs L, DSym S, DNum
 #pragma unroll
             for (int ni = 0 ; ni < NT ; ni++) dmma_m8n8k4 (d [ni][0], d [ni][1], af, wf [ks][ni]) ;
         }
-        const I32 r = ch * UPD_RC + w * 8 + grp ;
+        const I32 r = (ch0 + ch) * UPD_RC + w * 8 + grp ;
         if (r < mr)
         {
 #pragma unroll

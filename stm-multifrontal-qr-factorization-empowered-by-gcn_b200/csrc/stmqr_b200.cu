@@ -25,6 +25,7 @@
 #include "kernels_panel.cuh"
 #include "kernels_update.cuh"
 #include "kernels_wide.cuh"
+#include "kernels_small.cuh"
 #include "kernels_peak.cuh"
 
 using namespace stmqr ;
@@ -41,6 +42,12 @@ struct Level
     I32 maxfn ;         // max # columns in the level
     I64 maxFelems ;     // max bound Fm*fn in the level
     I32 maxFm ;         // max bound Fm in the level
+    // small-front batching path (kernels_small.cuh): the list is [big fronts | small | tiny], the
+    // small ones sorted by shared-memory footprint descending
+    I32 nbig ;          // fronts that take the tiled kernels (first in the list)
+    I32 nsmall [2] ;    // fronts of the two shared-memory classes of k_front_small
+    I32 scap [2] ;      // doubles of shared memory per front of the class ((Fm+1) * fn, max)
+    I32 srows [2] ;     // max bound on the # rows in the class
     // two-level blocked path (kernels_wide.cuh): few, large fronts
     bool wide ;
     I32 ldv ;           // leading dimension of the clean V buffers
@@ -55,7 +62,7 @@ constexpr I32 WIDE_MIN_COLS = 384, WIDE_MAX_FRONTS = 64 ;
 // ACTUAL # rows (known after k_front_setup) does
 void plan_wide (Level &L, I32 wide_rows)
 {
-    L.wide = (L.maxFm >= wide_rows && L.maxfn >= WIDE_MIN_COLS && L.count <= WIDE_MAX_FRONTS) ;
+    L.wide = (L.maxFm >= wide_rows && L.maxfn >= WIDE_MIN_COLS && L.nbig <= WIDE_MAX_FRONTS) ;
     L.ldv = ((L.maxFm + W_RT - 1) / W_RT) * W_RT + W_RT ;
     L.nsplit = (L.ldv + WIDE_RS - 1) / WIDE_RS ;
     L.nsplit_in = (L.ldv + WIDE_RS_IN - 1) / WIDE_RS_IN ;
@@ -177,6 +184,10 @@ struct stmqr_handle_s
     int nsm = 148 ;                         // SMs of the device (k_panel_grid: one CTA per SM)
     int cluster_max = 8 ;                   // largest panel cluster (8 portable; 16 non-portable, no gain measured)
     I32 cluster_rows = 160 ;                // do not split slabs below this many rows
+    I32 small_cap = 4096 ;                  // shared-memory doubles up to which a front takes k_front_small (0: off)
+    I32 small_cap_used = 0 ;                // the value the current plan was made with
+    int update_rsf_max = 8 ;                // max row split (cluster size) of the K = 32 update kernel
+    I64 lookahead_elems = 8000000 ;         // levels whose largest front (bound) has at least this many entries
     I32 wide_rows = 4096 ;                  // levels whose tallest front has at least this many rows: two-level path
     I32 grid_rows = 6100 ;                  // levels with taller fronts take k_panel_grid
     unsigned char *d_owned = nullptr ;
@@ -460,24 +471,68 @@ int partition_fronts (I64 nf, const int64_t *Childp, const int64_t *Child, const
     return STMQR_OK ;
 }
 
+constexpr I32 SMALL_TINY_ELEMS = 1024 ;     // boundary between the two shared-memory classes
+
+// shared-memory doubles of a front in k_front_small, or 0 if the front is not eligible
+inline I64 small_footprint (I64 FmB, I64 fn, I32 small_cap)
+{
+    const I64 e = (FmB + 2) * fn ;
+    return (small_cap > 0 && fn <= SMALL_MAX_FN && e <= small_cap) ? e : 0 ;
+}
+
+// order the fronts of one level ([big by # columns descending | small by footprint descending]) and
+// fill the level's statistics
+void finish_level (Level &L, std::vector<I32> &v, const std::vector<I32> &Rp, const std::vector<I32> &FmB,
+    I32 small_cap, I32 wide_rows)
+{
+    std::stable_sort (v.begin (), v.end (), [&] (I32 a, I32 b) {
+        const I64 fa = Rp [a+1] - Rp [a], fb = Rp [b+1] - Rp [b] ;
+        const I64 sa = small_footprint (FmB [a], fa, small_cap), sb = small_footprint (FmB [b], fb, small_cap) ;
+        if ((sa == 0) != (sb == 0)) return sa == 0 ;        // big fronts first
+        if (sa == 0) return fa > fb ;                       // big: # columns descending
+        return sa > sb ; }) ;                               // small: footprint descending
+    L.count = (I32) v.size () ;
+    L.nbig = 0 ; L.maxfn = 0 ; L.maxFelems = 0 ; L.maxFm = 0 ;
+    for (int c = 0 ; c < 2 ; c++) { L.nsmall [c] = 0 ; L.scap [c] = 0 ; L.srows [c] = 0 ; }
+    for (I32 f : v)
+    {
+        const I64 fn = Rp [f+1] - Rp [f] ;
+        const I64 sf = small_footprint (FmB [f], fn, small_cap) ;
+        if (sf == 0)
+        {
+            L.nbig++ ;
+            L.maxfn = std::max<I32> (L.maxfn, (I32) fn) ;
+            L.maxFelems = std::max (L.maxFelems, (I64) FmB [f] * fn) ;
+            L.maxFm = std::max (L.maxFm, FmB [f]) ;
+        }
+        else
+        {
+            const int c = (sf <= SMALL_TINY_ELEMS) ? 1 : 0 ;
+            L.nsmall [c]++ ;
+            L.scap [c] = std::max<I32> (L.scap [c], (I32) sf) ;
+            L.srows [c] = std::max<I32> (L.srows [c], FmB [f] + 2) ;
+        }
+    }
+    plan_wide (L, wide_rows) ;
+}
+
 void filter_levels (const LevelSet &all, const std::vector<unsigned char> &keep, const std::vector<I32> &Rp,
-    const std::vector<I32> &FmB, I32 wide_rows, LevelSet &out)
+    const std::vector<I32> &FmB, I32 small_cap, I32 wide_rows, LevelSet &out)
 {
     out.levels.clear () ; out.fronts.clear () ;
     for (const Level &Lv : all.levels)
     {
-        Level L ; L.first = (I32) out.fronts.size () ; L.count = 0 ; L.maxfn = 0 ; L.maxFelems = 0 ; L.maxFm = 0 ;
+        std::vector<I32> v ;
         for (I32 i = 0 ; i < Lv.count ; i++)
         {
             const I32 f = all.fronts [Lv.first + i] ;
-            if (!keep [f]) continue ;
-            const I64 fn = Rp [f+1] - Rp [f] ;
-            L.maxfn = std::max<I32> (L.maxfn, (I32) fn) ;
-            L.maxFelems = std::max (L.maxFelems, (I64) FmB [f] * fn) ;
-            L.maxFm = std::max (L.maxFm, FmB [f]) ;
-            out.fronts.push_back (f) ; L.count++ ;
+            if (keep [f]) v.push_back (f) ;
         }
-        if (L.count > 0) { plan_wide (L, wide_rows) ; out.levels.push_back (L) ; }
+        if (v.empty ()) continue ;
+        Level L ; L.first = (I32) out.fronts.size () ;
+        finish_level (L, v, Rp, FmB, small_cap, wide_rows) ;
+        for (I32 f : v) out.fronts.push_back (f) ;
+        out.levels.push_back (L) ;
     }
 }
 
@@ -509,6 +564,9 @@ int stmqr_b200_create (int device, stmqr_handle *out)
     h->nsm = std::min (148, prop.multiProcessorCount) ;
     if (const char *e = getenv ("STMQR_B200_GRID_ROWS")) h->grid_rows = std::max (256, atoi (e)) ;
     if (const char *e = getenv ("STMQR_B200_WIDE_ROWS")) h->wide_rows = std::max (256, atoi (e)) ;
+    if (const char *e = getenv ("STMQR_B200_SMALL_ELEMS")) h->small_cap = std::max (0, std::min (5600, atoi (e))) ;
+    if (const char *e = getenv ("STMQR_B200_UPDATE_RSF")) h->update_rsf_max = std::max (1, std::min (8, atoi (e))) ;
+    if (const char *e = getenv ("STMQR_B200_LOOKAHEAD_ELEMS")) h->lookahead_elems = std::max (1LL, atoll (e)) ;
     if (const char *e = getenv ("STMQR_B200_CLUSTER_MAX")) h->cluster_max = std::max (1, std::min (16, atoi (e))) ;
     if (const char *e = getenv ("STMQR_B200_CLUSTER_ROWS")) h->cluster_rows = std::max (32, atoi (e)) ;
     if (const char *e = getenv ("STMQR_B200_FLAGS")) h->opt.reserved = (int32_t) strtol (e, nullptr, 0) ;
@@ -726,28 +784,29 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     h->ls_all = LevelSet () ; h->ls_sub = LevelSet () ; h->ls_top = LevelSet () ;
     h->h_parent = parent ; h->nparts = 1 ; h->mypart = 0 ; h->h_owner.clear () ; h->h_istop.clear () ;
     h->Fcap = 0 ; h->maxLevelWidth = 0 ;
+    // the fused shared-memory path of the small fronts (off under debug capture: the assembled F of
+    // every front is tapped from the front arena)
+    h->small_cap_used = h->debug_capture ? 0 : h->small_cap ;
+    if (h->opt.small_elems > 0) h->small_cap_used = h->debug_capture ? 0 : std::min<I32> (h->opt.small_elems, 5600) ;
+    if (h->opt.reserved & 8) h->small_cap_used = 0 ;
+    I64 nsmall_tot = 0 ;
     for (I32 l = 0 ; l < nlev ; l++)
     {
         auto &v = byLevel [l] ;
-        std::stable_sort (v.begin (), v.end (), [&] (I32 a, I32 b) {
-            return (Rp [a+1] - Rp [a]) > (Rp [b+1] - Rp [b]) ; }) ;
-        Level L ; L.first = (I32) h->ls_all.fronts.size () ; L.count = (I32) v.size () ;
-        L.maxfn = 0 ; L.maxFelems = 0 ; L.maxFm = 0 ;
+        Level L ; L.first = (I32) h->ls_all.fronts.size () ;
+        finish_level (L, v, Rp, FmB, h->small_cap_used, h->wide_rows) ;
         I64 off = 0 ;
         for (I32 f : v)
         {
             const I64 fn = Rp [f+1] - Rp [f] ;
             const I64 fe = (I64) FmB [f] * fn ;
-            L.maxfn = std::max<I32> (L.maxfn, (I32) fn) ;
-            L.maxFelems = std::max (L.maxFelems, fe) ;
-            L.maxFm = std::max (L.maxFm, FmB [f]) ;
             h->h_Foff [f] = off ;
             off += (fe + 1) & ~(I64) 1 ;            // keep every front 16-byte aligned
             h->ls_all.fronts.push_back (f) ;
         }
         h->Fcap = std::max (h->Fcap, off) ;
-        h->maxLevelWidth = std::max (h->maxLevelWidth, L.count) ;
-        plan_wide (L, h->wide_rows) ;
+        h->maxLevelWidth = std::max (h->maxLevelWidth, std::max<I32> (L.nbig, 1)) ;
+        nsmall_tot += L.nsmall [0] + L.nsmall [1] ;
         h->ls_all.levels.push_back (L) ;
     }
 
@@ -799,7 +858,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
         for (const Level &Lv : h->ls_all.levels)
         {
             if (!Lv.wide) continue ;
-            const I64 c = Lv.count ;
+            const I64 c = Lv.nbig ;
             pslots = std::max (pslots, (I64) WB_PANELS * c) ;
             vb = std::max (vb, 2 * c * (I64) Lv.ldv * WB) ;
             tb = std::max (tb, 2 * c * (I64) (WB * WB)) ;
@@ -816,7 +875,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     ALLOC (N.Tws, pslots * PANEL_MAX * PANEL_MAX) ;
     {
         I64 gslots = 1 ;
-        for (const Level &Lv : h->ls_all.levels) if (Lv.maxFm >= h->grid_rows) gslots = std::max<I64> (gslots, Lv.count) ;
+        for (const Level &Lv : h->ls_all.levels) if (Lv.maxFm >= h->grid_rows) gslots = std::max<I64> (gslots, Lv.nbig) ;
         ALLOC (N.gridrec, gslots * 2 * 148 * 64) ;
         ALLOC (N.gridred, gslots * 2 * 148) ;
         ALLOC (N.gridll, gslots * 2 * 148 * 64) ;
@@ -864,6 +923,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     memset (&h->stats, 0, sizeof (h->stats)) ;
     h->stats.ms_plan = std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now () - t0).count () ;
     h->stats.nlevels = (I64) h->ls_all.levels.size () ;
+    h->stats.nf_small = nsmall_tot ; h->stats.nf_big = nf - nsmall_tot ;
     h->stats.device_bytes = (I64) h->device_bytes ;
     return STMQR_OK ;
 }
@@ -956,25 +1016,27 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
         levelno++ ;
         h->curtag = levelno << 32 ;
         const I32 *fr = LS.d_fronts + Lv.first ;
-        LAUNCH (1, k_front_setup<<<Lv.count, 128, 0, st>>> (fr, S, N)) ;
+        const I32 nbig = Lv.nbig ;
+        const int nsl = (int) std::min<I64> (148, std::max<I64> (1, Lv.maxFelems / 8192)) ;
+        auto big_path = [&] () -> int {
+        LAUNCH (1, k_front_setup<<<nbig, 128, 0, st>>> (fr, S, N)) ;
         // levels with large fronts: the ACTUAL # rows of the tallest front decides which kernels run
         // (the symbolic bound is ~2x too big under rank detection).  One tiny read-back per such level.
         I32 actFm = Lv.maxFm ;
         if (Lv.wide || Lv.maxFm >= h->grid_rows)
         {
-            k_level_maxfm<<<1, 256, 0, st>>> (fr, Lv.count, N) ; h->launches++ ;
+            k_level_maxfm<<<1, 256, 0, st>>> (fr, nbig, N) ; h->launches++ ;
             CK (cudaMemcpyAsync (h->pin_lvl, N.lvlstat, sizeof (I32), cudaMemcpyDeviceToHost, st)) ;
             CK (cudaStreamSynchronize (st)) ;
             actFm = std::min (Lv.maxFm, std::max (1, h->pin_lvl [0])) ;
         }
-        int nsl = (int) std::min<I64> (148, std::max<I64> (1, Lv.maxFelems / 8192)) ;
-        LAUNCH (2, k_assemble<<<dim3 (Lv.count, nsl), 256, 0, st>>> (fr, S, N)) ;
+        LAUNCH (2, k_assemble<<<dim3 (nbig, nsl), 256, 0, st>>> (fr, S, N)) ;
         if (h->debug_capture)
         {
             CK (cudaStreamSynchronize (st)) ;
             std::vector<I32> hm ((size_t) h->nf) ;
             CK (cudaMemcpy (hm.data (), N.Hm, h->nf * sizeof (I32), cudaMemcpyDeviceToHost)) ;
-            for (I32 i = 0 ; i < Lv.count ; i++)
+            for (I32 i = 0 ; i < nbig ; i++)
             {
                 I32 f = LS.fronts [Lv.first + i] ;
                 I64 cnt = (I64) hm [f] * (h->h_Rp [f+1] - h->h_Rp [f]) ;
@@ -982,14 +1044,14 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
                     cnt * sizeof (double), cudaMemcpyDeviceToDevice)) ;
             }
         }
-        LevelArgs L ; L.fronts = fr ; L.count = Lv.count ; L.tol = tol ; L.ntol = ntol ;
+        LevelArgs L ; L.fronts = fr ; L.count = nbig ; L.tol = tol ; L.ntol = ntol ;
         // ---- front QR of the level: panel steps of PB columns over all active fronts ---------------
         // cluster size: the row slab of one CTA (rows / CS x PB doubles) should fit in shared memory
         int CS = 1 ;
         while (CS < PANEL_CLUSTER_MAX && ((I64) (actFm + CS - 1) / CS + 4) * PB > PANEL_SLAB_MAX_DOUBLES) CS *= 2 ;
         // few fronts in the level: idle SMs are better spent on shorter slabs (a column step sweeps the
         // slab three times through shared memory); up to the non-portable cluster size 16
-        while (CS < h->cluster_max && (I64) Lv.count * CS * 2 <= h->nsm && (actFm + CS - 1) / CS > h->cluster_rows) CS *= 2 ;
+        while (CS < h->cluster_max && (I64) nbig * CS * 2 <= h->nsm && (actFm + CS - 1) / CS > h->cluster_rows) CS *= 2 ;
         const I64 rowsPerCta = ((I64) (actFm + CS - 1) / CS + 7) & ~(I64) 3 ;
         // (at least 2 x 32 x 33 doubles: the leader builds T in the slab after writing it back)
         const I32 slabCap = (I32) std::max<I64> (2 * PANEL_MAX * (PANEL_MAX + 1),
@@ -1044,20 +1106,37 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
         auto launch_update = [&] (cudaStream_t su, I32 nfronts, I32 cbeg, I32 cend, I32 parity) {
             if (nfronts <= 0 || cbeg >= cend) return ;
             // few CTAs (less than one per SM): deeper ring per CTA; many: two CTAs per SM
-            const I64 ctas = (I64) nfronts * ((cend - cbeg + UPD_NC - 1) / UPD_NC) ;
-            const dim3 grid (nfronts, (cend - cbeg + UPD_NC - 1) / UPD_NC) ;
-            if (nc_update == 4 || (nc_update == 0 && ctas <= 148))
-                k_update_dmma<4><<<grid, 256, update_smem_bytes<4> (), su>>> (L, S, N, cbeg, cend, parity) ;
+            const I32 ntile = (cend - cbeg + UPD_NC - 1) / UPD_NC ;
+            const I64 ctas = (I64) nfronts * ntile ;
+            // too few column tiles to fill the GPU and tall fronts: split the rows over a cluster
+            I32 rsf = 1 ;
+            while (rsf < h->update_rsf_max && ctas * rsf * 2 <= 4 * (I64) h->nsm && actFm / (rsf * 2) >= 256) rsf *= 2 ;
+            cudaLaunchConfig_t cfg = {} ;
+            cfg.gridDim = dim3 (nfronts, ntile, rsf) ;
+            cfg.blockDim = dim3 (256, 1, 1) ;
+            cfg.stream = su ;
+            cudaLaunchAttribute at [1] ;
+            at [0].id = cudaLaunchAttributeClusterDimension ;
+            at [0].val.clusterDim.x = 1 ; at [0].val.clusterDim.y = 1 ; at [0].val.clusterDim.z = rsf ;
+            cfg.attrs = at ; cfg.numAttrs = (rsf > 1) ? 1 : 0 ;
+            if (nc_update == 4 || (nc_update == 0 && ctas * rsf <= h->nsm))
+            {
+                cfg.dynamicSmemBytes = update_smem_bytes<4> () ;
+                cudaLaunchKernelEx (&cfg, k_update_dmma<4>, L, S, N, cbeg, cend, parity, rsf) ;
+            }
             else
-                k_update_dmma<2><<<grid, 256, update_smem_bytes<2> (), su>>> (L, S, N, cbeg, cend, parity) ;
+            {
+                cfg.dynamicSmemBytes = update_smem_bytes<2> () ;
+                cudaLaunchKernelEx (&cfg, k_update_dmma<2>, L, S, N, cbeg, cend, parity, rsf) ;
+            }
         } ;
         // look-ahead pays only when the trailing update is much bigger than its first 32 columns
-        const bool lookahead = !h->opt.profile_phases && !(h->opt.reserved & 1) && Lv.maxFelems >= (I64) 8000000 ;
+        const bool lookahead = !h->opt.profile_phases && !(h->opt.reserved & 1) && Lv.maxFelems >= h->lookahead_elems ;
         const bool wide = Lv.wide && actFm >= h->wide_rows && !(h->opt.reserved & 2) && PB == PANEL_MAX ;
         if (wide)
         {
             // ---- two-level blocking (kernels_wide.cuh): outer blocks of 128 columns = 4 panels -------
-            WideArgs WA ; WA.fronts = fr ; WA.count = Lv.count ; WA.buf = 0 ; WA.ldv = Lv.ldv ;
+            WideArgs WA ; WA.fronts = fr ; WA.count = nbig ; WA.buf = 0 ; WA.ldv = Lv.ldv ;
             WA.rs = WIDE_RS ; WA.nsplit = Lv.nsplit ; WA.ncmax = Lv.maxfn ;
             WideArgs WI = WA ; WI.rs = WIDE_RS_IN ; WI.nsplit = Lv.nsplit_in ;
             const I32 nrt = std::min<I32> (Lv.ldv / W_RT, (actFm + W_RT - 1) / W_RT) ;
@@ -1087,13 +1166,13 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
             for (I32 J = 0 ; J < nblk ; J++)
             {
                 const I32 j0 = J * WB ;
-                if (active_at (j0, Lv.count) == 0) break ;
+                if (active_at (j0, nbig) == 0) break ;
                 WA.buf = WI.buf = J & 1 ;
                 for (I32 p = 0 ; p < WB_PANELS ; p++)
                 {
                     const I32 k1 = j0 + p * PANEL_MAX ;
                     if (k1 >= Lv.maxfn) break ;
-                    const I32 act = active_at (k1, Lv.count) ;
+                    const I32 act = active_at (k1, nbig) ;
                     if (act == 0) break ;
                     h->curtag = (levelno << 32) | (long long) k1 ;
                     LAUNCH (3, CK (launch_panel (act, k1, p))) ;
@@ -1104,7 +1183,7 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
                 }
                 const I32 cb = j0 + WB ;
                 if (cb >= Lv.maxfn) break ;
-                const I32 act2 = active_at (cb, Lv.count) ;
+                const I32 act2 = active_at (cb, nbig) ;
                 if (act2 == 0) break ;
                 LAUNCH (13, k_wide_tmerge<<<act2, 1024, wide_tmerge_smem_bytes (), st>>> (WI, S, N)) ;
                 if (lookahead)
@@ -1137,7 +1216,7 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
         }
         else
         {
-            I32 active = active_at (0, Lv.count) ;
+            I32 active = active_at (0, nbig) ;
             if (active > 0) { LAUNCH (3, CK (launch_panel (active, 0, 0))) ; }
             for (I32 j = 0 ; active > 0 ; j++)
             {
@@ -1176,7 +1255,7 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
             CK (cudaStreamSynchronize (st)) ;
             std::vector<I32> hm ((size_t) h->nf) ;
             CK (cudaMemcpy (hm.data (), N.Hm, h->nf * sizeof (I32), cudaMemcpyDeviceToHost)) ;
-            for (I32 i = 0 ; i < Lv.count ; i++)
+            for (I32 i = 0 ; i < nbig ; i++)
             {
                 I32 f = LS.fronts [Lv.first + i] ;
                 I64 cnt = (I64) hm [f] * (h->h_Rp [f+1] - h->h_Rp [f]) ;
@@ -1184,7 +1263,21 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
                     cnt * sizeof (double), cudaMemcpyDeviceToDevice)) ;
             }
         }
-        LAUNCH (5, k_front_finish<<<Lv.count, 128, 0, st>>> (fr, S, N)) ;
+        LAUNCH (5, k_front_finish<<<nbig, 128, 0, st>>> (fr, S, N)) ;
+        return STMQR_OK ;
+        } ;
+        if (nbig > 0) { const int sb = big_path () ; if (sb != STMQR_OK) return sb ; }
+        // ---- the small fronts of the level: one warp per front, everything in shared memory -----------
+        {
+            I32 first = nbig ;
+            for (int c = 0 ; c < 2 ; c++)
+            {
+                if (Lv.nsmall [c] == 0) continue ;
+                const size_t smem = small_smem_bytes (Lv.scap [c], Lv.srows [c]) ;
+                LAUNCH (3, k_front_small<<<Lv.nsmall [c], 32, smem, st>>> (fr + first, S, N, tol, ntol, Lv.scap [c], Lv.srows [c])) ;
+                first += Lv.nsmall [c] ;
+            }
+        }
         LAUNCH (5, k_level_alloc<<<1, 1024, 0, st>>> (fr, Lv.count, N)) ;
         LAUNCH (6, k_pack<<<dim3 (Lv.count, nsl), 256, 0, st>>> (fr, S, N)) ;
         if (h->streaming && h->stream_levels < STREAM_MAX_LEVELS)
@@ -1431,8 +1524,8 @@ int stmqr_b200_set_partition (stmqr_handle h, int nparts, int mypart, const int3
         sub [f] = owned [f] && !is_top [f] ;
         top [f] = owned [f] && is_top [f] ;
     }
-    filter_levels (h->ls_all, sub, h->h_Rp, h->h_FmB, h->wide_rows, h->ls_sub) ;
-    filter_levels (h->ls_all, top, h->h_Rp, h->h_FmB, h->wide_rows, h->ls_top) ;
+    filter_levels (h->ls_all, sub, h->h_Rp, h->h_FmB, h->small_cap_used, h->wide_rows, h->ls_sub) ;
+    filter_levels (h->ls_all, top, h->h_Rp, h->h_FmB, h->small_cap_used, h->wide_rows, h->ls_top) ;
     UPLOAD (h->ls_sub.d_fronts, h->ls_sub.fronts) ;
     UPLOAD (h->ls_top.d_fronts, h->ls_top.fronts) ;
     if (nparts > 1) { UPLOAD (h->d_owned, owned) ; h->N.owned = h->d_owned ; }
