@@ -225,6 +225,9 @@ def run_b200_arm(args):
     sym = ref.symbolic(QR)
     At, ttol, ntol = ref.tapped()
 
+    # one engine at a time on the device: the drop-in's own handle (used by host_setup's first
+    # factorization and again by the e2e leg below) is released while the resident leg runs
+    ref.dropin_shutdown()
     eng = sq.Engine(local)
     eng.set_options(panel=args.panel)
     eng.analyze(sym)
@@ -273,42 +276,6 @@ def run_b200_arm(args):
         t_dev = float(tt[0].item())
         launches = int(t2[1].item())
 
-    # ---------------- e2e: host sparse_csc in, host qr_numeric out -----------------------------
-    # one GPU: through the reference-facing plug-in, qr_factorize (drop-in) called by the reference
-    # host library.  several GPUs: every rank uploads A from host memory, the partitioned numeric
-    # phase runs, every rank downloads the R+H blocks of its own fronts into host arrays.
-    e2e_s = []
-    can_e2e = setup["n1cols"] == 0
-    rh_local = int(info.rh_size)
-    if can_e2e:
-        for s in range(min(args.warmup, 2) + args.steps):
-            flush.zero_()
-            barrier()
-            if pf is None:
-                t = ref.refactorize(A, QR)
-            else:
-                t0 = time.perf_counter()
-                eng.upload_matrix(At)
-                inf = pf.factorize(ttol, ntol)[rank]
-                eng.download(inf)
-                barrier()
-                t = time.perf_counter() - t0
-            if s >= min(args.warmup, 2):
-                e2e_s.append(t)
-    clocks = sampler.stop()
-    t_e2e = float(np.sum(e2e_s)) if e2e_s else None
-    rh_total = rh_local
-    if dist is not None:
-        tt = torch.tensor([t_e2e or 0.0], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_e2e = float(tt.item()) if t_e2e is not None else None
-        tt = torch.tensor([float(rh_local)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
-        rh_total = int(tt.item())
-    rh_bytes = rh_total * 8
-    h2d = ((sym.n + 1) * 8 + sym.anz * 16) * world
-    d2h = rh_bytes + (8 * (2 * sym.rjsize + sym.hisize + 3 * sym.nf + sym.m) + sym.n) * world
-
     # ---------------- roofline of the dominant kernel class (extra, untimed steps) ------------
     eng.set_options(panel=args.panel, profile_phases=1)
     cls_ms = np.zeros(8)
@@ -351,6 +318,45 @@ def run_b200_arm(args):
     roof["fp64_dmma_peak_tflops"] = dmma_tf
     roof["fp64_dfma_peak_tflops"] = dfma_tf
     eng.set_options(panel=args.panel, profile_phases=0)
+
+    if pf is None:
+        eng.close()                                   # the e2e leg below uses the drop-in's own handle
+
+    # ---------------- e2e: host sparse_csc in, host qr_numeric out -----------------------------
+    # one GPU: through the reference-facing plug-in, qr_factorize (drop-in) called by the reference
+    # host library.  several GPUs: every rank uploads A from host memory, the partitioned numeric
+    # phase runs, every rank downloads the R+H blocks of its own fronts into host arrays.
+    e2e_s = []
+    can_e2e = setup["n1cols"] == 0
+    rh_local = int(info.rh_size)
+    if can_e2e:
+        for s in range(min(args.warmup, 2) + args.steps):
+            flush.zero_()
+            barrier()
+            if pf is None:
+                t = ref.refactorize(A, QR)
+            else:
+                t0 = time.perf_counter()
+                eng.upload_matrix(At)
+                inf = pf.factorize(ttol, ntol)[rank]
+                eng.download(inf)
+                barrier()
+                t = time.perf_counter() - t0
+            if s >= min(args.warmup, 2):
+                e2e_s.append(t)
+    clocks = sampler.stop()
+    t_e2e = float(np.sum(e2e_s)) if e2e_s else None
+    rh_total = rh_local
+    if dist is not None:
+        tt = torch.tensor([t_e2e or 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_e2e = float(tt.item()) if t_e2e is not None else None
+        tt = torch.tensor([float(rh_local)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        rh_total = int(tt.item())
+    rh_bytes = rh_total * 8
+    h2d = ((sym.n + 1) * 8 + sym.anz * 16) * world
+    d2h = rh_bytes + (8 * (2 * sym.rjsize + sym.hisize + 3 * sym.nf + sym.m) + sym.n) * world
 
     # ---------------- CPU baseline: the reference's own qr_factorize on this box's cores --------
     cpu = None

@@ -199,6 +199,11 @@ class Reference:
         else:
             raise ValueError(backend)
 
+    @staticmethod
+    def dropin_shutdown():
+        """release the device memory held by the drop-in's engine handle (it re-plans on its next call)"""
+        C.CDLL(sq.DROPIN_PATH).stmqr_b200_dropin_shutdown()
+
     def sparseqr(self, A, ordering_arg: int, tol: float, grain: float = 1.0, pool: int = 0,
                  blas_threads: int = 1, tap: bool = False):
         self.L.rh_set_blas_threads(blas_threads)
