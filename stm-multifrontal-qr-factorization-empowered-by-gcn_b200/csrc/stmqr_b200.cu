@@ -187,7 +187,7 @@ struct stmqr_handle_s
     I32 small_cap = 4096 ;                  // shared-memory doubles up to which a front takes k_front_small (0: off)
     I32 small_cap_used = 0 ;                // the value the current plan was made with
     int update_rsf_max = 8 ;                // max row split (cluster size) of the K = 32 update kernel
-    I64 lookahead_elems = 8000000 ;         // levels whose largest front (bound) has at least this many entries
+    I64 lookahead_elems = 1000000 ;         // levels whose largest front (bound) has at least this many entries
     I32 wide_rows = 4096 ;                  // levels whose tallest front has at least this many rows: two-level path
     I32 grid_rows = 6100 ;                  // levels with taller fronts take k_panel_grid
     unsigned char *d_owned = nullptr ;
@@ -1056,7 +1056,10 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
         // (at least 2 x 32 x 33 doubles: the leader builds T in the slab after writing it back)
         const I32 slabCap = (I32) std::max<I64> (2 * PANEL_MAX * (PANEL_MAX + 1),
             std::min<I64> (PANEL_SLAB_MAX_DOUBLES, rowsPerCta * PB)) ;
-        int pthreads = (rowsPerCta >= 256) ? 512 : ((rowsPerCta >= 64) ? 256 : 128) ;
+        // 8 warps per CTA beat 16 even on 768-row slabs (measured: a column step is latency bound, and
+        // two CTAs of different fronts per SM hide each other's exchanges); 16 only on request
+        int pthreads = (rowsPerCta >= 64) ? 256 : 128 ;
+        if (((h->opt.reserved >> 16) & 0xff) >= 16 && rowsPerCta >= 256) pthreads = 512 ;
         if ((h->opt.reserved >> 16) & 0xff) pthreads = std::min (pthreads, 32 * ((h->opt.reserved >> 16) & 0xff)) ;   // tuning
         // number of fronts of the level with more than k columns (sorted by # columns descending)
         auto active_at = [&] (I32 k, I32 hi) -> I32 {
