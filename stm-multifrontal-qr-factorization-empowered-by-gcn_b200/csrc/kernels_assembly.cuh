@@ -109,6 +109,24 @@ __global__ void k_front_setup (const I32 *__restrict__ fronts, DSym S, DNum N)
     }
 }
 
+// debug (STMQR_B200_CHECK=1): first front of the level whose F holds a non-finite value
+__global__ void k_check_finite (const I32 *__restrict__ fronts, I32 count, DSym S, DNum N, I32 *out)
+{
+    const I32 f = fronts [blockIdx.x] ;
+    const I32 fn = S.Rp [f+1] - S.Rp [f] ;
+    const I64 fm = N.Hm [f] ;
+    const double *F = N.F + S.Foff [f] ;
+    bool bad = false ;
+    I64 where = -1 ;
+    for (I64 e = threadIdx.x ; e < fm * fn ; e += blockDim.x)
+        if (!(fabs (F [e]) < 1e100)) { if (!bad) where = e ; bad = true ; }
+    if (bad)
+    {
+        const I32 old = atomicCAS (out, -1, f) ;
+        if (old == -1) { out [1] = (I32) (where % fm) ; out [2] = (I32) (where / fm) ; }
+    }
+}
+
 // max actual # rows over the fronts of one level (read back by the host for the large-front levels)
 __global__ void k_level_maxfm (const I32 *__restrict__ fronts, I32 count, DNum N)
 {

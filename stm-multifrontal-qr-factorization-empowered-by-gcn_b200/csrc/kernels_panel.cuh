@@ -232,11 +232,12 @@ __device__ __forceinline__ void panel_columns (cg::cluster_group &cluster, doubl
         else mx = 1.0 ;
         const double xnorm = mx * sqrt (ss) ;
         double beta = alpha, tau = 0, scale = 0 ;
-        if (t - g > 1 && xnorm != 0)
+        if (t - g > 1 && xnorm != 0 && hypot (alpha, xnorm) >= 1e-290)     // (underflowed noise: H = I)
         {
             beta = -copysign (hypot (alpha, xnorm), alpha) ;
             tau = (beta - alpha) / beta ;
             scale = 1.0 / (alpha - beta) ;
+            if (!(fabs (tau) <= 2.0) || !(fabs (scale) < 1e300)) { beta = alpha ; tau = 0 ; scale = 0 ; }
         }
         const bool dead = (k < ntol) && (fabs (beta) <= tol) ;
 
@@ -503,6 +504,15 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
             if (i + 2 * NW < i1) a6 = fma (xc [i + 2*NW], yc [i + 2*NW], a6) ;
             s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)) ;
         }
+        if (lane == c && s == 0.0)
+        {
+            // ||x||^2 = 0 over my rows: exactly zero entries, or squares that underflow?  Mark the
+            // second case with a positive value below every regular sum of squares, so that the total
+            // is 0 if and only if the sub-column is exactly zero (no extra exchange needed later)
+            bool nz = false ;
+            for (I32 i = ifirst ; i < i1 ; i += NW) nz |= (xc [i] != 0.0) ;
+            if (nz) s = 1e-300 ;
+        }
         PT_MARK (0) ;
         part [(par * NW + w) * PANEL_MAX + lane] = mycol ? s : 0.0 ;
         if (own_g) prow [par * PANEL_MAX + lane] = mycol ? yc [gi] : 0.0 ;
@@ -606,10 +616,37 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
             {
                 nrm = sqrt (fma (alpha, alpha, ss)) ;           // hypot (alpha, ||x||)
             }
+            else if (ss == 0)
+            {
+                // exactly zero sub-column (see the marker above): dlarfg returns tau = 0, beta = alpha
+                nrm = 0 ;
+            }
+            else if (ss <= 1e-280 && fabs (alpha) > 1e-120 && fabs (alpha) < 1e140)
+            {
+                // ||x|| <= 1e-140 (every x_i^2 <= ss) next to a pivot >= 1e-120: rounding noise of a
+                // sub-column that is zero in exact arithmetic (frequent in the top fronts of mesh
+                // problems).  H = I to far below double precision: same as dlarfg for x = 0 (tau = 0,
+                // beta = alpha); for noise dlarfg would return tau = 2, which only flips the sign of R's
+                // row.  No exchange needed (the rescale path below costs several cluster/grid barriers).
+                nrm = 0 ; ss = 0 ;
+            }
             else
             {
                 // rare: zero or badly scaled sub-column: max |x| first, then the rescaled sum of
                 // squares (dnrm2 semantics).  The decision is uniform over the cluster.
+#ifdef STMQR_PANEL_TIMING
+                if (tid == 0 && leader)
+                {
+                    atomicAdd (N.dbg + 63, 1ULL) ;
+                    if (ss == 0) atomicAdd (N.dbg + 62, 1ULL) ;
+                    if (ss > 0 && ss <= 1e-280) atomicAdd (N.dbg + 61, 1ULL) ;
+                    if (ss >= 1e280) atomicAdd (N.dbg + 60, 1ULL) ;
+                    if (!(ss == ss)) atomicAdd (N.dbg + 59, 1ULL) ;
+                    if (fabs (alpha) <= 1e-120) atomicAdd (N.dbg + 58, 1ULL) ;
+                    if (alpha == 0) atomicAdd (N.dbg + 57, 1ULL) ;
+                    if (fabs (alpha) >= 1e140) atomicAdd (N.dbg + 56, 1ULL) ;
+                }
+#endif
                 double mx = 0 ;
                 for (I32 i = ifirst ; i < i1 ; i += NW) mx = fmax (mx, fabs (xc [i])) ;
                 mx = panel_allreduce<NW, true, GRID> (cluster, gc, ECS, mx, red, xch [par], par) ;
@@ -621,6 +658,10 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
                     s2 = panel_allreduce<NW, false, GRID> (cluster, gc, ECS, s2, red + NW, xch [par], par) ;
                     nrm = hypot (alpha, mx * sqrt (s2)) ;
                     ss = 1.0 ;
+                    // pivot and sub-column both below ~safmin/eps (underflowed rounding noise deep in a
+                    // large front): 1/(alpha-beta) would overflow.  dlarfg rescales by 1/safmin here; the
+                    // column is numerically zero either way, so H = I (tau = 0, beta = alpha)
+                    if (!(nrm >= 1e-290)) { nrm = 0 ; ss = 0 ; }
                 }
                 else { nrm = 0 ; ss = 0 ; }
             }
@@ -629,6 +670,8 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
                 beta = -copysign (nrm, alpha) ;
                 tau = (beta - alpha) / beta ;
                 scale = 1.0 / (alpha - beta) ;
+                // safety net (overflow of the norm or of 1/(alpha-beta)): never emit a non-finite reflector
+                if (!(fabs (tau) <= 2.0) || !(fabs (scale) < 1e300)) { beta = alpha ; tau = 0 ; scale = 0 ; }
             }
         }
         const bool dead = (k < ntol) && (fabs (beta) <= tol) ;

@@ -187,6 +187,7 @@ __global__ void __launch_bounds__ (32) k_front_small (const I32 *__restrict__ fr
         {
             double nrm ;
             if (ss > 1e-280 && ss < 1e280 && fabs (alpha) < 1e140) nrm = sqrt (fma (alpha, alpha, ss)) ;
+            else if (ss <= 1e-280 && fabs (alpha) > 1e-120 && fabs (alpha) < 1e140) { nrm = 0 ; ss = 0 ; }   // noise: H = I (see kernels_panel.cuh)
             else
             {
                 // rare: zero or badly scaled sub-column (dnrm2 semantics)
@@ -201,6 +202,7 @@ __global__ void __launch_bounds__ (32) k_front_small (const I32 *__restrict__ fr
                     s2 = warp_sum (s2) ;
                     nrm = hypot (alpha, mx * sqrt (s2)) ;
                     ss = 1.0 ;
+                    if (!(nrm >= 1e-290)) { nrm = 0 ; ss = 0 ; }    // underflowed noise: H = I (see kernels_panel.cuh)
                 }
                 else { nrm = 0 ; ss = 0 ; }
             }
@@ -209,6 +211,7 @@ __global__ void __launch_bounds__ (32) k_front_small (const I32 *__restrict__ fr
                 beta = -copysign (nrm, alpha) ;
                 tau = (beta - alpha) / beta ;
                 scale = 1.0 / (alpha - beta) ;
+                if (!(fabs (tau) <= 2.0) || !(fabs (scale) < 1e300)) { beta = alpha ; tau = 0 ; scale = 0 ; }
             }
         }
         const bool dead = (k < ntol) && (fabs (beta) <= tol) ;

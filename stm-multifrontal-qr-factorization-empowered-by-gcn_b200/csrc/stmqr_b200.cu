@@ -180,6 +180,7 @@ struct stmqr_handle_s
     int serr = STMQR_OK ;
     bool stack_streamed = false ;
     I32 *pin_lvl = nullptr ;                // pinned: actual max # rows of the level being processed
+    bool check_hit = false ;                // STMQR_B200_CHECK: a non-finite value was already reported
     unsigned grid_seq = 0 ;                 // launch sequence number of k_panel_grid (tags of its exchange lines)
     int nsm = 148 ;                         // SMs of the device (k_panel_grid: one CTA per SM)
     int cluster_max = 8 ;                   // largest panel cluster (8 portable; 16 non-portable, no gain measured)
@@ -189,6 +190,7 @@ struct stmqr_handle_s
     int update_rsf_max = 8 ;                // max row split (cluster size) of the K = 32 update kernel
     I64 lookahead_elems = 1000000 ;         // levels whose largest front (bound) has at least this many entries
     I32 wide_rows = 4096 ;                  // levels whose tallest front has at least this many rows: two-level path
+    I32 grid_maxg = 128 ;                   // most CTAs per front of k_panel_grid (a grid on ALL SMs was measured 15x slower)
     I32 grid_rows = 6100 ;                  // levels with taller fronts take k_panel_grid
     unsigned char *d_owned = nullptr ;
     double cur_tol = -1 ; I64 cur_ntol = 0 ;
@@ -563,6 +565,7 @@ int stmqr_b200_create (int device, stmqr_handle *out)
     h->device = device ;
     h->nsm = std::min (148, prop.multiProcessorCount) ;
     if (const char *e = getenv ("STMQR_B200_GRID_ROWS")) h->grid_rows = std::max (256, atoi (e)) ;
+    if (const char *e = getenv ("STMQR_B200_GRID_MAXG")) h->grid_maxg = std::max (1, std::min (148, atoi (e))) ;
     if (const char *e = getenv ("STMQR_B200_WIDE_ROWS")) h->wide_rows = std::max (256, atoi (e)) ;
     if (const char *e = getenv ("STMQR_B200_SMALL_ELEMS")) h->small_cap = std::max (0, std::min (5600, atoi (e))) ;
     if (const char *e = getenv ("STMQR_B200_UPDATE_RSF")) h->update_rsf_max = std::max (1, std::min (8, atoi (e))) ;
@@ -1044,6 +1047,23 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
                     cnt * sizeof (double), cudaMemcpyDeviceToDevice)) ;
             }
         }
+        static const bool checking = getenv ("STMQR_B200_CHECK") != nullptr ;
+        auto check = [&] (const char *stage, long long a, long long b) {
+            if (!checking || h->check_hit) return ;
+            cudaStreamSynchronize (st) ; cudaStreamSynchronize (st2) ;
+            I32 init [4] = {-1, 0, 0, 0} ;
+            cudaMemcpy (N.lvlstat, init, sizeof (init), cudaMemcpyHostToDevice) ;
+            k_check_finite<<<nbig, 256, 0, st>>> (fr, nbig, S, N, N.lvlstat) ;
+            I32 res [4] ;
+            cudaMemcpy (res, N.lvlstat, sizeof (res), cudaMemcpyDeviceToHost) ;
+            if (res [0] >= 0)
+            {
+                h->check_hit = true ;
+                fprintf (stderr, "STMQR_B200_CHECK: first |F| >= 1e100 or non-finite after %s (level %lld, %lld, %lld): front %d row %d col %d\n",
+                    stage, levelno, a, b, res [0], res [1], res [2]) ;
+            }
+        } ;
+        check ("assemble", 0, 0) ;
         LevelArgs L ; L.fronts = fr ; L.count = nbig ; L.tol = tol ; L.ntol = ntol ;
         // ---- front QR of the level: panel steps of PB columns over all active fronts ---------------
         // cluster size: the row slab of one CTA (rows / CS x PB doubles) should fit in shared memory
@@ -1086,7 +1106,8 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
                     const I32 nb = std::min<I32> (per, active - s0) ;
                     // no more CTAs than the step-cost model of k_panel_grid can use (they all have to
                     // become resident before the panel starts)
-                    const I32 G = std::min<I32> (h->nsm / nb, std::max<I32> (gneed, (I32) std::sqrt (0.84 * (double) actFm) + 1)) ;
+                    const I32 G = std::min<I32> (std::min<I32> (h->nsm / nb, std::max<I32> (gneed, h->grid_maxg)),
+                        std::max<I32> (gneed, (I32) std::sqrt (0.84 * (double) actFm) + 1)) ;
                     k_panel_grid<<<(unsigned) (G * nb), 512, smem, st>>> (L, S, N, k1, (I32) PB, parity,
                         (I32) PANEL_SLAB_MAX_DOUBLES, G, s0, ++h->grid_seq) ;
                     if (s0 + per < active) h->launches++ ;
@@ -1266,6 +1287,7 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
                     cnt * sizeof (double), cudaMemcpyDeviceToDevice)) ;
             }
         }
+        check ("front QR", 0, 0) ;
         LAUNCH (5, k_front_finish<<<nbig, 128, 0, st>>> (fr, S, N)) ;
         return STMQR_OK ;
         } ;
@@ -1351,6 +1373,8 @@ int stmqr_b200_factorize_hpinv_b (stmqr_handle h, stmqr_numeric_info *info)
     {
         unsigned long long dbg [64] ;
         cudaMemcpy (dbg, N.dbg, sizeof (dbg), cudaMemcpyDeviceToHost) ;
+        fprintf (stderr, "panel rare (rescale) path taken %llu times: ss==0 %llu, 0<ss<=1e-280 %llu, ss>=1e280 %llu, nan %llu, |alpha|<=1e-120 %llu, alpha==0 %llu, |alpha|>=1e140 %llu\n",
+            dbg [63], dbg [62], dbg [61], dbg [60], dbg [59], dbg [58], dbg [57], dbg [56]) ;
         const char *nm [8] = {"dots", "bar", "reduce+xchg", "scalar", "update", "endsync", "epilogue", "looptop"} ;
         for (int b = 0 ; b < 48 ; b += 8)
         {

@@ -8,6 +8,7 @@ os.environ["STMQR_B200_CACHE_PLAN"] = "1"
 R, ref, A, QR, tol, desc, setup = bench.host_setup(wl, "b200")
 sym = ref.symbolic(QR)
 At, ttol, ntol = ref.tapped()
+ref.dropin_shutdown()
 import stmqr_b200 as sq
 for env in sys.argv[3:]:
     kv = dict(x.split("=") for x in env.split(",") if x)
