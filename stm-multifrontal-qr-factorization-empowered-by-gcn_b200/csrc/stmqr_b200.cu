@@ -190,7 +190,7 @@ struct stmqr_handle_s
     int update_rsf_max = 8 ;                // max row split (cluster size) of the K = 32 update kernel
     I64 lookahead_elems = 1000000 ;         // levels whose largest front (bound) has at least this many entries
     I32 wide_rows = 4096 ;                  // levels whose tallest front has at least this many rows: two-level path
-    I32 grid_maxg = 128 ;                   // most CTAs per front of k_panel_grid (a grid on ALL SMs was measured 15x slower)
+    I32 grid_maxg = 48 ;                    // most CTAs per front of k_panel_grid (48 measured best on 29k-row fronts: fewer records to poll)
     I32 grid_rows = 6100 ;                  // levels with taller fronts take k_panel_grid
     unsigned char *d_owned = nullptr ;
     double cur_tol = -1 ; I64 cur_ntol = 0 ;
