@@ -45,9 +45,9 @@ struct Level
     // small-front batching path (kernels_small.cuh): the list is [big fronts | small | tiny], the
     // small ones sorted by shared-memory footprint descending
     I32 nbig ;          // fronts that take the tiled kernels (first in the list)
-    I32 nsmall [2] ;    // fronts of the two shared-memory classes of k_front_small
-    I32 scap [2] ;      // doubles of shared memory per front of the class ((Fm+1) * fn, max)
-    I32 srows [2] ;     // max bound on the # rows in the class
+    I32 nsmall [3] ;    // fronts of the shared-memory classes of k_front_small (> 2048, > 1024, <= 1024 doubles)
+    I32 scap [3] ;      // doubles of shared memory per front of the class ((Fm+2) * fn, max)
+    I32 srows [3] ;     // max bound on the # rows in the class
     // two-level blocked path (kernels_wide.cuh): few, large fronts
     bool wide ;
     I32 ldv ;           // leading dimension of the clean V buffers
@@ -187,6 +187,7 @@ struct stmqr_handle_s
     I32 cluster_rows = 160 ;                // do not split slabs below this many rows
     I32 small_cap = 4096 ;                  // shared-memory doubles up to which a front takes k_front_small (0: off)
     I32 small_cap_used = 0 ;                // the value the current plan was made with
+    I32 panel128_rows = 256 ;               // levels of >= 2 fronts per SM with slabs up to this many rows: 128-thread panels
     int update_rsf_max = 8 ;                // max row split (cluster size) of the K = 32 update kernel
     I64 lookahead_elems = 1000000 ;         // levels whose largest front (bound) has at least this many entries
     I32 wide_rows = 4096 ;                  // levels whose tallest front has at least this many rows: two-level path
@@ -473,7 +474,7 @@ int partition_fronts (I64 nf, const int64_t *Childp, const int64_t *Child, const
     return STMQR_OK ;
 }
 
-constexpr I32 SMALL_TINY_ELEMS = 1024 ;     // boundary between the two shared-memory classes
+constexpr I32 SMALL_CLASS_ELEMS [2] = {2048, 1024} ;     // boundaries between the shared-memory classes
 
 // shared-memory doubles of a front in k_front_small, or 0 if the front is not eligible
 inline I64 small_footprint (I64 FmB, I64 fn, I32 small_cap)
@@ -495,7 +496,7 @@ void finish_level (Level &L, std::vector<I32> &v, const std::vector<I32> &Rp, co
         return sa > sb ; }) ;                               // small: footprint descending
     L.count = (I32) v.size () ;
     L.nbig = 0 ; L.maxfn = 0 ; L.maxFelems = 0 ; L.maxFm = 0 ;
-    for (int c = 0 ; c < 2 ; c++) { L.nsmall [c] = 0 ; L.scap [c] = 0 ; L.srows [c] = 0 ; }
+    for (int c = 0 ; c < 3 ; c++) { L.nsmall [c] = 0 ; L.scap [c] = 0 ; L.srows [c] = 0 ; }
     for (I32 f : v)
     {
         const I64 fn = Rp [f+1] - Rp [f] ;
@@ -509,7 +510,7 @@ void finish_level (Level &L, std::vector<I32> &v, const std::vector<I32> &Rp, co
         }
         else
         {
-            const int c = (sf <= SMALL_TINY_ELEMS) ? 1 : 0 ;
+            const int c = (sf <= SMALL_CLASS_ELEMS [1]) ? 2 : ((sf <= SMALL_CLASS_ELEMS [0]) ? 1 : 0) ;
             L.nsmall [c]++ ;
             L.scap [c] = std::max<I32> (L.scap [c], (I32) sf) ;
             L.srows [c] = std::max<I32> (L.srows [c], FmB [f] + 2) ;
@@ -568,6 +569,7 @@ int stmqr_b200_create (int device, stmqr_handle *out)
     if (const char *e = getenv ("STMQR_B200_GRID_MAXG")) h->grid_maxg = std::max (1, std::min (148, atoi (e))) ;
     if (const char *e = getenv ("STMQR_B200_WIDE_ROWS")) h->wide_rows = std::max (256, atoi (e)) ;
     if (const char *e = getenv ("STMQR_B200_SMALL_ELEMS")) h->small_cap = std::max (0, std::min (5600, atoi (e))) ;
+    if (const char *e = getenv ("STMQR_B200_PANEL128_ROWS")) h->panel128_rows = std::max (0, atoi (e)) ;
     if (const char *e = getenv ("STMQR_B200_UPDATE_RSF")) h->update_rsf_max = std::max (1, std::min (8, atoi (e))) ;
     if (const char *e = getenv ("STMQR_B200_LOOKAHEAD_ELEMS")) h->lookahead_elems = std::max (1LL, atoll (e)) ;
     if (const char *e = getenv ("STMQR_B200_CLUSTER_MAX")) h->cluster_max = std::max (1, std::min (16, atoi (e))) ;
@@ -809,7 +811,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
         }
         h->Fcap = std::max (h->Fcap, off) ;
         h->maxLevelWidth = std::max (h->maxLevelWidth, std::max<I32> (L.nbig, 1)) ;
-        nsmall_tot += L.nsmall [0] + L.nsmall [1] ;
+        nsmall_tot += L.nsmall [0] + L.nsmall [1] + L.nsmall [2] ;
         h->ls_all.levels.push_back (L) ;
     }
 
@@ -1079,6 +1081,8 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
         // 8 warps per CTA beat 16 even on 768-row slabs (measured: a column step is latency bound, and
         // two CTAs of different fronts per SM hide each other's exchanges); 16 only on request
         int pthreads = (rowsPerCta >= 64) ? 256 : 128 ;
+        // many short fronts: 4-warp CTAs, up to 5-6 of them per SM (tunable: STMQR_B200_PANEL128_ROWS)
+        if (rowsPerCta <= h->panel128_rows && (I64) nbig >= 2 * (I64) h->nsm) pthreads = 128 ;
         if (((h->opt.reserved >> 16) & 0xff) >= 16 && rowsPerCta >= 256) pthreads = 512 ;
         if ((h->opt.reserved >> 16) & 0xff) pthreads = std::min (pthreads, 32 * ((h->opt.reserved >> 16) & 0xff)) ;   // tuning
         // number of fronts of the level with more than k columns (sorted by # columns descending)
@@ -1295,7 +1299,7 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
         // ---- the small fronts of the level: one warp per front, everything in shared memory -----------
         {
             I32 first = nbig ;
-            for (int c = 0 ; c < 2 ; c++)
+            for (int c = 0 ; c < 3 ; c++)
             {
                 if (Lv.nsmall [c] == 0) continue ;
                 const size_t smem = small_smem_bytes (Lv.scap [c], Lv.srows [c]) ;

@@ -183,6 +183,11 @@ qr_numeric *stmqr_b200_qr_factorize (sparse_csc **Ahandle, Long freeA, double to
 #define STACK_HUGEPAGES(ptr, doubles) do { } while (0)
 #endif
 
+    /* the big integer / tau arrays are also written once, front to back, by the download */
+    STACK_HUGEPAGES (QRnum->HStair, rjsize) ;
+    STACK_HUGEPAGES (QRnum->HTau, rjsize) ;
+    STACK_HUGEPAGES (QRnum->Hii, hisize) ;
+    STACK_HUGEPAGES (QRnum->HPinv, m) ;
     if (streamed && cap > 0)
     {
         STACK_HUGEPAGES (QRnum->Stacks [0], cap) ;
