@@ -538,6 +538,138 @@ template <int KVT> constexpr size_t wide_apply_smem_bytes ()
 }
 
 // ---------------------------------------------------------------------------------------------
+// The K = 128 apply, persistent over row tiles: a CTA owns 64 columns, keeps its 128 x 64 tile of W2
+// in shared memory and walks down the rows (tiles rg, rg + nrg, ...) with ONE continuous cp.async ring
+// over the (row tile, 32-reflector slab) pairs of V: no pipeline fill / drain per 128 rows, W2 loaded
+// once.  The old values of C are loaded into registers when a row tile starts and added at its end.
+// grid = (column tiles x nrg, fronts).
+// ---------------------------------------------------------------------------------------------
+constexpr int WP_NST = 3 ;
+__global__ void __launch_bounds__ (256) k_wide_apply_rows (WideArgs A, DSym S, DNum N, I32 cbeg, I32 cend, I32 nct,
+    I32 nrg)
+{
+    constexpr int KVT = WB_PANELS ;
+    constexpr int VSLAB = PANEL_MAX * W_LDV ;           // one 32-reflector slab of V: [32][132]
+    constexpr int WSLAB = W_NC * W_LDC ;                // one 32-reflector slab of W2: [64][36]
+    extern __shared__ double sm [] ;
+    double *Wsm = sm ;                                  // [4][WSLAB]
+    double *ring = sm + KVT * WSLAB ;                   // [WP_NST][VSLAB]
+    const I32 slot = blockIdx.y ;
+    const I32 *blk = wide_blk (A, N, slot) ;
+    if (blk [2] == 0) return ;
+    const I32 g0 = blk [0], mr = blk [1] ;
+    const I32 f = A.fronts [slot] ;
+    const I32 fn = S.Rp [f+1] - S.Rp [f] ;
+    const I32 ct = blockIdx.x % nct, rg = blockIdx.x / nct ;
+    const I32 nrt = (mr + W_RT - 1) / W_RT ;
+    if (rg >= nrt) return ;
+    const I32 clim = min (cend, fn) ;
+    const I32 c0 = cbeg + ct * W_NC ;
+    if (c0 >= clim) return ;
+    const I32 ncol = min (W_NC, clim - c0) ;
+    const I64 fm = N.Hm [f] ;
+    double *Cbase = N.F + S.Foff [f] + g0 + (I64) c0 * fm ;
+    const double *Vb = wide_vb (A, N, slot) ;
+    const double *W2 = N.wW2 + (I64) slot * ((I64) A.ncmax * WB) + (I64) c0 * WB ;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5 ;
+    const int grp = lane >> 2, tig = lane & 3 ;
+    const int wr = w & 3, wc = w >> 2 ;
+
+    const I32 ntile = (nrt - rg + nrg - 1) / nrg ;      // my row tiles: rg, rg + nrg, ...
+    const I32 nq = ntile * KVT ;                        // (tile, slab) pairs
+
+    // W2 tile, all four slabs (first cp.async group)
+#pragma unroll
+    for (int a = 0 ; a < (KVT * W_NC * (PANEL_MAX / 2)) / 256 ; a++)
+    {
+        const int e = tid + a * 256 ;
+        const int kk = e >> 10, c = (e >> 4) & 63, g = e & 15 ;
+        const bool ok = (c < ncol) ;
+        cp_async16z (Wsm + kk * WSLAB + c * W_LDC + 2 * g, ok ? (W2 + (I64) c * WB + kk * PANEL_MAX + 2 * g) : W2, ok) ;
+    }
+    auto issue = [&] (const I32 q)
+    {
+        const I32 r0 = (rg + (q / KVT) * nrg) * W_RT ;
+        const int kk = q % KVT ;
+        double *Vs = ring + (q % WP_NST) * VSLAB ;
+        const double *Va = Vb + (I64) (kk * PANEL_MAX) * A.ldv + r0 ;
+#pragma unroll
+        for (int a = 0 ; a < (PANEL_MAX * (W_RT / 2)) / 256 ; a++)
+        {
+            const int e = tid + a * 256 ;
+            const int k = e >> 6, g = e & 63 ;
+            cp_async16 (Vs + k * W_LDV + 2 * g, Va + (I64) k * A.ldv + 2 * g) ;
+        }
+    } ;
+#pragma unroll
+    for (int s = 0 ; s < WP_NST - 1 ; s++)
+    {
+        if (s < nq) issue (s) ;
+        cp_async_commit () ;            // (the W2 tile rides in the first group)
+    }
+
+    double acc [4][4][2], cold [4][4][2] ;
+    for (I32 q = 0 ; q < nq ; q++)
+    {
+        const int kk = q % KVT ;
+        const I32 r0 = (rg + (q / KVT) * nrg) * W_RT ;
+        if (kk == 0)
+        {
+            double *C = Cbase + r0 ;
+#pragma unroll
+            for (int mi = 0 ; mi < 4 ; mi++)
+#pragma unroll
+                for (int ni = 0 ; ni < 4 ; ni++)
+#pragma unroll
+                    for (int e = 0 ; e < 2 ; e++)
+                    {
+                        const int r = wr * 32 + mi * 8 + grp, c = wc * 32 + ni * 8 + tig * 2 + e ;
+                        acc [mi][ni][e] = 0.0 ;
+                        cold [mi][ni][e] = (r0 + r < mr && c < ncol) ? __ldcg (C + r + (I64) c * fm) : 0.0 ;
+                    }
+        }
+        if (q + WP_NST - 1 < nq) issue (q + WP_NST - 1) ;
+        cp_async_commit () ;
+        cp_async_wait<WP_NST - 1> () ;
+        __syncthreads () ;
+        const double *Vs = ring + (q % WP_NST) * VSLAB, *Ws = Wsm + kk * WSLAB ;
+#pragma unroll
+        for (int ks = 0 ; ks < PANEL_MAX / 4 ; ks++)
+        {
+            double af [4], bf [4] ;
+#pragma unroll
+            for (int mi = 0 ; mi < 4 ; mi++) af [mi] = Vs [(ks * 4 + tig) * W_LDV + wr * 32 + mi * 8 + grp] ;
+#pragma unroll
+            for (int ni = 0 ; ni < 4 ; ni++) bf [ni] = Ws [(wc * 32 + ni * 8 + grp) * W_LDC + ks * 4 + tig] ;
+#pragma unroll
+            for (int mi = 0 ; mi < 4 ; mi++)
+#pragma unroll
+                for (int ni = 0 ; ni < 4 ; ni++) dmma_m8n8k4 (acc [mi][ni][0], acc [mi][ni][1], af [mi], bf [ni]) ;
+        }
+        __syncthreads () ;
+        if (kk == KVT - 1)
+        {
+            double *C = Cbase + r0 ;
+#pragma unroll
+            for (int mi = 0 ; mi < 4 ; mi++)
+#pragma unroll
+                for (int ni = 0 ; ni < 4 ; ni++)
+#pragma unroll
+                    for (int e = 0 ; e < 2 ; e++)
+                    {
+                        const int r = wr * 32 + mi * 8 + grp, c = wc * 32 + ni * 8 + tig * 2 + e ;
+                        if (r0 + r < mr && c < ncol) C [r + (I64) c * fm] = cold [mi][ni][e] + acc [mi][ni][e] ;
+                    }
+        }
+    }
+    cp_async_wait<0> () ;
+}
+constexpr size_t wide_apply_rows_smem_bytes ()
+{
+    return sizeof (double) * (size_t) (WB_PANELS * W_NC * W_LDC + WP_NST * PANEL_MAX * W_LDV) ;
+}
+
+// ---------------------------------------------------------------------------------------------
 // T of the outer block from its panels' T (dlarft of each panel, k_panel_cluster) and the Gram
 // matrix G = Vb'Vb:  T(0:32p, p) = -T(0:32p,0:32p) G(0:32p, p) T(p,p).  One CTA per front.  Output
 // transposed (k_wide_wt reads it coalesced): Tbt[q' + 128 q] = T(q,q').

@@ -612,6 +612,8 @@ int stmqr_b200_create (int device, stmqr_handle *out)
             (int) wide_apply_smem_bytes<1> ()) == cudaSuccess &&
         cudaFuncSetAttribute (k_wide_apply<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (int) wide_apply_smem_bytes<4> ()) == cudaSuccess &&
+        cudaFuncSetAttribute (k_wide_apply_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int) wide_apply_rows_smem_bytes ()) == cudaSuccess &&
         cudaFuncSetAttribute (k_wide_tmerge, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (int) wide_tmerge_smem_bytes ()) == cudaSuccess ;
     if (!ok)
@@ -1187,7 +1189,16 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
                 const I32 nct = (ce - cb + W_NC - 1) / W_NC ;
                 LAUNCH (14, k_wide_vtc<4><<<dim3 (nct * nsplA, nfronts), 256, wide_vtc_smem_bytes<4> (), su>>> (WA, S, N, WIDE_OUTER, 0, cb, ce, nct)) ;
                 LAUNCH (15, k_wide_wt<4><<<dim3 ((ce - cb + 15) / 16, nfronts), 256, 0, su>>> (WA, S, N, WIDE_OUTER, 0, cb, ce)) ;
-                LAUNCH (16, k_wide_apply<4><<<dim3 (nct * nrt, nfronts), 256, wide_apply_smem_bytes<4> (), su>>> (WA, S, N, WIDE_OUTER, 0, cb, ce, nct)) ;
+                if (h->opt.reserved & 16)
+                {
+                    LAUNCH (16, k_wide_apply<4><<<dim3 (nct * nrt, nfronts), 256, wide_apply_smem_bytes<4> (), su>>> (WA, S, N, WIDE_OUTER, 0, cb, ce, nct)) ;
+                }
+                else
+                {
+                    // row groups: about 3 CTAs per SM in total, every CTA walks down its share of the row tiles
+                    const I32 nrg = (I32) std::max<I64> (1, std::min<I64> (nrt, (3 * (I64) h->nsm + (I64) nct * nfronts - 1) / ((I64) nct * nfronts))) ;
+                    LAUNCH (16, k_wide_apply_rows<<<dim3 (nct * nrg, nfronts), 256, wide_apply_rows_smem_bytes (), su>>> (WA, S, N, cb, ce, nct, nrg)) ;
+                }
             } ;
             const I32 nblk = (Lv.maxfn + WB - 1) / WB ;
             bool pending [2] = {false, false} ;     // a "rest of the trailing matrix" update in flight on stream2
