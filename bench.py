@@ -344,8 +344,10 @@ def run_b200_arm(args):
             else:
                 t0 = time.perf_counter()
                 eng.upload_matrix(At)
+                stack = eng.stream_begin()                  # this rank's R+H blocks go to the host level by level
                 inf = pf.factorize(ttol, ntol)[rank]
-                eng.download(inf)
+                eng.stream_end()
+                eng.download(inf, stack=stack[: max(int(inf.rh_size), 1)])
                 barrier()
                 t = time.perf_counter() - t0
             if s >= min(args.warmup, 2):
@@ -413,8 +415,8 @@ def run_b200_arm(args):
                          "how": ("wall clock around qr_factorize (drop-in) called by the reference host "
                                  "library with a host sparse_csc; host qr_numeric out; plan cached "
                                  "(STMQR_B200_CACHE_PLAN=1)") if world == 1 else
-                                ("per rank: upload A from host, partitioned numeric phase, download of the "
-                                 "rank's own R+H blocks to host arrays; max over ranks"),
+                                ("per rank: upload A from host, partitioned numeric phase with the rank's own R+H "
+                                 "blocks streamed to host arrays level by level; max over ranks"),
                          "first_call_with_plan_s": setup["first_factorize_s"],
                          "plan_ms": float(st.ms_plan)} if t_e2e else None),
                 "gpu_launches": launches * args.steps,

@@ -178,6 +178,10 @@ int  stmqr_b200_factorize (stmqr_handle h, const stmqr_csc_view *A, double tol, 
  * doubles; on return the first info->rh_size of them are valid.  Afterwards call stmqr_b200_download
  * with out->stack = NULL for the remaining arrays. */
 int  stmqr_b200_rh_bound (stmqr_handle h, int64_t *doubles) ;
+/* The same overlap for the numeric phase in pieces (several GPUs: every handle streams the blocks of its
+ * own fronts): stream_begin before factorize_begin, stream_end after factorize_hpinv_b. */
+int  stmqr_b200_stream_begin (stmqr_handle h, double *stack, int64_t capacity) ;
+int  stmqr_b200_stream_end (stmqr_handle h) ;
 int  stmqr_b200_factorize_streamed (stmqr_handle h, const stmqr_csc_view *A, double tol, int64_t ntol,
                                     double *stack, int64_t capacity, stmqr_numeric_info *info) ;
 

@@ -179,6 +179,9 @@ struct stmqr_handle_s
     bool sdone = false ;
     int serr = STMQR_OK ;
     bool stack_streamed = false ;
+    std::thread *sworker = nullptr ;
+    I64 stream_cap = 0 ;
+    double *stream_dst = nullptr ;
     I32 *pin_lvl = nullptr ;                // pinned: actual max # rows of the level being processed
     bool check_hit = false ;                // STMQR_B200_CHECK: a non-finite value was already reported
     unsigned grid_seq = 0 ;                 // launch sequence number of k_panel_grid (tags of its exchange lines)
@@ -1476,34 +1479,55 @@ int stmqr_b200_rh_bound (stmqr_handle h, int64_t *doubles)
     return STMQR_OK ;
 }
 
+int stmqr_b200_stream_begin (stmqr_handle h, double *stack, int64_t capacity)
+{
+    if (!h || !h->analyzed || !stack || capacity < 1) return fail (h, STMQR_ERR_INVALID, "stream_begin: no destination") ;
+    if (h->streaming) return fail (h, STMQR_ERR_INVALID, "stream_begin: already streaming") ;
+    cudaSetDevice (h->device) ;
+    int s ;
+    if ((s = ensure_copy_pipeline (h)) != STMQR_OK) return s ;
+    if (!h->pin_cursor) CK (cudaHostAlloc ((void **) &h->pin_cursor, STREAM_MAX_LEVELS * sizeof (unsigned long long), cudaHostAllocDefault)) ;
+    h->squeue.clear () ; h->sdone = false ; h->serr = STMQR_OK ; h->stream_levels = 0 ;
+    h->stream_cap = capacity ; h->stream_dst = stack ;
+    h->streaming = true ;
+    h->sworker = new std::thread (stream_worker, h, stack, (I64) capacity) ;
+    return STMQR_OK ;
+}
+
+int stmqr_b200_stream_end (stmqr_handle h)
+{
+    if (!h || !h->streaming) return fail (h, STMQR_ERR_INVALID, "stream_end: not streaming") ;
+    cudaSetDevice (h->device) ;
+    { std::lock_guard<std::mutex> lk (h->smu) ; h->sdone = true ; }
+    h->scv.notify_all () ;
+    h->sworker->join () ;
+    delete h->sworker ; h->sworker = nullptr ;
+    h->streaming = false ;
+    if (h->serr != STMQR_OK) return fail (h, h->serr, "stream_end: download of the R+H stack failed") ;
+    if (!h->factorized) return STMQR_OK ;              // the factorization itself failed: its status counts
+    if (h->info.rh_size > h->stream_cap) return fail (h, STMQR_ERR_INVALID, "stream_end: stack capacity too small") ;
+    if (h->stream_levels >= STREAM_MAX_LEVELS)
+    {
+        // (more etree levels than events: the tail was not streamed) copy everything again
+        const int s = d2h_pipelined (h, h->stream_dst, h->N.R, h->info.rh_size * sizeof (double)) ;
+        if (s != STMQR_OK) return s ;
+    }
+    return STMQR_OK ;
+}
+
 int stmqr_b200_factorize_streamed (stmqr_handle h, const stmqr_csc_view *A, double tol, int64_t ntol,
     double *stack, int64_t capacity, stmqr_numeric_info *info)
 {
     if (!h || !stack || capacity < 1) return fail (h, STMQR_ERR_INVALID, "factorize_streamed: no destination") ;
     int s = stmqr_b200_upload_matrix (h, A) ;
     if (s != STMQR_OK) return s ;
-    if ((s = ensure_copy_pipeline (h)) != STMQR_OK) return s ;
-    if (!h->pin_cursor) CK (cudaHostAlloc ((void **) &h->pin_cursor, STREAM_MAX_LEVELS * sizeof (unsigned long long), cudaHostAllocDefault)) ;
-    h->squeue.clear () ; h->sdone = false ; h->serr = STMQR_OK ; h->stream_levels = 0 ;
-    h->streaming = true ;
-    std::thread worker (stream_worker, h, stack, (I64) capacity) ;
+    if ((s = stmqr_b200_stream_begin (h, stack, capacity)) != STMQR_OK) return s ;
     if ((s = stmqr_b200_factorize_begin (h, tol, ntol)) == STMQR_OK &&
         (s = stmqr_b200_factorize_levels (h, 0)) == STMQR_OK &&
         (s = stmqr_b200_factorize_hpinv_a (h)) == STMQR_OK)
         s = stmqr_b200_factorize_hpinv_b (h, info) ;
-    { std::lock_guard<std::mutex> lk (h->smu) ; h->sdone = true ; }
-    h->scv.notify_all () ;
-    worker.join () ;
-    h->streaming = false ;
-    if (s != STMQR_OK) return s ;
-    if (h->serr != STMQR_OK) return fail (h, h->serr, "factorize_streamed: download of the R+H stack failed") ;
-    if (h->info.rh_size > capacity) return fail (h, STMQR_ERR_INVALID, "factorize_streamed: stack capacity too small") ;
-    if (h->stream_levels >= STREAM_MAX_LEVELS)
-    {
-        // (more etree levels than events: the tail was not streamed) copy everything again
-        if ((s = d2h_pipelined (h, stack, h->N.R, h->info.rh_size * sizeof (double))) != STMQR_OK) return s ;
-    }
-    return STMQR_OK ;
+    const int s2 = stmqr_b200_stream_end (h) ;
+    return (s != STMQR_OK) ? s : s2 ;
 }
 
 // -------------------------------------------------------------------------------------------------

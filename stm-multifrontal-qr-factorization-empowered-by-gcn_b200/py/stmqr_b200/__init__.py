@@ -94,7 +94,7 @@ EXPORTS = (
     "stmqr_b200_factorize_begin", "stmqr_b200_factorize_levels", "stmqr_b200_factorize_hpinv_a",
     "stmqr_b200_factorize_hpinv_b", "stmqr_b200_sync", "stmqr_b200_partition_fronts",
     "stmqr_b200_set_partition", "stmqr_b200_device_array", "stmqr_b200_front_regions",
-    "stmqr_b200_rh_bound", "stmqr_b200_factorize_streamed",
+    "stmqr_b200_rh_bound", "stmqr_b200_factorize_streamed", "stmqr_b200_stream_begin", "stmqr_b200_stream_end",
 )
 
 _lib = None
@@ -139,6 +139,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
                                             C.POINTER(C.c_int32)]
     lib.stmqr_b200_front_regions.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                              C.POINTER(FrontRegions)]
+    lib.stmqr_b200_stream_begin.argtypes = [C.c_void_p, _f64p, C.c_int64]
+    lib.stmqr_b200_stream_end.argtypes = [C.c_void_p]
     lib.stmqr_b200_rh_bound.argtypes = [C.c_void_p, _i64p]
     lib.stmqr_b200_factorize_streamed.argtypes = [C.c_void_p, C.POINTER(CscView), C.c_double, C.c_int64, _f64p,
                                                   C.c_int64, C.POINTER(NumericInfo)]
@@ -307,6 +309,20 @@ class Engine:
             self.h, C.byref(A.view), tol, ntol, stack.ctypes.data_as(_f64p), stack.size, C.byref(info)),
             "factorize_streamed")
         return info, stack[: max(int(info.rh_size), 1)]
+
+    def stream_begin(self):
+        """start copying the R+H blocks of finished levels into a host stack (allocated by the bound) while
+        the phased numeric calls run -> the stack; call stream_end() after factorize_hpinv_b"""
+        cap = C.c_int64()
+        self._check(self.lib.stmqr_b200_rh_bound(self.h, C.byref(cap)), "rh_bound")
+        if getattr(self, "_stream_stack", None) is None or self._stream_stack.size < max(int(cap.value), 1):
+            self._stream_stack = np.empty(max(int(cap.value), 1), np.float64)
+        self._check(self.lib.stmqr_b200_stream_begin(self.h, self._stream_stack.ctypes.data_as(_f64p),
+                                                     self._stream_stack.size), "stream_begin")
+        return self._stream_stack
+
+    def stream_end(self):
+        self._check(self.lib.stmqr_b200_stream_end(self.h), "stream_end")
 
     def download(self, info: NumericInfo, stack=None) -> Numeric:
         s = self.sym
