@@ -66,3 +66,13 @@ def test_product_does_not_reference_oracle():
             if f.endswith((".cu", ".cuh", ".c", ".h", ".py", ".sh")):
                 txt = open(os.path.join(root, f), errors="ignore").read()
                 assert "stmqr_oracle" not in txt and "libref_harness" not in txt, os.path.join(root, f)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/stmqr_b200.h is the FFI surface: it must compile as C99 on its own (no C++, no
+    reference headers, no torch types)."""
+    src = tmp_path / "t.c"
+    src.write_text('#include "stmqr_b200.h"\nint main (void) { stmqr_numeric_info i ; (void) i ; return STMQR_OK ; }\n')
+    out = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only",
+                          "-I", os.path.join(R.ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
