@@ -1199,7 +1199,19 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
                 else
                 {
                     // row groups: about 3 CTAs per SM in total, every CTA walks down its share of the row tiles
-                    const I32 nrg = (I32) std::max<I64> (1, std::min<I64> (nrt, (3 * (I64) h->nsm + (I64) nct * nfronts - 1) / ((I64) nct * nfronts))) ;
+                    // (the count that fills whole waves of one CTA per SM best, every CTA at least 4 row tiles)
+                    I32 nrg = 1 ;
+                    {
+                        const I64 base = (I64) nct * nfronts ;
+                        double best = -1 ;
+                        const I32 hi = std::max<I32> (1, std::min<I32> (nrt / 4, (I32) ((8 * (I64) h->nsm + base - 1) / base))) ;
+                        for (I32 c = 1 ; c <= hi ; c++)
+                        {
+                            const I64 tot = base * c, waves = (tot + h->nsm - 1) / h->nsm ;
+                            const double eff = (double) tot / (double) (waves * h->nsm) ;
+                            if (eff >= best - 1e-9) { best = eff ; nrg = c ; }
+                        }
+                    }
                     LAUNCH (16, k_wide_apply_rows<<<dim3 (nct * nrg, nfronts), 256, wide_apply_rows_smem_bytes (), su>>> (WA, S, N, cb, ce, nct, nrg)) ;
                 }
             } ;
