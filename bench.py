@@ -303,14 +303,14 @@ def run_b200_arm(args):
         # DRAM traffic of the dominant kernel from one `ncu --set full` capture (profiles/): a top-level
         # k_panel_cluster launch of lap2d_1024 reads 1.49 MB and writes nothing (slabs in shared memory,
         # front in L2); null for other workloads (not captured)
-        traffic = ({"dram_bytes_per_launch": 1489152, "kernel": "k_panel_cluster<256,2>",
-                    "source": "profiles/r01_u_ncu_full_k_panel_cluster_lap2d_1024_raw.csv"}
-                   if args.workload == "lap2d_1024" else None)
+        traffic = 1489152 if args.workload == "lap2d_1024" else None        # bytes per launch
+        traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum of one top-level k_panel_cluster<256,2> launch, "
+                       "profiles/r01_u_ncu_full_k_panel_cluster_lap2d_1024_raw.csv") if traffic else None
         roof = {"bound": "tensor", "kernel": "front QR (k_panel + k_update)", "achieved": ach, "peak": dmma_tf,
                 "unit": "TFLOP/s", "frac": ach / dmma_tf if dmma_tf else None, "traffic": traffic,
                 "peak_source": "FP64 mma.sync (DMMA) register-loop microbenchmark run in this process "
                                "(stmqr_b200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
-                "avg_launch_ms": front_ms / max(1.0, float(cls_n[3] + cls_n[4]))}
+                "avg_launch_ms": front_ms / max(1.0, float(cls_n[3] + cls_n[4])), "traffic_source": traffic_src}
     else:
         ach = float(s2.bytes_assemble) / (asm_ms * 1e-3) * 1e-9
         roof = {"bound": "hbm", "kernel": "assembly+pack (k_front_setup, k_assemble, k_front_finish, k_pack)",

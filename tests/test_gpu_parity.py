@@ -238,3 +238,46 @@ def test_errors_and_edge_cases(engine):
     n2 = engine.download(info2)
     assert np.array_equal(n1.HStair, n2.HStair) and np.array_equal(n1.Hii, n2.Hii)
     assert R.compare_R(sym, n2, sq.Numeric(**{**n1.__dict__, "stack": 2.0 * n1.stack}), R.a_norm(A2)) <= 1e-13
+
+
+def test_config2_full_size_properties():
+    """BASELINE config[1] at FULL size (2-D Laplacian 1024 x 1024, METIS) through the drop-in, checked by
+    size-independent properties: full rank, solve residual through the reference's own QR_solve /
+    QR_qmult (qrtest.c check_error), run-to-run determinism (bitwise), and exact linearity under a
+    power-of-two scaling of A (every operation of the factorization commutes with it)."""
+    if not R.have_reference():
+        pytest.skip("needs oracle/_ref for the symbolic analysis and the consumers")
+    g = 1024
+    m, n, p, i, x = M.laplacian_2d(g)
+    ref = R.Reference()
+    ref.set_backend("b200")
+    os.environ["STMQR_B200_CACHE_PLAN"] = "1"
+    try:
+        A = ref.csc_from_arrays(m, n, p, i, x)
+        tol = ref.default_tol(A)
+        QR = ref.sparseqr(A, 2, tol, grain=1.0)
+        info = ref.qr_info(QR)
+        assert int(info["rank"]) == n and int(info["n1cols"]) == 0
+        res = ref.check_error(A, QR)
+        assert res <= 1e-8, res
+        sym = ref.symbolic(QR)
+        a = ref.numeric(QR, sym)
+        assert np.isfinite(a.stack[: a.rh_size]).all() and np.isfinite(a.HTau).all()
+        stack1, tau1, hii1 = a.stack[: a.rh_size].copy(), a.HTau.copy(), a.Hii.copy()
+        ref.refactorize(A, QR)                                   # same symbolic object, new numeric
+        b = ref.numeric(QR, sym)
+        assert b.rh_size == a.rh_size and np.array_equal(b.stack[: b.rh_size], stack1)       # deterministic
+        assert np.array_equal(b.HTau, tau1) and np.array_equal(b.Hii, hii1)
+        A2 = ref.csc_from_arrays(m, n, p, i, 4.0 * x)
+        ref.refactorize(A2, QR)                                  # (tol is stored in the QR object: unchanged,
+        c = ref.numeric(QR, sym)                                 #  no pivot of this matrix is anywhere near it)
+        assert np.array_equal(c.HStair, a.HStair) and np.array_equal(c.Hii, hii1)
+        # R scales by 4 exactly, Householder vectors and tau do not change: compare R rows front by front
+        assert np.array_equal(c.HTau, tau1)
+        d = R.compare_R(sym, c, sq.Numeric(**{**b.__dict__, "stack": 4.0 * stack1}), 1.0)
+        assert d == 0.0, d
+        ref.free_qr(QR); ref.free_sparse(A); ref.free_sparse(A2)
+    finally:
+        os.environ.pop("STMQR_B200_CACHE_PLAN", None)
+        ref.set_backend("reference")
+        ref.close()
