@@ -1,3 +1,6 @@
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 tests/micro/dmma_bench.cu -o tests/micro/dmma_bench
+// measured on B200 (this round): register loop 36.98 TFLOP/s at 32 warps/SM x 16 accumulators, 30.4 at 8 warps x 1;
+// 4x4 tile from shared memory, 8 warps, 1 CTA/SM: 36.5 TFLOP/s (ld 36) vs 34.8 (ld 33, bank conflicts)
 // micro-benchmark (not a test): FP64 DMMA (mma.sync.m8n8k4.f64) issue behaviour on B200.
 // How many warps per SM and independent accumulators per warp are needed to reach the pipe's peak,
 // and what does a 4x4 register tile fed from shared memory (the inner loop of kernels_wide.cuh) reach?
