@@ -137,7 +137,11 @@ typedef struct
     int32_t small_elems ;            /* fronts with at most this many doubles take the fused
                                         shared-memory path (0 = engine default)               */
     int32_t profile_phases ;         /* 1: time assemble/front phases separately (adds syncs)  */
-    int32_t reserved ;
+    int32_t reserved ;               /* A/B switches for tests and tuning (0 = production path): bit 0 no
+                                        look-ahead, bit 1 no two-level (128-column) blocking, bit 2 no
+                                        k_panel_grid, bit 3 no small-front kernel (read by analyze),
+                                        bit 4 non-persistent K = 128 apply; bits 8-15 ring stages of
+                                        k_update_dmma (2/4), bits 16-23 max warps per panel CTA      */
 } stmqr_options ;
 
 int  stmqr_b200_device_count (void) ;

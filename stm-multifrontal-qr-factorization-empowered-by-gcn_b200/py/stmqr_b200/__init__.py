@@ -277,7 +277,9 @@ class Engine:
             raise EngineError(f"{what}: {ERRORS.get(st, st)}: {msg.decode() if msg else ''}")
 
     def set_options(self, panel=0, small_elems=0, profile_phases=0, flags=0):
-        """flags (tuning / A-B tests): bit 0 no look-ahead, bit 1 no two-level (128-column) blocking"""
+        """flags (tuning / A-B tests, stmqr_options.reserved): bit 0 no look-ahead, bit 1 no two-level
+        (128-column) blocking, bit 2 no k_panel_grid, bit 3 no small-front kernel (set before analyze),
+        bit 4 non-persistent K = 128 apply"""
         o = Options(panel, small_elems, profile_phases, flags)
         self._check(self.lib.stmqr_b200_set_options(self.h, C.byref(o)), "set_options")
 
