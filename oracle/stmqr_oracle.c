@@ -497,3 +497,99 @@ void stmqr_oracle_free (stmqr_oracle_result *r)
     }
     free (r) ;
 }
+
+/* ------------------------------------------------------------------------- */
+/* Consumer of the numeric object (the row next to the  */
+/* path): Y = Q'X and Y = QX from the packed R+H blocks, for factorizations   */
+/* without singletons.                                                        */
+/*   qr_private_get_H_vectors   SparseQR.c:1455-1546  where the Householder   */
+/*                              vectors of a front live inside its R+H block   */
+/*   qr_private_Happly          :1706-1832  front order (forward for Q', back- */
+/*                              ward for Q), rows Hii[Hip[f]+h ..] of vector h */
+/*   QR_qmult                   :1838-2110  row permutation HPinv around it    */
+/* The reference applies the vectors in panels of 32 through dlarft/dlarfb;    */
+/* here one reflector at a time (same product, different rounding).            */
+/* ------------------------------------------------------------------------- */
+static Int oracle_get_H_vectors (Int f, const stmqr_symbolic_view *sym, const int64_t *HStair,
+    const double *HTau, const int64_t *Hm, double *H_Tau, Int *H_start, Int *H_end)
+{
+    Int col1 = sym->Super [f], fp = sym->Super [f+1] - col1 ;
+    Int pr = sym->Rp [f], fn = sym->Rp [f+1] - pr ;
+    const int64_t *Stair = HStair + pr ;
+    const double *Tau = HTau + pr ;
+    Int fm = Hm [f], h = 0, nh = 0, p = 0, rm = 0 ;
+    for (Int k = 0 ; k < fn && nh < fm ; k++)
+    {
+        Int t ;
+        if (k < fp)
+        {
+            t = Stair [k] ;
+            if (t == 0) { p += rm ; continue ; }        /* dead column: R part only (:1509-1513) */
+            else if (rm < fm) rm++ ;
+            h = rm ;
+        }
+        else
+        {
+            t = Stair [k] ;
+            h = IMIN (h+1, fm) ;
+        }
+        p += rm ;
+        H_Tau [nh] = Tau [k] ;
+        H_start [nh] = p ;
+        p += (t-h) ;
+        H_end [nh] = p ;
+        nh++ ;
+        if (h == fm) break ;
+    }
+    return nh ;
+}
+
+/* method 0: Y = Q'X, method 1: Y = QX (QR_QTX / QR_QX, SparseQR_definitions.h); X, Y are m-by-nx,
+ * column major, ld = m.  Returns 0, or -1 on a bad method / allocation failure. */
+int stmqr_oracle_qmult (int method, const stmqr_symbolic_view *sym, const stmqr_numeric_view *num,
+    int64_t nx, const double *X, double *Y)
+{
+    if (method != 0 && method != 1) return -1 ;
+    Int m = sym->m, nf = sym->nf, maxfn = sym->maxfn ;
+    double *H_Tau = (double *) malloc ((size_t) IMAX (maxfn, 1) * sizeof (double)) ;
+    Int *H_start = (Int *) malloc ((size_t) IMAX (maxfn, 1) * sizeof (Int)) ;
+    Int *H_end = (Int *) malloc ((size_t) IMAX (maxfn, 1) * sizeof (Int)) ;
+    double *Z = (double *) malloc ((size_t) IMAX (m * nx, 1) * sizeof (double)) ;
+    if (!H_Tau || !H_start || !H_end || !Z) { free (H_Tau) ; free (H_start) ; free (H_end) ; free (Z) ; return -1 ; }
+    /* Q'X works on Y(HPinv[i],:) = X(i,:) (:2004-2014); QX on a copy of X, permuted at the end (:2036-2048) */
+    for (Int k = 0 ; k < nx ; k++)
+        for (Int i = 0 ; i < m ; i++)
+        {
+            if (method == 0) Z [num->HPinv [i] + k*m] = X [i + k*m] ;
+            else Z [i + k*m] = X [i + k*m] ;
+        }
+    for (Int ff = 0 ; ff < nf ; ff++)
+    {
+        Int f = (method == 0) ? ff : (nf - 1 - ff) ;
+        Int nh = oracle_get_H_vectors (f, sym, num->HStair, num->HTau, num->Hm, H_Tau, H_start, H_end) ;
+        const double *R = num->stack + num->Roff [f] ;
+        const int64_t *Hi = num->Hii + sym->Hip [f] ;
+        for (Int hh = 0 ; hh < nh ; hh++)
+        {
+            Int h = (method == 0) ? hh : (nh - 1 - hh) ;
+            double tau = H_Tau [h] ;
+            if (tau == 0) continue ;
+            Int len = H_end [h] - H_start [h] ;            /* entries below the unit diagonal */
+            const double *v = R + H_start [h] ;
+            for (Int k = 0 ; k < nx ; k++)
+            {
+                double *z = Z + k*m ;
+                double s = z [Hi [h]] ;
+                for (Int i = 0 ; i < len ; i++) s += v [i] * z [Hi [h+1+i]] ;
+                s *= tau ;
+                z [Hi [h]] -= s ;
+                for (Int i = 0 ; i < len ; i++) z [Hi [h+1+i]] -= s * v [i] ;
+            }
+        }
+    }
+    for (Int k = 0 ; k < nx ; k++)
+        for (Int i = 0 ; i < m ; i++)
+            Y [i + k*m] = (method == 0) ? Z [i + k*m] : Z [num->HPinv [i] + k*m] ;
+    free (H_Tau) ; free (H_start) ; free (H_end) ; free (Z) ;
+    return 0 ;
+}

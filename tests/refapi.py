@@ -65,6 +65,26 @@ class Oracle:
         self.lib.stmqr_oracle_free.argtypes = [C.POINTER(_OracleResult)]
         self.lib.stmqr_oracle_free.restype = None
 
+    def qmult(self, sym: sq.Symbolic, num: sq.Numeric, method: int, X: np.ndarray) -> np.ndarray:
+        """Y = Q'X (method 0) or QX (method 1) from a numeric object in the reference's layout"""
+        X = np.asfortranarray(X, dtype=np.float64)
+        if X.ndim == 1:
+            X = X.reshape(-1, 1, order="F")
+        Y = np.zeros_like(X, order="F")
+        v = sq.NumericView()
+        keep = [np.ascontiguousarray(a) for a in (num.stack, num.Roff, num.HStair, num.HTau, num.Hii, num.Hm,
+                                                   num.Hr, num.HPinv)]
+        v.stack = keep[0].ctypes.data_as(_f64p); v.Roff = keep[1].ctypes.data_as(_i64p)
+        v.HStair = keep[2].ctypes.data_as(_i64p); v.HTau = keep[3].ctypes.data_as(_f64p)
+        v.Hii = keep[4].ctypes.data_as(_i64p); v.Hm = keep[5].ctypes.data_as(_i64p)
+        v.Hr = keep[6].ctypes.data_as(_i64p); v.HPinv = keep[7].ctypes.data_as(_i64p)
+        self.lib.stmqr_oracle_qmult.argtypes = [C.c_int, C.POINTER(sq.SymbolicView), C.POINTER(sq.NumericView),
+                                                C.c_int64, _f64p, _f64p]
+        st = self.lib.stmqr_oracle_qmult(method, C.byref(sym.view), C.byref(v), X.shape[1],
+                                         X.ctypes.data_as(_f64p), Y.ctypes.data_as(_f64p))
+        assert st == 0
+        return Y
+
     def factorize(self, sym: sq.Symbolic, A: sq.Csc, tol: float, ntol: int, capture: bool = False,
                   fchunk=32, small=5000, minchunk=4, minchunk_ratio=4):
         rp = self.lib.stmqr_oracle_factorize(C.byref(sym.view), C.byref(A.view), tol, ntol,

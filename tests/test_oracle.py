@@ -92,3 +92,30 @@ def test_oracle_matches_reference_live(oracle, name, order):
     ref.free_qr(QR)
     ref.free_sparse(A)
     ref.close()
+
+
+@pytest.mark.skipif(not R.have_reference(), reason="oracle/_ref not built (reference tree absent)")
+@pytest.mark.parametrize("name,order", [("dwt_992", 2), ("t2d_q9", 2), ("epb1", 1)])
+def test_oracle_qmult_matches_reference(oracle, name, order):
+    """The restatement of the consumer next to the path (QR_qmult: Y = Q'X, Y = QX),
+    pinned against the reference's own QR_qmult on the reference's own numeric object (matrices without
+    column singletons; dwt_992 has 496 dead columns)."""
+    path = os.path.join(R.DATA_DIR, name + ".mtx")
+    ref = R.Reference()
+    ref.set_backend("reference")
+    A = ref.read_mtx(path)
+    QR = ref.sparseqr(A, order, ref.default_tol(A), grain=1.0, tap=True)
+    if ref.qr_info(QR)["n1cols"] != 0:
+        pytest.skip("column singletons")
+    sym = ref.symbolic(QR)
+    num = ref.numeric(QR, sym)
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((sym.m, 3))
+    for method in (R.QR_QTX, R.QR_QX):
+        want = ref.qmult(QR, method, X)
+        got = oracle.qmult(sym, num, method, X)
+        assert np.max(np.abs(got - want)) <= 1e-12 * max(1.0, np.max(np.abs(want))), (name, method)
+    # Q'(QX) = X through the restatement alone
+    back = oracle.qmult(sym, num, R.QR_QTX, oracle.qmult(sym, num, R.QR_QX, X))
+    assert np.max(np.abs(back - X)) <= 1e-12
+    ref.free_qr(QR); ref.free_sparse(A); ref.close()
