@@ -593,3 +593,84 @@ int stmqr_oracle_qmult (int method, const stmqr_symbolic_view *sym, const stmqr_
     free (H_Tau) ; free (H_start) ; free (H_end) ; free (Z) ;
     return 0 ;
 }
+
+/* ------------------------------------------------------------------------- */
+/* X = R\B (use_Qfill = 0) or X = E*(R\B) (use_Qfill = 1) from the packed R+H  */
+/* blocks: qr_rsolve, SparseQR.c:2218-2465 (multifrontal rows only; no          */
+/* singletons, keepH = 1).  B is m-by-nrhs (ld = m; only its first `rank` rows  */
+/* are used), X is n-by-nrhs.  Dead columns get the basic solution x_j = 0.     */
+/* ------------------------------------------------------------------------- */
+int stmqr_oracle_rsolve (const stmqr_symbolic_view *sym, const stmqr_numeric_view *num, int64_t rank,
+    int64_t maxfrank, int use_Qfill, int64_t nrhs, const double *B, double *X)
+{
+    Int m = sym->m, n = sym->n, nf = sym->nf ;
+    const int64_t *Qfill = use_Qfill ? sym->Qfill : NULL ;
+    Int mf = IMAX (maxfrank, 1) ;
+    const double **Rcolp = (const double **) malloc ((size_t) mf * sizeof (double *)) ;
+    Int *Rlive = (Int *) malloc ((size_t) mf * sizeof (Int)) ;
+    double *W = (double *) malloc ((size_t) (mf * IMAX (nrhs, 1)) * sizeof (double)) ;
+    if (!Rcolp || !Rlive || !W) { free (Rcolp) ; free (Rlive) ; free (W) ; return -1 ; }
+    for (Int e = 0 ; e < n * nrhs ; e++) X [e] = 0 ;
+    Int row2 = rank ;                                   /* last row of R + 1 (:2307) */
+    for (Int f = nf-1 ; f >= 0 ; f--)
+    {
+        const double *R = num->stack + num->Roff [f] ;
+        Int col1 = sym->Super [f], fp = sym->Super [f+1] - col1 ;
+        Int pr = sym->Rp [f], fn = sym->Rp [f+1] - pr ;
+        const int64_t *Stair = num->HStair + pr ;
+        Int fm = num->Hm [f], h = 0, t = 0, rm = 0, k ;
+        for (k = 0 ; k < fp ; k++)                      /* live pivot columns (:2331-2381) */
+        {
+            Int j = col1 + k, live ;
+            t = Stair [k] ;
+            if (t == 0) { live = 0 ; t = rm ; h = rm ; }
+            else { live = (rm < fm) ; h = rm + 1 ; }
+            if (live) { Rcolp [rm] = R ; Rlive [rm] = j ; rm++ ; }
+            else
+            {
+                Int ii = Qfill ? Qfill [j] : j ;
+                if (ii < n) for (Int kk = 0 ; kk < nrhs ; kk++) X [ii + kk*n] = 0 ;
+            }
+            R += rm + (t-h) ;
+        }
+        Int row1 = row2 - rm ;
+        for (Int kk = 0 ; kk < nrhs ; kk++)             /* right-hand side of these rm equations */
+            for (Int i = 0 ; i < rm ; i++)
+            {
+                Int ii = row1 + i ;
+                W [i + kk*rm] = (ii < rank) ? B [ii + kk*m] : 0 ;
+            }
+        for ( ; k < fn ; k++)                           /* rectangular part: W -= R2 x2 (:2409-2444) */
+        {
+            Int j = sym->Rj [pr + k] ;
+            Int ii = Qfill ? Qfill [j] : j ;
+            if (ii >= n) break ;
+            if (!num->Rdead [j])
+                for (Int kk = 0 ; kk < nrhs ; kk++)
+                {
+                    double xi = X [ii + kk*n] ;
+                    if (xi != 0) for (Int i = 0 ; i < rm ; i++) W [i + kk*rm] -= R [i] * xi ;
+                }
+            R += rm ;
+            t = Stair [k] ;
+            h = IMIN (h+1, fm) ;
+            R += (t-h) ;
+        }
+        for (k = rm-1 ; k >= 0 ; k--)                   /* packed upper triangular part (:2450-2478) */
+        {
+            const double *Rk = Rcolp [k] ;
+            Int j = Rlive [k] ;
+            Int ii = Qfill ? Qfill [j] : j ;
+            if (ii < n)
+                for (Int kk = 0 ; kk < nrhs ; kk++)
+                {
+                    double xi = W [k + kk*rm] / Rk [k] ;
+                    X [ii + kk*n] = xi ;
+                    if (xi != 0) for (Int i = 0 ; i < k ; i++) W [i + kk*rm] -= Rk [i] * xi ;
+                }
+        }
+        row2 = row1 ;
+    }
+    free (Rcolp) ; free (Rlive) ; free (W) ;
+    return 0 ;
+}

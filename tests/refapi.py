@@ -65,6 +65,36 @@ class Oracle:
         self.lib.stmqr_oracle_free.argtypes = [C.POINTER(_OracleResult)]
         self.lib.stmqr_oracle_free.restype = None
 
+    @staticmethod
+    def _numview(num: sq.Numeric):
+        v = sq.NumericView()
+        keep = [np.ascontiguousarray(a) for a in (num.stack, num.Roff, num.HStair, num.HTau, num.Hii, num.Hm,
+                                                   num.Hr, num.HPinv, num.Rdead.astype(np.int8))]
+        v.stack = keep[0].ctypes.data_as(_f64p); v.Roff = keep[1].ctypes.data_as(_i64p)
+        v.HStair = keep[2].ctypes.data_as(_i64p); v.HTau = keep[3].ctypes.data_as(_f64p)
+        v.Hii = keep[4].ctypes.data_as(_i64p); v.Hm = keep[5].ctypes.data_as(_i64p)
+        v.Hr = keep[6].ctypes.data_as(_i64p); v.HPinv = keep[7].ctypes.data_as(_i64p)
+        v.Rdead = keep[8].ctypes.data
+        return v, keep
+
+    def rsolve(self, sym: sq.Symbolic, num: sq.Numeric, B: np.ndarray, permuted: bool = True) -> np.ndarray:
+        """X = E*(R\\B) (permuted) or R\\B from a numeric object in the reference's layout (qr_rsolve)"""
+        B = np.asfortranarray(B, dtype=np.float64)
+        if B.ndim == 1:
+            B = B.reshape(-1, 1, order="F")
+        X = np.zeros((sym.n, B.shape[1]), order="F")
+        v, keep = self._numview(num)
+        self.lib.stmqr_oracle_rsolve.argtypes = [C.POINTER(sq.SymbolicView), C.POINTER(sq.NumericView), C.c_int64,
+                                                 C.c_int64, C.c_int, C.c_int64, _f64p, _f64p]
+        st = self.lib.stmqr_oracle_rsolve(C.byref(sym.view), C.byref(v), int(num.rank), int(num.maxfrank),
+                                          int(permuted), B.shape[1], B.ctypes.data_as(_f64p), X.ctypes.data_as(_f64p))
+        assert st == 0
+        return X
+
+    def least_squares(self, sym: sq.Symbolic, num: sq.Numeric, b: np.ndarray) -> np.ndarray:
+        """x = E * (R \\ (Q'b)): the reference's solve path (qrtest.c:11-53) from the restatements alone"""
+        return self.rsolve(sym, num, self.qmult(sym, num, QR_QTX, b), permuted=True)
+
     def qmult(self, sym: sq.Symbolic, num: sq.Numeric, method: int, X: np.ndarray) -> np.ndarray:
         """Y = Q'X (method 0) or QX (method 1) from a numeric object in the reference's layout"""
         X = np.asfortranarray(X, dtype=np.float64)

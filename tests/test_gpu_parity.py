@@ -281,3 +281,24 @@ def test_config2_full_size_properties():
         os.environ.pop("STMQR_B200_CACHE_PLAN", None)
         ref.set_backend("reference")
         ref.close()
+
+
+@pytest.mark.parametrize("case", ["lap2d_24_metis", "lap3d_8_metis", "tall_600x150_colamd", "lap2d_16_notol"])
+def test_engine_factorization_solves(engine, oracle, case):
+    """Functional check of what is NOT comparable entrywise (Householder vectors, tau): the GPU engine's
+    packed R+H, pushed through the restated consumers x = E*(R\\(Q'b)) (oracle.qmult / oracle.rsolve, both
+    pinned against the reference's QR_qmult / QR_solve on CPU), solves min ||Ax - b||: normal-equation
+    residual at rounding level, and Q'(Qx) = x."""
+    sym, A, tol, ntol, want = R.load_golden(case)
+    got = run_engine(engine, sym, A, tol, ntol)
+    assert got.rank == sym.n                                   # these cases are full rank
+    S = A.to_scipy()
+    rng = np.random.default_rng(8)
+    b = rng.standard_normal(sym.m)
+    x = oracle.least_squares(sym, got, b)[:, 0]
+    r = S @ x - b
+    nrm = np.linalg.norm(S.toarray(), 2)
+    assert np.linalg.norm(S.T @ r) <= 1e-10 * nrm * max(np.linalg.norm(b), 1.0), case
+    X = rng.standard_normal((sym.m, 2))
+    back = oracle.qmult(sym, got, R.QR_QTX, oracle.qmult(sym, got, R.QR_QX, X))
+    assert np.max(np.abs(back - X)) <= 1e-12

@@ -119,3 +119,31 @@ def test_oracle_qmult_matches_reference(oracle, name, order):
     back = oracle.qmult(sym, num, R.QR_QTX, oracle.qmult(sym, num, R.QR_QX, X))
     assert np.max(np.abs(back - X)) <= 1e-12
     ref.free_qr(QR); ref.free_sparse(A); ref.close()
+
+
+@pytest.mark.skipif(not R.have_reference(), reason="oracle/_ref not built (reference tree absent)")
+@pytest.mark.parametrize("name,order", [("dwt_992", 2), ("t2d_q9", 2), ("epb1", 1)])
+def test_oracle_rsolve_matches_reference(oracle, name, order):
+    """qr_rsolve restated (X = E*(R\\B), basic solution on dead columns), pinned against QR_solve of the
+    reference; and the whole solve path x = E*(R\\(Q'b)) from the restatements reproduces the reference's x."""
+    path = os.path.join(R.DATA_DIR, name + ".mtx")
+    ref = R.Reference()
+    ref.set_backend("reference")
+    A = ref.read_mtx(path)
+    QR = ref.sparseqr(A, order, ref.default_tol(A), grain=1.0, tap=True)
+    if ref.qr_info(QR)["n1cols"] != 0:
+        pytest.skip("column singletons")
+    sym = ref.symbolic(QR)
+    num = ref.numeric(QR, sym)
+    rng = np.random.default_rng(6)
+    B = rng.standard_normal((sym.m, 2))
+    for permuted, system in ((True, R.QR_RETX_EQUALS_B), (False, R.QR_RX_EQUALS_B)):
+        want = ref.solve(QR, system, B, sym.n)
+        got = oracle.rsolve(sym, num, B, permuted=permuted)
+        scale = max(1.0, np.max(np.abs(want)))
+        assert np.max(np.abs(got - want)) <= 1e-10 * scale, (name, system)
+    y = ref.qmult(QR, R.QR_QTX, B)
+    want = ref.solve(QR, R.QR_RETX_EQUALS_B, y, sym.n)
+    got = oracle.least_squares(sym, num, B)
+    assert np.max(np.abs(got - want)) <= 1e-9 * max(1.0, np.max(np.abs(want)))
+    ref.free_qr(QR); ref.free_sparse(A); ref.close()
