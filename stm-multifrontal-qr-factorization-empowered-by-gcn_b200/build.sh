@@ -13,7 +13,7 @@ echo "built $HERE/lib/libstmqr_b200.so"
 if [ -d "$REF/STMMQR/include" ] && [ -f "$HERE/host/qr_factorize_b200.c" ]; then
     S="$REF/STMMQR"
     gcc -std=gnu99 -fcommon -w -O2 -fPIC -shared \
-        -I"$S/include" -I"$S/include/tpsm" -I"$HERE/../oracle/shim" -I"$HERE/../include" \
+        -I"$S/include" -I"$S/include/tpsm" -idirafter "$HERE/host/compat" -I"$HERE/../include" \
         "$HERE/host/qr_factorize_b200.c" -o "$HERE/lib/libstmqr_dropin.so" \
         -L"$HERE/lib" -lstmqr_b200 -Wl,-rpath,'$ORIGIN'
     echo "built $HERE/lib/libstmqr_dropin.so"

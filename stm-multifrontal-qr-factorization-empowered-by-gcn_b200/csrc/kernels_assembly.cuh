@@ -10,6 +10,8 @@ namespace stmqr {
 // S = A(P,Q) values in row form.  Reference: qr_stranspose2, SparseQR_factorize.c:755-785, a
 // serial scatter through a running row cursor.  Here one thread per entry of A finds its slot by
 // binary search of the permuted column inside the (ascending) row of S: no atomics, deterministic.
+// Duplicate entries of A (legal in a sparse_csc) land in consecutive slots in storage order, exactly
+// as the reference's cursor places them (the later one then wins in qr_assemble, :1199-1203).
 // ---------------------------------------------------------------------------------------------
 __global__ void k_build_S (I32 n, const I64 *__restrict__ Ap, const I64 *__restrict__ Ai,
     const double *__restrict__ Ax, DSym S, double *__restrict__ Sx, I32 *err)
@@ -31,7 +33,22 @@ __global__ void k_build_S (I32 n, const I64 *__restrict__ Ap, const I64 *__restr
                 I32 mid = (lo + hi) >> 1 ;
                 if (S.Sj [mid] < col) lo = mid + 1 ; else hi = mid ;
             }
-            if (lo < S.Sp [row+1] && S.Sj [lo] == col) Sx [lo] = Ax [p] ;
+            if (lo < S.Sp [row+1] && S.Sj [lo] == col)
+            {
+                // duplicate (i,j) entries of A occupy consecutive slots of S in the order they are
+                // stored in the column (qr_stranspose2's running cursor W[row]++, :779-781): the d-th
+                // duplicate of this entry goes to slot lo + d.  Rare: only looked at when the next slot
+                // holds the same column.
+                if (lo + 1 < S.Sp [row+1] && S.Sj [lo+1] == col)
+                {
+                    const I64 ai = Ai [p] ;
+                    I32 d = 0 ;
+                    for (I64 q = p1 ; q < p ; q++) d += (Ai [q] == ai) ;
+                    lo += d ;
+                    if (!(lo < S.Sp [row+1] && S.Sj [lo] == col)) { atomicExch (err, 1) ; continue ; }
+                }
+                Sx [lo] = Ax [p] ;
+            }
             else atomicExch (err, 1) ;
         }
     }

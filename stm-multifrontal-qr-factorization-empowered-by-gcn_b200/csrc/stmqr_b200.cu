@@ -7,6 +7,7 @@
 // device-side arenas sized from the symbolic bounds.  No host synchronisation between levels:
 // all data-dependent shapes (fm, Cm, rank, R+H sizes) stay on the device.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -177,7 +178,8 @@ struct stmqr_handle_s
     std::condition_variable scv ;
     std::deque<int> squeue ;
     bool sdone = false ;
-    int serr = STMQR_OK ;
+    std::atomic<int> serr {STMQR_OK} ;
+    bool stream_overflow = false ;          // a level had no pre-created event: the whole stack is copied at the end
     bool stack_streamed = false ;
     std::thread *sworker = nullptr ;
     I64 stream_cap = 0 ;
@@ -387,14 +389,15 @@ void stream_worker (stmqr_handle h, double *dst, I64 capacity)
             if (h->squeue.empty ()) break ;
             li = h->squeue.front () ; h->squeue.pop_front () ;
         }
-        if (h->serr != STMQR_OK) continue ;
-        if (cudaEventSynchronize (h->evLvl [li]) != cudaSuccess) { h->serr = STMQR_ERR_CUDA ; continue ; }
+        if (h->serr.load () != STMQR_OK) continue ;
+        // evLvl is sized in stream_begin, before this thread starts, and never grows while it runs
+        if (cudaEventSynchronize (h->evLvl [li]) != cudaSuccess) { h->serr.store (STMQR_ERR_CUDA) ; continue ; }
         const I64 end = (I64) h->pin_cursor [li] ;
-        if (end > capacity) { h->serr = STMQR_ERR_INVALID ; continue ; }
+        if (end > capacity) { h->serr.store (STMQR_ERR_INVALID) ; continue ; }
         if (end > begin)
         {
             const int s = d2h_pipelined (h, dst + begin, h->N.R + begin, (size_t) (end - begin) * sizeof (double)) ;
-            if (s != STMQR_OK) h->serr = s ;
+            if (s != STMQR_OK) h->serr.store (s) ;
         }
         begin = end ;
     }
@@ -700,6 +703,10 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     h->m = m ; h->n = n ; h->nf = nf ; h->anz = anz ; h->rjsize = rjsize ; h->hisize = hisize ;
     h->maxfn = sym->maxfn ;
     h->do_rank_detection = (int) sym->do_rank_detection ;
+    // the engine always packs R+H (qr_rhpack's keepH branch, :1726-1780): an R-only numeric object
+    // would be laid out differently, so refuse it instead of returning the wrong layout.  The
+    // reference always analyses with keepH = TRUE (SparseQR_analyze.c:205).
+    if (!sym->keepH) return fail (h, STMQR_ERR_INVALID, "analyze: keepH = 0 (R-only packing) is not supported") ;
 
     std::vector<I32> Super, Rp, Rj, Sleft, Sp, Sj, Child, Childp, Hip, PLinv, FmB, CmB ;
     bool ok = narrow (sym->Super, nf+1, Super) && narrow (sym->Rp, nf+1, Rp) &&
@@ -993,6 +1000,9 @@ int stmqr_b200_factorize_begin (stmqr_handle h, double tol, int64_t ntol)
     CK (cudaMemsetAsync (h->d_err, 0, sizeof (I32), st)) ;
     CK (cudaMemsetAsync (N.dbg, 0, 64 * sizeof (unsigned long long), st)) ;
     CK (cudaMemsetAsync (N.HTau, 0, std::max<I64> (h->rjsize, 1) * sizeof (double), st)) ;
+    // every slot of S is written by k_build_S when A matches the analysed pattern; a slot that no
+    // entry of A maps to must read as an explicit zero, not as stale memory
+    CK (cudaMemsetAsync (N.Sx, 0, std::max<I64> (h->anz, 1) * sizeof (double), st)) ;
     if (h->nparts > 1)
     {
         // arrays that are merged over the GPUs with an element-wise max: neutral element first
@@ -1335,16 +1345,12 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
         }
         LAUNCH (5, k_level_alloc<<<1, 1024, 0, st>>> (fr, Lv.count, N)) ;
         LAUNCH (6, k_pack<<<dim3 (Lv.count, nsl), 256, 0, st>>> (fr, S, N)) ;
-        if (h->streaming && h->stream_levels < STREAM_MAX_LEVELS)
+        if (h->streaming && h->stream_levels >= (int) h->evLvl.size ()) h->stream_overflow = true ;
+        if (h->streaming && !h->stream_overflow)
         {
             // the level's R+H blocks are final: hand their slice of the arena to the downloader
+            // (the events were all created in stream_begin: the downloader thread reads evLvl)
             const int li = h->stream_levels++ ;
-            while ((int) h->evLvl.size () <= li)
-            {
-                cudaEvent_t e ;
-                CK (cudaEventCreateWithFlags (&e, cudaEventDisableTiming)) ;
-                h->evLvl.push_back (e) ;
-            }
             CK (cudaMemcpyAsync (h->pin_cursor + li, N.rcursor, sizeof (unsigned long long), cudaMemcpyDeviceToHost, st)) ;
             CK (cudaEventRecord (h->evLvl [li], st)) ;
             { std::lock_guard<std::mutex> lk (h->smu) ; h->squeue.push_back (li) ; }
@@ -1499,7 +1505,19 @@ int stmqr_b200_stream_begin (stmqr_handle h, double *stack, int64_t capacity)
     int s ;
     if ((s = ensure_copy_pipeline (h)) != STMQR_OK) return s ;
     if (!h->pin_cursor) CK (cudaHostAlloc ((void **) &h->pin_cursor, STREAM_MAX_LEVELS * sizeof (unsigned long long), cudaHostAllocDefault)) ;
-    h->squeue.clear () ; h->sdone = false ; h->serr = STMQR_OK ; h->stream_levels = 0 ;
+    h->squeue.clear () ; h->sdone = false ; h->serr.store (STMQR_OK) ; h->stream_levels = 0 ;
+    h->stream_overflow = false ;
+    {
+        // one event per level that can be streamed, created BEFORE the downloader thread exists
+        const size_t need = std::min<size_t> ((size_t) STREAM_MAX_LEVELS,
+            h->ls_all.levels.size () + h->ls_sub.levels.size () + h->ls_top.levels.size () + 1) ;
+        while (h->evLvl.size () < need)
+        {
+            cudaEvent_t e ;
+            CK (cudaEventCreateWithFlags (&e, cudaEventDisableTiming)) ;
+            h->evLvl.push_back (e) ;
+        }
+    }
     h->stream_cap = capacity ; h->stream_dst = stack ;
     h->streaming = true ;
     h->sworker = new std::thread (stream_worker, h, stack, (I64) capacity) ;
@@ -1515,10 +1533,10 @@ int stmqr_b200_stream_end (stmqr_handle h)
     h->sworker->join () ;
     delete h->sworker ; h->sworker = nullptr ;
     h->streaming = false ;
-    if (h->serr != STMQR_OK) return fail (h, h->serr, "stream_end: download of the R+H stack failed") ;
+    if (h->serr.load () != STMQR_OK) return fail (h, h->serr.load (), "stream_end: download of the R+H stack failed") ;
     if (!h->factorized) return STMQR_OK ;              // the factorization itself failed: its status counts
     if (h->info.rh_size > h->stream_cap) return fail (h, STMQR_ERR_INVALID, "stream_end: stack capacity too small") ;
-    if (h->stream_levels >= STREAM_MAX_LEVELS)
+    if (h->stream_overflow)
     {
         // (more etree levels than events: the tail was not streamed) copy everything again
         const int s = d2h_pipelined (h, h->stream_dst, h->N.R, h->info.rh_size * sizeof (double)) ;

@@ -20,6 +20,7 @@
  * placement is legal for the consumers, which only use Rblock[f]).
  */
 #define _GNU_SOURCE
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <sys/mman.h>
@@ -29,8 +30,46 @@
 
 /* One engine handle per process, re-planned when the symbolic object changes. */
 static stmqr_handle g_handle = NULL ;
-static qr_symbolic *g_planned_for = NULL ;
-static Long g_planned_sig [6] ;
+static int g_have_plan = 0 ;
+static uint64_t g_planned_key = 0 ;
+
+/* Key of the device plan: a 64-bit hash of the CONTENT of the symbolic object, not of its address (a
+ * new qr_symbolic can be malloc'ed where a freed one was).  The arrays of size O(nf) are hashed in
+ * full; of the O(n), O(m), O(anz) arrays every stride-th word plus the last 512 words are hashed so
+ * that the key costs well under a millisecond on the 1M-unknown configs.  Two analyses of the same
+ * pattern under another ordering / relaxation / tolerance mode differ in Super/Rp/Fm/Cm (hashed in
+ * full) long before they agree on all sampled words.  STMQR_B200_CACHE_PLAN=0 re-plans on every call;
+ * stmqr_b200_dropin_invalidate_plan() drops the cached plan explicitly. */
+static uint64_t mix64 (uint64_t h, uint64_t v)
+{
+    h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2) ;
+    h *= 0xff51afd7ed558ccdULL ;
+    return h ^ (h >> 32) ;
+}
+static uint64_t hash_words (uint64_t h, const Long *a, Long count, Long max_samples)
+{
+    if (a == NULL || count <= 0) return mix64 (h, (uint64_t) count) ;
+    Long stride = (max_samples > 0 && count > max_samples) ? (count + max_samples - 1) / max_samples : 1 ;
+    for (Long i = 0 ; i < count ; i += stride) h = mix64 (h, (uint64_t) a [i]) ;
+    if (stride > 1) for (Long i = (count > 512) ? count - 512 : 0 ; i < count ; i++) h = mix64 (h, (uint64_t) a [i]) ;
+    return mix64 (h, (uint64_t) count) ;
+}
+static uint64_t symbolic_key (const qr_symbolic *Q)
+{
+    const Long S = 65536 ;
+    uint64_t h = 0x53544d5152423230ULL ;
+    const Long sc [12] = { Q->m, Q->n, Q->anz, Q->nf, Q->maxfn, Q->rjsize, Q->hisize, Q->do_rank_detection,
+        Q->keepH, Q->maxstack, Q->ntasks, Q->ns } ;
+    for (int i = 0 ; i < 12 ; i++) h = mix64 (h, (uint64_t) sc [i]) ;
+    h = hash_words (h, Q->Super, Q->nf + 1, 0) ;  h = hash_words (h, Q->Rp, Q->nf + 1, 0) ;
+    h = hash_words (h, Q->Childp, Q->nf + 2, 0) ; h = hash_words (h, Q->Child, Q->nf + 1, 0) ;
+    h = hash_words (h, Q->Hip, Q->nf + 1, 0) ;    h = hash_words (h, Q->Fm, Q->nf, 0) ;
+    h = hash_words (h, Q->Cm, Q->nf, 0) ;
+    h = hash_words (h, Q->Rj, Q->rjsize, S) ;     h = hash_words (h, Q->Sp, Q->m + 1, S) ;
+    h = hash_words (h, Q->Sj, Q->anz, S) ;        h = hash_words (h, Q->PLinv, Q->m, S) ;
+    h = hash_words (h, Q->Sleft, Q->n + 2, S) ;   h = hash_words (h, Q->Qfill, Q->Qfill ? Q->n : 0, S) ;
+    return h ;
+}
 
 static double now_ms (void)
 {
@@ -88,14 +127,13 @@ qr_numeric *stmqr_b200_qr_factorize (sparse_csc **Ahandle, Long freeA, double to
         }
     }
 
-    /* plan (level sets, maps, arenas): depends only on the symbolic object */
-    Long sig [6] = { m, n, nf, rjsize, hisize, QRsym->anz } ;
-    int same = (g_planned_for == QRsym) ;
-    for (int i = 0 ; same && i < 6 ; i++) same = (sig [i] == g_planned_sig [i]) ;
-    /* Re-planning is the safe default (a new qr_symbolic can be malloc'ed at the address of a
-     * freed one); STMQR_B200_CACHE_PLAN=1 keeps the plan across calls with the same object,
-     * which is what a refactorization loop over same-pattern matrices wants. */
-    if (!(same && getenv ("STMQR_B200_CACHE_PLAN")))
+    /* plan (level sets, maps, arenas): depends only on the symbolic object.  It is kept across calls
+     * and reused when the content key of the symbolic object is unchanged (a refactorization loop over
+     * same-pattern matrices, SparseQR.c:349,371, pays for it once). */
+    const char *cache_env = getenv ("STMQR_B200_CACHE_PLAN") ;
+    const int use_cache = !(cache_env && cache_env [0] == '0') ;
+    const uint64_t key = use_cache ? symbolic_key (QRsym) : 0 ;
+    if (!(use_cache && g_have_plan && key == g_planned_key))
     {
         stmqr_symbolic_view v ;
         v.m = m ; v.n = n ; v.anz = QRsym->anz ; v.nf = nf ; v.maxfn = QRsym->maxfn ;
@@ -105,16 +143,16 @@ qr_numeric *stmqr_b200_qr_factorize (sparse_csc **Ahandle, Long freeA, double to
         v.Sleft = QRsym->Sleft ; v.Parent = QRsym->Parent ; v.Child = QRsym->Child ;
         v.Childp = QRsym->Childp ; v.Super = QRsym->Super ; v.Rp = QRsym->Rp ; v.Rj = QRsym->Rj ;
         v.Post = QRsym->Post ; v.Hip = QRsym->Hip ; v.Fm = QRsym->Fm ; v.Cm = QRsym->Cm ;
+        g_have_plan = 0 ;
         s = stmqr_b200_analyze (g_handle, &v) ;
         if (s != STMQR_OK)
         {
-            g_planned_for = NULL ;
             if (freeA) SparseCore_free_sparse (Ahandle, cc) ;
             report (cc, s, "analyze") ;
             return (NULL) ;
         }
-        g_planned_for = QRsym ;
-        for (int i = 0 ; i < 6 ; i++) g_planned_sig [i] = sig [i] ;
+        g_have_plan = 1 ;
+        g_planned_key = key ;
     }
 
     t_plan = now_ms () ;
@@ -272,5 +310,11 @@ void stmqr_b200_dropin_shutdown (void)
 {
     if (g_handle) stmqr_b200_destroy (g_handle) ;
     g_handle = NULL ;
-    g_planned_for = NULL ;
+    g_have_plan = 0 ;
+}
+
+/* Forget the cached device plan: the next qr_factorize re-plans whatever its symbolic object is. */
+void stmqr_b200_dropin_invalidate_plan (void)
+{
+    g_have_plan = 0 ;
 }
