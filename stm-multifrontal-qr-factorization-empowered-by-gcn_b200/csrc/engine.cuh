@@ -68,7 +68,7 @@ struct DNum
     I64 *base1, *base2 ;    // [nf] scans used by qr_hpinv
     // exchange area of k_panel_grid (fronts too tall for a cluster of shared-memory slabs)
     double *gridrec ;       // [slots][2][148][64]
-    int4 *gridll ;          // [slots][2][148][64] the records as {lo, tag, hi, tag} lines
+    int4 *gridll ;          // [slots][2][148][128] the records as {lo, tag, hi, tag} lines
     double *gridred ;       // [slots][2][148]
     unsigned *gridctr ;     // [slots][GRID_CTR_STRIDE] arrival counters, zero between launches
     I32 *griderr ;

@@ -44,6 +44,7 @@ struct LevelArgs
     I32 count ;
     double tol ;
     I64 ntol ;
+    I32 flags ;             // bit 0: one column per exchange in the panel (A/B switch of the look-ahead)
 } ;
 
 // what one CTA publishes to its cluster for one Householder column
@@ -51,6 +52,8 @@ struct PanelXch
 {
     double dot [PANEL_MAX] ;    // sum over my rows in (g,t) of F(i,k) * F(i,c), every panel column c
     double rowg [PANEL_MAX] ;   // F(g,c), published by the CTA whose slab holds the pivot row g
+    double dotb [PANEL_MAX] ;   // the same dots for column k+1 (two columns per exchange, panel_columns_smem)
+    double rowg1 [PANEL_MAX] ;  // F(g+1,c), published by the CTA whose slab holds row g+1
     double mx ;                 // max over my rows in (g,t) of |F(i,k)|
     double ssq2 ;               // rescaled sum of squares (rare under/overflow path)
 } ;
@@ -302,8 +305,8 @@ constexpr int PANEL_NW_MAX = 16 ;       // 512 threads
 // per-CTA scratch carved from dynamic shared memory after the slab (sized by the # of warps)
 __host__ __device__ constexpr int panel_scratch_doubles (int nw)
 {
-    return 2 * nw * PANEL_MAX           // part [2][nw][32]  per-warp partial dots of the current column
-        + 2 * PANEL_MAX                 // prow [2][32]      the pivot row, published by its owner warp
+    return 4 * nw * PANEL_MAX           // part [2][nw][64]  per-warp partial dots of columns k and k+1
+        + 4 * PANEL_MAX                 // prow [2][64]      rows g and g+1, published by their owner warps
         + 2 * nw                        // red  [2][nw]      block reductions of the rescale path
         + PANEL_MAX * (PANEL_MAX + 1)   // Gs   [32][33]     V'V, then T in place (dlarft)
         + 4 * PANEL_MAX ;               // taus, stair in, stair out, flags (as doubles/ints)
@@ -320,7 +323,7 @@ struct GridComm
     unsigned G ;            // CTAs taking part
     unsigned cr ;           // my rank
     unsigned epoch ;        // barriers passed
-    int4 *ll ;              // [2][G][64] the same records as 16-byte lines {lo, tag, hi, tag}: data and
+    int4 *ll ;              // [2][G][128] the records (a | b | row g | row g+1) as 16-byte lines {lo, tag, hi, tag}: data and
                             // flag travel together (8-byte stores are atomic), so a step needs no
                             // barrier: readers poll the lines until the tag of the step shows up
     unsigned tagbase ;      // launch sequence number * 64
@@ -410,6 +413,23 @@ __device__ __forceinline__ double panel_allreduce (cg::cluster_group &cluster, G
     return v ;
 }
 
+// Two columns per exchange (look-ahead inside the panel).  The per-column cost of this loop is latency:
+// one block barrier, one cluster / L2 exchange and a sqrt + two divisions, all serial.  So the pass
+// that computes the dots of column k with every panel column (a) also computes the dots of column k+1
+// with every panel column (b), both over the rows from g+2 on, and the owners of rows g and g+1
+// publish those rows.  After ONE exchange every thread can derive H_k exactly as before (the row g+1
+// terms are added from the published row, no cancellation), and then H_{k+1} from the Gram entries:
+//   x' = x_{k+1} - v_k w           (w = tau_k v_k' x_{k+1})
+//   ||x'(g+2:)||^2 = b_{k+1} - 2 w s a_{k+1} + (w s)^2 a_k              (s = 1/(alpha_k - beta_k))
+//   x'(g+2:)' y'_c = (b_c - s w_c a_{k+1}) - w s (a_c - s w_c a_k)      (y'_c = y_c - v_k w_c)
+// The down-dated norm is only trusted when it keeps at least LA_THETA of the magnitude of its terms
+// (cancellation bounded: relative error <= eps / LA_THETA, and the error of the second reflector's
+// inner products stays a small multiple of eps ||y||, i.e. the update remains backward stable with a
+// constant 1/sqrt(LA_THETA)); otherwise, or when column k+1 looks dead, or in any of dlarfg's rare
+// scaling paths, the step handles column k alone and column k+1 gets its own direct pass -- exactly
+// the one-column algorithm.  Both reflectors are applied in one sweep: y <- ya y - fa x_k - fb x_{k+1}.
+constexpr double LA_THETA = 1.0 / 32.0 ;
+
 template <int NW, bool GRID>
 __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, GridComm &gc, const unsigned ECS,
     const I32 slab_cap, const I32 ldp, const LevelArgs &L, const DSym &S, const DNum &N,
@@ -417,10 +437,11 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
     const I32 nloc, const I32 rbeg, const I32 RL, const I32 rend, PanelXch *xch, I32 *cols, I32 *tq)
 {
     extern __shared__ double slab [] ;
+    constexpr int PM2 = 2 * PANEL_MAX ;
     double *const P = slab ;
-    double *const part = slab + slab_cap ;
-    double *const prow = part + 2 * NW * PANEL_MAX ;
-    double *const red = prow + 2 * PANEL_MAX ;
+    double *const part = slab + slab_cap ;              // [2][NW][64]  per-warp partial dots: a (0..31) | b (32..63)
+    double *const prow = part + 2 * NW * PM2 ;          // [2][64]      row g | row g+1, published by their owner warps
+    double *const red = prow + 2 * PM2 ;
     double *const Gs = red + 2 * NW ;
     double *const taus = Gs + PANEL_MAX * (PANEL_MAX + 1) ;
     I32 *const stl = (I32 *) (taus + PANEL_MAX) ;       // [32] staircase of the panel's columns (in)
@@ -444,6 +465,7 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
     const I32 np = k2 - k1 ;
     const bool leader = (cr == 0) ;
     const bool mycol = (lane < np) ;
+    const bool la_on = (L.flags & 1) == 0 ;
     double *yc = P + (I64) (mycol ? lane : 0) * ldp ;       // my column of the slab
 
     if (tid < PANEL_MAX)
@@ -463,90 +485,144 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
     I32 kstop = k2 ;
     PT_DECL ;
 
-    for (I32 k = k1 ; k < k2 ; k++)
+    for (I32 k = k1 ; k < k2 ; )
     {
         PT_MARK (7) ;
         if (g >= fm) { out_of_rows = true ; kstop = k ; break ; }
-        const I32 c = k - k1 ;
+        const I32 c = k - k1, c1 = c + 1 ;
         const I32 t = max (g + 1, stl [c]) ;
-        // slab rows strictly below the pivot row and inside the staircase: local [i0,i1)
-        const I32 i0 = max (g + 1, lrow0) - lrow0 ;
-        const I32 i1 = min (min (t, rend), lrow0 + nloc) - lrow0 ;
-        const unsigned owner = (ECS > 1) ? (unsigned) ((g - rbeg) / RL) : 0u ;
-        const I32 gi = g - lrow0 ;
-        const bool own_g = (cr == owner) && ((gi & (NW - 1)) == w) ;    // my warp owns the pivot row
+        // may column k+1 ride on this exchange?  (it needs a pivot row g+1 inside the front)
+        const bool la = la_on && (k + 1 < k2) && (g + 1 < fm) ;
+        const I32 t1 = la ? max (g + 2, stl [c1]) : t ;
+        // slab rows from row g+2 on inside the staircase of column k: local [j0,e0); of column k+1: [j0,e1)
+        const I32 j0 = max (g + 2, lrow0) - lrow0 ;
+        const I32 e0 = min (min (t, rend), lrow0 + nloc) - lrow0 ;
+        const I32 e1 = min (min (t1, rend), lrow0 + nloc) - lrow0 ;
+        const bool have1 = (g + 1 < rend) ;                 // row g+1 lies in the panel's row window
+        const unsigned owner0 = (ECS > 1) ? (unsigned) ((g - rbeg) / RL) : 0u ;
+        const unsigned owner1 = (ECS > 1 && have1) ? (unsigned) ((g + 1 - rbeg) / RL) : 0u ;
+        const I32 gi0 = g - lrow0, gi1 = g + 1 - lrow0 ;
+        const bool own_g0 = (cr == owner0) && ((gi0 & (NW - 1)) == w) ;             // my warp owns the pivot row
+        const bool own_g1 = have1 && (cr == owner1) && ((gi1 & (NW - 1)) == w) ;    // ... the row below it
         const int par = step & 1 ;
         step++ ;
-        const double *xc = P + (I64) c * ldp ;
-        // first row of my warp at or after i0
-        const I32 ifirst = i0 + ((w - i0) & (NW - 1)) ;
+        const double *x0 = P + (I64) c * ldp ;
+        const double *x1 = P + (I64) (la ? c1 : c) * ldp ;
+        // first row of my warp at or after j0
+        const I32 ifirst = j0 + ((w - j0) & (NW - 1)) ;
 
-        // ---- partial dots of column k with my column over my warp's rows ---------------------------
-        double s ;
+        // ---- partial dots of columns k and k+1 with my column over my warp's rows -----------------
+        double sA, sB = 0 ;
+        if (la)
+        {
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0 ;
+            I32 i = ifirst ;
+            for ( ; i + 3 * NW < e0 ; i += 4 * NW)
+            {
+                const double y0 = yc [i], y1 = yc [i + NW], y2 = yc [i + 2*NW], y3 = yc [i + 3*NW] ;
+                a0 = fma (x0 [i], y0, a0) ;             a1 = fma (x0 [i + NW], y1, a1) ;
+                a2 = fma (x0 [i + 2*NW], y2, a2) ;      a3 = fma (x0 [i + 3*NW], y3, a3) ;
+                b0 = fma (x1 [i], y0, b0) ;             b1 = fma (x1 [i + NW], y1, b1) ;
+                b2 = fma (x1 [i + 2*NW], y2, b2) ;      b3 = fma (x1 [i + 3*NW], y3, b3) ;
+            }
+            for ( ; i < e0 ; i += NW)
+            {
+                const double y0 = yc [i] ;
+                a0 = fma (x0 [i], y0, a0) ; b0 = fma (x1 [i], y0, b0) ;
+            }
+            // rows below the staircase of column k: column k is zero there
+            for ( ; i + 3 * NW < e1 ; i += 4 * NW)
+            {
+                b0 = fma (x1 [i], yc [i], b0) ;                 b1 = fma (x1 [i + NW], yc [i + NW], b1) ;
+                b2 = fma (x1 [i + 2*NW], yc [i + 2*NW], b2) ;   b3 = fma (x1 [i + 3*NW], yc [i + 3*NW], b3) ;
+            }
+            for ( ; i < e1 ; i += NW) b0 = fma (x1 [i], yc [i], b0) ;
+            sA = (a0 + a1) + (a2 + a3) ;
+            sB = (b0 + b1) + (b2 + b3) ;
+        }
+        else
         {
             double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0 ;
             I32 i = ifirst ;
-            for ( ; i + 7 * NW < i1 ; i += 8 * NW)
+            for ( ; i + 7 * NW < e0 ; i += 8 * NW)
             {
-                a0 = fma (xc [i], yc [i], a0) ;                 a1 = fma (xc [i + NW], yc [i + NW], a1) ;
-                a2 = fma (xc [i + 2*NW], yc [i + 2*NW], a2) ;   a3 = fma (xc [i + 3*NW], yc [i + 3*NW], a3) ;
-                a4 = fma (xc [i + 4*NW], yc [i + 4*NW], a4) ;   a5 = fma (xc [i + 5*NW], yc [i + 5*NW], a5) ;
-                a6 = fma (xc [i + 6*NW], yc [i + 6*NW], a6) ;   a7 = fma (xc [i + 7*NW], yc [i + 7*NW], a7) ;
+                a0 = fma (x0 [i], yc [i], a0) ;                 a1 = fma (x0 [i + NW], yc [i + NW], a1) ;
+                a2 = fma (x0 [i + 2*NW], yc [i + 2*NW], a2) ;   a3 = fma (x0 [i + 3*NW], yc [i + 3*NW], a3) ;
+                a4 = fma (x0 [i + 4*NW], yc [i + 4*NW], a4) ;   a5 = fma (x0 [i + 5*NW], yc [i + 5*NW], a5) ;
+                a6 = fma (x0 [i + 6*NW], yc [i + 6*NW], a6) ;   a7 = fma (x0 [i + 7*NW], yc [i + 7*NW], a7) ;
             }
-            if (i + 3 * NW < i1)
+            if (i + 3 * NW < e0)
             {
-                a0 = fma (xc [i], yc [i], a0) ;                 a1 = fma (xc [i + NW], yc [i + NW], a1) ;
-                a2 = fma (xc [i + 2*NW], yc [i + 2*NW], a2) ;   a3 = fma (xc [i + 3*NW], yc [i + 3*NW], a3) ;
+                a0 = fma (x0 [i], yc [i], a0) ;                 a1 = fma (x0 [i + NW], yc [i + NW], a1) ;
+                a2 = fma (x0 [i + 2*NW], yc [i + 2*NW], a2) ;   a3 = fma (x0 [i + 3*NW], yc [i + 3*NW], a3) ;
                 i += 4 * NW ;
             }
-            if (i < i1) a4 = fma (xc [i], yc [i], a4) ;
-            if (i + NW < i1) a5 = fma (xc [i + NW], yc [i + NW], a5) ;
-            if (i + 2 * NW < i1) a6 = fma (xc [i + 2*NW], yc [i + 2*NW], a6) ;
-            s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)) ;
+            if (i < e0) a4 = fma (x0 [i], yc [i], a4) ;
+            if (i + NW < e0) a5 = fma (x0 [i + NW], yc [i + NW], a5) ;
+            if (i + 2 * NW < e0) a6 = fma (x0 [i + 2*NW], yc [i + 2*NW], a6) ;
+            sA = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)) ;
         }
-        if (lane == c && s == 0.0)
+        if (lane == c && sA == 0.0)
         {
             // ||x||^2 = 0 over my rows: exactly zero entries, or squares that underflow?  Mark the
             // second case with a positive value below every regular sum of squares, so that the total
             // is 0 if and only if the sub-column is exactly zero (no extra exchange needed later)
             bool nz = false ;
-            for (I32 i = ifirst ; i < i1 ; i += NW) nz |= (xc [i] != 0.0) ;
-            if (nz) s = 1e-300 ;
+            for (I32 i = ifirst ; i < e0 ; i += NW) nz |= (x0 [i] != 0.0) ;
+            if (nz) sA = 1e-300 ;
         }
         PT_MARK (0) ;
-        part [(par * NW + w) * PANEL_MAX + lane] = mycol ? s : 0.0 ;
-        if (own_g) prow [par * PANEL_MAX + lane] = mycol ? yc [gi] : 0.0 ;
+        part [(par * NW + w) * PM2 + lane] = mycol ? sA : 0.0 ;
+        if (la) part [(par * NW + w) * PM2 + PANEL_MAX + lane] = mycol ? sB : 0.0 ;
+        if (own_g0) prow [par * PM2 + lane] = mycol ? yc [gi0] : 0.0 ;
+        if (own_g1) prow [par * PM2 + PANEL_MAX + lane] = mycol ? yc [gi1] : 0.0 ;
         __syncthreads () ;
         PT_MARK (1) ;
         {
             // FP64 adds have a long dependent latency: sum the NW partials as a tree
-            double pv [NW] ;
+            double pv [NW], pb [NW] ;
 #pragma unroll
-            for (int ww = 0 ; ww < NW ; ww++) pv [ww] = part [(par * NW + ww) * PANEL_MAX + lane] ;
+            for (int ww = 0 ; ww < NW ; ww++) pv [ww] = part [(par * NW + ww) * PM2 + lane] ;
+            if (la)
+            {
+#pragma unroll
+                for (int ww = 0 ; ww < NW ; ww++) pb [ww] = part [(par * NW + ww) * PM2 + PANEL_MAX + lane] ;
+            }
+            else
+            {
+#pragma unroll
+                for (int ww = 0 ; ww < NW ; ww++) pb [ww] = 0.0 ;
+            }
 #pragma unroll
             for (int h = NW / 2 ; h > 0 ; h >>= 1)
 #pragma unroll
-                for (int ww = 0 ; ww < h ; ww++) pv [ww] += pv [ww + h] ;
-            s = pv [0] ;
+                for (int ww = 0 ; ww < h ; ww++) { pv [ww] += pv [ww + h] ; pb [ww] += pb [ww + h] ; }
+            sA = pv [0] ; sB = pb [0] ;
         }
-        double rgv = (cr == owner) ? prow [par * PANEL_MAX + lane] : 0.0 ;
+        double r0 = (cr == owner0) ? prow [par * PM2 + lane] : 0.0 ;
+        double r1 = (have1 && cr == owner1) ? prow [par * PM2 + PANEL_MAX + lane] : 0.0 ;
         if (ECS > 1 && GRID)
         {
-            // one record per CTA in global memory (L2), summed in CTA order by warp 0 of every CTA:
-            // bitwise identical decisions everywhere
-            int4 *rec = gc.ll + (I64) par * gc.G * 64 ;
+            // one record per CTA in global memory (L2): a | b | row g | row g+1, summed in CTA order by
+            // every CTA: bitwise identical decisions everywhere
+            int4 *rec = gc.ll + (I64) par * gc.G * 128 ;
             const unsigned tag = gc.tagbase + (unsigned) step ;
             if (w == 0)
             {
-                ll_store (rec + cr * 64 + lane, s, tag) ;
-                if (cr == owner) ll_store (rec + cr * 64 + 32 + lane, rgv, tag) ;
+                ll_store (rec + cr * 128 + lane, sA, tag) ;
+                if (cr == owner0) ll_store (rec + cr * 128 + 64 + lane, r0, tag) ;
+            }
+            else if (w == 1)
+            {
+                if (la) ll_store (rec + cr * 128 + 32 + lane, sB, tag) ;
+                if (have1 && cr == owner1) ll_store (rec + cr * 128 + 96 + lane, r1, tag) ;
             }
             __syncthreads () ;          // part[par] is overwritten below: everybody has read its partials
             {
                 // warp w gathers the records w, w+NW, ...: all loads in flight at once, polled until the
                 // tag of this step shows up; summed in a fixed order, the same in every CTA
                 static_assert (!GRID || NW * 10 >= 148, "records per warp") ;
-                double v [10] ;
+                double v [10], vb [10] ;
                 bool ok ;
                 do
                 {
@@ -555,38 +631,55 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
                     for (int j = 0 ; j < 10 ; j++)
                     {
                         const unsigned r = (unsigned) (w + NW * j) ;
-                        v [j] = 0.0 ;
-                        if (r < ECS) ok &= ll_load (rec + r * 64 + lane, tag, v [j]) ;
+                        v [j] = 0.0 ; vb [j] = 0.0 ;
+                        if (r < ECS)
+                        {
+                            ok &= ll_load (rec + r * 128 + lane, tag, v [j]) ;
+                            if (la) ok &= ll_load (rec + r * 128 + 32 + lane, tag, vb [j]) ;
+                        }
                     }
                 } while (!__all_sync (STMQR_FULL_MASK, ok)) ;
                 if (w == 0)
                 {
                     double rv ;
-                    while (!__all_sync (STMQR_FULL_MASK, ll_load (rec + owner * 64 + 32 + lane, tag, rv))) { }
-                    prow [par * PANEL_MAX + lane] = rv ;
+                    while (!__all_sync (STMQR_FULL_MASK, ll_load (rec + owner0 * 128 + 64 + lane, tag, rv))) { }
+                    prow [par * PM2 + lane] = rv ;
                 }
-                part [(par * NW + w) * PANEL_MAX + lane] = (((v [0] + v [1]) + (v [2] + v [3])) + ((v [4] + v [5]) + (v [6] + v [7])))
+                else if (w == 1)
+                {
+                    double rv = 0.0 ;
+                    if (have1) while (!__all_sync (STMQR_FULL_MASK, ll_load (rec + owner1 * 128 + 96 + lane, tag, rv))) { }
+                    prow [par * PM2 + PANEL_MAX + lane] = rv ;
+                }
+                part [(par * NW + w) * PM2 + lane] = (((v [0] + v [1]) + (v [2] + v [3])) + ((v [4] + v [5]) + (v [6] + v [7])))
                     + (v [8] + v [9]) ;
+                part [(par * NW + w) * PM2 + PANEL_MAX + lane] = (((vb [0] + vb [1]) + (vb [2] + vb [3])) + ((vb [4] + vb [5]) + (vb [6] + vb [7])))
+                    + (vb [8] + vb [9]) ;
             }
             __syncthreads () ;
             {
-                double pv [NW] ;
+                double pv [NW], pb [NW] ;
 #pragma unroll
-                for (int ww = 0 ; ww < NW ; ww++) pv [ww] = part [(par * NW + ww) * PANEL_MAX + lane] ;
+                for (int ww = 0 ; ww < NW ; ww++)
+                {
+                    pv [ww] = part [(par * NW + ww) * PM2 + lane] ;
+                    pb [ww] = part [(par * NW + ww) * PM2 + PANEL_MAX + lane] ;
+                }
 #pragma unroll
                 for (int h = NW / 2 ; h > 0 ; h >>= 1)
 #pragma unroll
-                    for (int ww = 0 ; ww < h ; ww++) pv [ww] += pv [ww + h] ;
-                s = pv [0] ;
+                    for (int ww = 0 ; ww < h ; ww++) { pv [ww] += pv [ww + h] ; pb [ww] += pb [ww + h] ; }
+                sA = pv [0] ; sB = pb [0] ;
             }
-            rgv = prow [par * PANEL_MAX + lane] ;
+            r0 = prow [par * PM2 + lane] ; r1 = prow [par * PM2 + PANEL_MAX + lane] ;
         }
         else if (ECS > 1)
         {
-            // one record per CTA through distributed shared memory; only warp 0 talks to the peers
-            // (DSMEM bandwidth is ~20 B/clk per SM) and re-publishes the totals locally
+            // one record per CTA through distributed shared memory; only warps 0 (a, row g) and 1 (b,
+            // row g+1) talk to the peers (DSMEM bandwidth is ~20 B/clk per SM) and re-publish the totals
             PanelXch &X = xch [par] ;
-            if (w == 0) { X.dot [lane] = s ; X.rowg [lane] = rgv ; }
+            if (w == 0) { X.dot [lane] = sA ; X.rowg [lane] = r0 ; }
+            else if (w == 1) { X.dotb [lane] = sB ; X.rowg1 [lane] = r1 ; }
             cluster.sync () ;
             if (w == 0)
             {
@@ -595,20 +688,43 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
 #pragma unroll
                 for (unsigned r = 0 ; r < 16 ; r++)
                     dv [r] = (r < 8 || ECS > 8) ? cluster.map_shared_rank (&X, (r < ECS) ? r : 0)->dot [lane] : 0.0 ;
-                rgv = cluster.map_shared_rank (&X, owner)->rowg [lane] ;
-                s = 0 ;
+                r0 = cluster.map_shared_rank (&X, owner0)->rowg [lane] ;
+                double sum = 0 ;
 #pragma unroll
-                for (unsigned r = 0 ; r < 16 ; r++) if (r < ECS) s += dv [r] ;
-                part [(par * NW) * PANEL_MAX + lane] = s ;      // part[par] is dead after the block reduction
-                prow [par * PANEL_MAX + lane] = rgv ;
+                for (unsigned r = 0 ; r < 16 ; r++) if (r < ECS) sum += dv [r] ;
+                part [(par * NW) * PM2 + lane] = sum ;      // part[par] is dead after the block reduction
+                prow [par * PM2 + lane] = r0 ;
+            }
+            else if (w == 1)
+            {
+                double sum = 0 ;
+                if (la)
+                {
+                    double dv [16] ;
+#pragma unroll
+                    for (unsigned r = 0 ; r < 16 ; r++)
+                        dv [r] = (r < 8 || ECS > 8) ? cluster.map_shared_rank (&X, (r < ECS) ? r : 0)->dotb [lane] : 0.0 ;
+#pragma unroll
+                    for (unsigned r = 0 ; r < 16 ; r++) if (r < ECS) sum += dv [r] ;
+                }
+                r1 = have1 ? cluster.map_shared_rank (&X, owner1)->rowg1 [lane] : 0.0 ;
+                part [(par * NW) * PM2 + PANEL_MAX + lane] = sum ;
+                prow [par * PM2 + PANEL_MAX + lane] = r1 ;
             }
             __syncthreads () ;
-            s = part [(par * NW) * PANEL_MAX + lane] ; rgv = prow [par * PANEL_MAX + lane] ;
+            sA = part [(par * NW) * PM2 + lane] ; sB = part [(par * NW) * PM2 + PANEL_MAX + lane] ;
+            r0 = prow [par * PM2 + lane] ; r1 = prow [par * PM2 + PANEL_MAX + lane] ;
         }
         PT_MARK (2) ;
+        // ---- H_k: dlarfg on F(g:t-1,k) -------------------------------------------------------------
+        // F(g+1,k): inside the staircase it comes from the published row g+1, below it is structurally zero
+        const double x0g1 = (g + 1 < t) ? __shfl_sync (STMQR_FULL_MASK, r1, c) : 0.0 ;
+        const double s = fma (x0g1, r1, sA) ;       // dot of column k with my column over the rows (g, t)
         double ss = __shfl_sync (STMQR_FULL_MASK, s, c) ;
-        const double alpha = __shfl_sync (STMQR_FULL_MASK, rgv, c) ;
+        if (ss == 0.0 && x0g1 != 0.0) ss = 1e-300 ;         // (underflowed square of a non-zero entry, see the marker above)
+        const double alpha = __shfl_sync (STMQR_FULL_MASK, r0, c) ;
         double beta = alpha, tau = 0, scale = 0 ;
+        bool rare = false ;
         if (t - g > 1)
         {
             double nrm ;
@@ -634,6 +750,7 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
             {
                 // rare: zero or badly scaled sub-column: max |x| first, then the rescaled sum of
                 // squares (dnrm2 semantics).  The decision is uniform over the cluster.
+                rare = true ;
 #ifdef STMQR_PANEL_TIMING
                 if (tid == 0 && leader)
                 {
@@ -647,14 +764,17 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
                     if (fabs (alpha) >= 1e140) atomicAdd (N.dbg + 56, 1ULL) ;
                 }
 #endif
+                // my warp's rows in (g, t): local [i0, e0)
+                const I32 i0 = max (g + 1, lrow0) - lrow0 ;
+                const I32 if1 = i0 + ((w - i0) & (NW - 1)) ;
                 double mx = 0 ;
-                for (I32 i = ifirst ; i < i1 ; i += NW) mx = fmax (mx, fabs (xc [i])) ;
+                for (I32 i = if1 ; i < e0 ; i += NW) mx = fmax (mx, fabs (x0 [i])) ;
                 mx = panel_allreduce<NW, true, GRID> (cluster, gc, ECS, mx, red, xch [par], par) ;
                 if (mx > 0)
                 {
                     const double inv = 1.0 / mx ;
                     double s2 = 0 ;
-                    for (I32 i = ifirst ; i < i1 ; i += NW) { const double v = xc [i] * inv ; s2 += v * v ; }
+                    for (I32 i = if1 ; i < e0 ; i += NW) { const double v = x0 [i] * inv ; s2 += v * v ; }
                     s2 = panel_allreduce<NW, false, GRID> (cluster, gc, ECS, s2, red + NW, xch [par], par) ;
                     nrm = hypot (alpha, mx * sqrt (s2)) ;
                     ss = 1.0 ;
@@ -675,6 +795,47 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
             }
         }
         const bool dead = (k < ntol) && (fabs (beta) <= tol) ;
+        const double wv = tau * (r0 + scale * s) ;          // w_c = tau v_k' y_c (meaningful on lanes > c)
+        const double vg1 = scale * x0g1 ;                   // v_k (g+1)
+
+        // ---- H_{k+1} from the same exchange (see the header of this function) ----------------------
+        bool two = false ;
+        double beta1 = 0, tau1 = 0, scale1 = 0, so = 0, A_c = 0, A_c1 = 0 ;
+        if (la && !dead && !rare)
+        {
+            A_c = __shfl_sync (STMQR_FULL_MASK, sA, c) ;
+            if (A_c == 1e-300) A_c = 0 ;                    // (the exact-zero marker is not a value)
+            A_c1 = __shfl_sync (STMQR_FULL_MASK, sA, c1) ;
+            const double B_c1 = __shfl_sync (STMQR_FULL_MASK, sB, c1) ;
+            const double om = __shfl_sync (STMQR_FULL_MASK, wv, c1) ;
+            const double alpha1 = __shfl_sync (STMQR_FULL_MASK, r1, c1) - vg1 * om ;
+            so = scale * om ;
+            bool ok1 = false ;
+            if (t1 - (g + 1) <= 1)
+            {
+                // no rows below the new pivot: H = I (dlarfg with n = 1)
+                beta1 = alpha1 ; ok1 = true ;
+            }
+            else
+            {
+                const double m1 = 2.0 * so * A_c1, m2 = so * so * A_c ;
+                const double ss1 = (B_c1 - m1) + m2 ;
+                const double mag = B_c1 + fabs (m1) + m2 ;
+                if (ss1 >= LA_THETA * mag && ss1 > 1e-280 && mag < 1e280 && fabs (alpha1) < 1e140)
+                {
+                    beta1 = -copysign (sqrt (fma (alpha1, alpha1, ss1)), alpha1) ;
+                    tau1 = (beta1 - alpha1) / beta1 ;
+                    scale1 = 1.0 / (alpha1 - beta1) ;
+                    ok1 = (fabs (tau1) <= 2.0) && (fabs (scale1) < 1e300) ;
+                }
+            }
+            // a column that looks dead gets the direct (one-column) pass: its decision is then made on
+            // a norm without any down-date
+            two = ok1 && !((k + 1 < ntol) && (fabs (beta1) <= tol)) ;
+#ifdef STMQR_PANEL_TIMING
+            if (tid == 0 && leader) atomicAdd (N.dbg + (two ? 54 : 55), 1ULL) ;
+#endif
+        }
         PT_MARK (3) ;
 
         if (dead)
@@ -691,40 +852,84 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
                 for (I32 i = rend + tid ; i < fm ; i += nt) xg [i] = 0.0 ;
                 if (tid == 0) { sto [c] = 0 ; tauo [c] = 0 ; }
             }
+            k++ ;
         }
         else
         {
-            // ---- dlarf on my warp's rows: columns > k get the rank-1 update, column k is scaled ----
-            const double wv = tau * (rgv + scale * s) ;
-            const double fct = (lane == c) ? 0.0 : scale * wv ;
-            if (tau != 0)
+            // ---- dlarf on my warp's rows from g+2 on: y <- ya y - fa x_k - fb x_{k+1} -----------------
+            //   lane c    : v_k = scale x_k                                    (ya, fa, fb) = (scale, 0, 0)
+            //   lane c+1  : v_{k+1} = scale1 (x_{k+1} - scale w x_k)           (scale1, scale1 scale w, 0)
+            //   lanes > c+1: y - v_k w_c - v_{k+1} w'_c
+            double r1p = r1, w1 = 0 ;                       // row g+1 of my column after H_k; w'_c
+            if (lane > c) r1p = fma (-vg1, wv, r1) ;
+            else if (lane == c) r1p = vg1 ;
+            double d1 = 0 ;                                 // x'(g+2:)' y'_c  (v_c for the lanes <= c)
+            if (two)
             {
-                // lane c turns x into v = x * scale, lanes > c subtract x * fct: one formula
-                // y = y * a - x * b with (a,b) = (scale,0) on lane c and (1,fct) on the others
-                const double ya = (lane == c) ? scale : 1.0 ;
-                if (lane >= c && mycol)
+                const double swv = (lane > c) ? scale * wv : 0.0 ;
+                d1 = (lane == c) ? scale * (A_c1 - so * A_c) : ((sB - swv * A_c1) - so * (sA - swv * A_c)) ;
+                w1 = tau1 * (r1p + scale1 * d1) ;
+            }
+            double ya = 1.0, fa = 0.0, fb = 0.0 ;
+            if (lane == c) { if (tau != 0) ya = scale ; }
+            else if (two && lane == c1) { if (tau1 != 0) ya = scale1 ; fa = ya * so ; }
+            else if (lane > c) { fb = scale1 * w1 ; fa = fma (-fb, so, scale * wv) ; }
+            if ((tau != 0 || two) && lane >= c && mycol)
+            {
+                const I32 ee = two ? e1 : e0 ;
+                I32 i = ifirst ;
+                if (two)
                 {
-                    I32 i = ifirst ;
-                    for ( ; i + 3 * NW < i1 ; i += 4 * NW)
+                    for ( ; i + 3 * NW < ee ; i += 4 * NW)
                     {
-                        const double x0 = xc [i], x1 = xc [i + NW], x2 = xc [i + 2*NW], x3 = xc [i + 3*NW] ;
+                        const double u0 = x0 [i], u1 = x0 [i + NW], u2 = x0 [i + 2*NW], u3 = x0 [i + 3*NW] ;
+                        const double z0 = x1 [i], z1 = x1 [i + NW], z2 = x1 [i + 2*NW], z3 = x1 [i + 3*NW] ;
                         const double y0 = yc [i], y1 = yc [i + NW], y2 = yc [i + 2*NW], y3 = yc [i + 3*NW] ;
                         __syncwarp (__activemask ()) ;
-                        yc [i] = fma (-x0, fct, y0 * ya) ; yc [i + NW] = fma (-x1, fct, y1 * ya) ;
-                        yc [i + 2*NW] = fma (-x2, fct, y2 * ya) ; yc [i + 3*NW] = fma (-x3, fct, y3 * ya) ;
+                        yc [i] = fma (-z0, fb, fma (-u0, fa, y0 * ya)) ;
+                        yc [i + NW] = fma (-z1, fb, fma (-u1, fa, y1 * ya)) ;
+                        yc [i + 2*NW] = fma (-z2, fb, fma (-u2, fa, y2 * ya)) ;
+                        yc [i + 3*NW] = fma (-z3, fb, fma (-u3, fa, y3 * ya)) ;
                     }
-                    for ( ; i < i1 ; i += NW)
+                    for ( ; i < ee ; i += NW)
                     {
-                        const double x0 = xc [i], y0 = yc [i] ;
+                        const double u0 = x0 [i], z0 = x1 [i], y0 = yc [i] ;
                         __syncwarp (__activemask ()) ;
-                        yc [i] = fma (-x0, fct, y0 * ya) ;
+                        yc [i] = fma (-z0, fb, fma (-u0, fa, y0 * ya)) ;
                     }
                 }
-                if (own_g && lane > c && mycol) yc [gi] -= wv ;
+                else
+                {
+                    for ( ; i + 3 * NW < ee ; i += 4 * NW)
+                    {
+                        const double u0 = x0 [i], u1 = x0 [i + NW], u2 = x0 [i + 2*NW], u3 = x0 [i + 3*NW] ;
+                        const double y0 = yc [i], y1 = yc [i + NW], y2 = yc [i + 2*NW], y3 = yc [i + 3*NW] ;
+                        __syncwarp (__activemask ()) ;
+                        yc [i] = fma (-u0, fa, y0 * ya) ; yc [i + NW] = fma (-u1, fa, y1 * ya) ;
+                        yc [i + 2*NW] = fma (-u2, fa, y2 * ya) ; yc [i + 3*NW] = fma (-u3, fa, y3 * ya) ;
+                    }
+                    for ( ; i < ee ; i += NW)
+                    {
+                        const double u0 = x0 [i], y0 = yc [i] ;
+                        __syncwarp (__activemask ()) ;
+                        yc [i] = fma (-u0, fa, y0 * ya) ;
+                    }
+                }
             }
-            if (own_g && lane == c) yc [gi] = beta ;
+            // the two pivot rows, by their owner warps
+            if (own_g0 && mycol)
+            {
+                if (lane == c) yc [gi0] = beta ;
+                else if (lane > c && tau != 0) yc [gi0] -= wv ;
+            }
+            if (own_g1 && mycol && lane >= c)
+            {
+                if (two && lane == c1) yc [gi1] = beta1 ;
+                else if (two && lane > c1) yc [gi1] = r1p - w1 ;
+                else if (tau != 0 && g + 1 < t) yc [gi1] = r1p ;   // (lane c: v_k (g+1); lanes > c: row g+1 after H_k)
+            }
             // V'V entries for dlarft: v_j' v_k = scale * (v_j' x) + v_j (g), j an earlier reflector
-            if (leader && w == 0 && myq >= 0) Gs [myq + nv * (PANEL_MAX + 1)] = scale * s + rgv ;
+            if (leader && w == 0 && myq >= 0) Gs [myq + nv * (PANEL_MAX + 1)] = scale * s + r0 ;
             if (leader && tid == 0)
             {
                 sto [c] = t ; tauo [c] = tau ;
@@ -734,8 +939,28 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
             flops += (double) (t - g) * (3.0 + 4.0 * (double) (fn - k - 1)) ;
             nv++ ;
             g++ ;
+            if (k == fp - 1 && leader && tid == 0) N.rank [f] = g ;
+            k++ ;
+            if (two)
+            {
+                // v_j' v_{k+1} = v_j (g+1) + scale1 * (v_j' x'),  j <= k
+                if (leader && w == 0 && myq >= 0) Gs [myq + nv * (PANEL_MAX + 1)] = r1p + scale1 * d1 ;
+                if (leader && tid == 0)
+                {
+                    sto [c1] = t1 ; tauo [c1] = tau1 ;
+                    cols [nv] = k ; tq [nv] = t1 ; taus [nv] = tau1 ;
+                }
+                if (lane == c1) myq = nv ;
+                flops += (double) (t1 - g) * (3.0 + 4.0 * (double) (fn - k - 1)) ;
+                nv++ ;
+                g++ ;
+                if (k == fp - 1 && leader && tid == 0) N.rank [f] = g ;
+                k++ ;
+            }
         }
-        if (k == fp - 1 && leader && tid == 0) N.rank [f] = g ;
+        if (dead && k - 1 == fp - 1 && leader && tid == 0) N.rank [f] = g ;
+        // the next step's dots read, on this warp's rows, columns that other lanes of the warp just wrote
+        __syncwarp () ;
         PT_MARK (4) ;
     }
     __syncthreads () ;
@@ -850,7 +1075,7 @@ __global__ void __launch_bounds__ (NT, MINB) k_panel_cluster (LevelArgs L, DSym 
     __shared__ I32 cols [PANEL_MAX], tq [PANEL_MAX] ;
     constexpr int NW = NT / 32 ;
     // global-mode scratch (V'V / T, taus) lives behind the slab like the shared-memory mode's
-    double *Gs = slab + slab_cap + 2 * NW * PANEL_MAX + 2 * PANEL_MAX + 2 * NW ;
+    double *Gs = slab + slab_cap + 4 * NW * PANEL_MAX + 4 * PANEL_MAX + 2 * NW ;
     double *Tsh = Gs ;
     double *taus = Gs + PANEL_MAX * (PANEL_MAX + 1) ;
 
@@ -988,7 +1213,7 @@ __global__ void __launch_bounds__ (512, 1) k_panel_grid (LevelArgs L, DSym S, DN
         gc.rec = N.gridrec + (I64) slot * (2 * 148 * 64) ;
         gc.red = N.gridred + (I64) slot * (2 * 148) ;
         gc.ctr = ctr + 128 ; gc.G = ECS ; gc.cr = cr ; gc.epoch = 0 ;
-        gc.ll = N.gridll + (I64) slot * (2 * 148 * 64) ; gc.tagbase = seq * 64u ;
+        gc.ll = N.gridll + (I64) slot * (2 * 148 * 128) ; gc.tagbase = seq * 64u ;
         panel_columns_smem<NW, true> (cluster, gc, ECS, slab_cap, ldp, L, S, N, slot, f, k1, k2, parity, lrow0, nloc, g1,
             RL, rend, xch, cols, tq) ;
     }

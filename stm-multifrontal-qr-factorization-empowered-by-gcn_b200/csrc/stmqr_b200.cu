@@ -895,8 +895,8 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
         for (const Level &Lv : h->ls_all.levels) if (Lv.maxFm >= h->grid_rows) gslots = std::max<I64> (gslots, Lv.nbig) ;
         ALLOC (N.gridrec, gslots * 2 * 148 * 64) ;
         ALLOC (N.gridred, gslots * 2 * 148) ;
-        ALLOC (N.gridll, gslots * 2 * 148 * 64) ;
-        CK (cudaMemsetAsync (N.gridll, 0, gslots * 2 * 148 * 64 * sizeof (int4), h->stream)) ;
+        ALLOC (N.gridll, gslots * 2 * 148 * 128) ;
+        CK (cudaMemsetAsync (N.gridll, 0, gslots * 2 * 148 * 128 * sizeof (int4), h->stream)) ;
         ALLOC (N.gridctr, gslots * GRID_CTR_STRIDE) ;
         ALLOC (N.griderr, 1) ;
         CK (cudaMemsetAsync (N.gridctr, 0, gslots * GRID_CTR_STRIDE * sizeof (unsigned), h->stream)) ;
@@ -1082,6 +1082,7 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
         } ;
         check ("assemble", 0, 0) ;
         LevelArgs L ; L.fronts = fr ; L.count = nbig ; L.tol = tol ; L.ntol = ntol ;
+        L.flags = (h->opt.reserved & 32) ? 1 : 0 ;          // bit 5: one column per panel exchange
         // ---- front QR of the level: panel steps of PB columns over all active fronts ---------------
         // cluster size: the row slab of one CTA (rows / CS x PB doubles) should fit in shared memory
         int CS = 1 ;
