@@ -52,8 +52,6 @@ struct PanelXch
 {
     double dot [PANEL_MAX] ;    // sum over my rows in (g,t) of F(i,k) * F(i,c), every panel column c
     double rowg [PANEL_MAX] ;   // F(g,c), published by the CTA whose slab holds the pivot row g
-    double dotb [PANEL_MAX] ;   // the same dots for column k+1 (two columns per exchange, panel_columns_smem)
-    double rowg1 [PANEL_MAX] ;  // F(g+1,c), published by the CTA whose slab holds row g+1
     double mx ;                 // max over my rows in (g,t) of |F(i,k)|
     double ssq2 ;               // rescaled sum of squares (rare under/overflow path)
 } ;
@@ -301,6 +299,8 @@ __device__ __forceinline__ void panel_columns (cg::cluster_group &cluster, doubl
 // touches global memory: the staircase of the panel's columns is staged in shared memory and the
 // per-column outputs (Stair, Tau, Rdead) are written once at the end.
 constexpr int PANEL_NW_MAX = 16 ;       // 512 threads
+constexpr int PANEL_XR_CTAS = 8 ;       // largest cluster of k_panel_cluster (portable size)
+constexpr int PANEL_XR_DOUBLES = 2 * PANEL_XR_CTAS * 2 * PANEL_MAX + 2 * 2 * PANEL_MAX ;   // xrec [2][8][64] + xrows [2][64]
 
 // per-CTA scratch carved from dynamic shared memory after the slab (sized by the # of warps)
 __host__ __device__ constexpr int panel_scratch_doubles (int nw)
@@ -434,7 +434,8 @@ template <int NW, bool GRID>
 __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, GridComm &gc, const unsigned ECS,
     const I32 slab_cap, const I32 ldp, const LevelArgs &L, const DSym &S, const DNum &N,
     const I32 slot, const I32 f, const I32 k1, const I32 k2, const I32 parity, const I32 lrow0,
-    const I32 nloc, const I32 rbeg, const I32 RL, const I32 rend, PanelXch *xch, I32 *cols, I32 *tq)
+    const I32 nloc, const I32 rbeg, const I32 RL, const I32 rend, PanelXch *xch, double *xrec, double *xrows,
+    I32 *cols, I32 *tq)
 {
     extern __shared__ double slab [] ;
     constexpr int PM2 = 2 * PANEL_MAX ;
@@ -675,45 +676,39 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
         }
         else if (ECS > 1)
         {
-            // one record per CTA through distributed shared memory; only warps 0 (a, row g) and 1 (b,
-            // row g+1) talk to the peers (DSMEM bandwidth is ~20 B/clk per SM) and re-publish the totals
-            PanelXch &X = xch [par] ;
-            if (w == 0) { X.dot [lane] = sA ; X.rowg [lane] = r0 ; }
-            else if (w == 1) { X.dotb [lane] = sB ; X.rowg1 [lane] = r1 ; }
+            // PUSH through distributed shared memory: warp w stores this CTA's record (a | b, and the rows
+            // g, g+1 if it holds them) straight into the shared memory of the CTAs w, w+NW, ... of the
+            // cluster -- remote stores are fire-and-forget -- ONE cluster barrier makes all records
+            // visible, and then every thread sums the ECS records from its OWN shared memory in rank
+            // order: bitwise identical totals everywhere, no remote-load latency, no re-publishing.
+            // (A record buffer is reused two steps later; by then every CTA has passed the barrier of
+            // the step in between, which it reaches only after reading this step's records.)
+            double *rec = xrec + par * (PANEL_XR_CTAS * PM2) ;      // [ECS][64]
+            double *rws = xrows + par * PM2 ;                       // row g | row g+1
+            for (unsigned r = (unsigned) w ; r < ECS ; r += NW)
+            {
+                double *dst = cluster.map_shared_rank (rec, r) + cr * PM2 ;
+                dst [lane] = sA ;
+                dst [PANEL_MAX + lane] = sB ;
+                double *drw = cluster.map_shared_rank (rws, r) ;
+                if (cr == owner0) drw [lane] = r0 ;
+                if (have1 && cr == owner1) drw [PANEL_MAX + lane] = r1 ;
+            }
             cluster.sync () ;
-            if (w == 0)
             {
-                // same order in every CTA: bitwise identical decisions
-                double dv [16] ;
+                double dv [PANEL_XR_CTAS], db [PANEL_XR_CTAS] ;
 #pragma unroll
-                for (unsigned r = 0 ; r < 16 ; r++)
-                    dv [r] = (r < 8 || ECS > 8) ? cluster.map_shared_rank (&X, (r < ECS) ? r : 0)->dot [lane] : 0.0 ;
-                r0 = cluster.map_shared_rank (&X, owner0)->rowg [lane] ;
-                double sum = 0 ;
-#pragma unroll
-                for (unsigned r = 0 ; r < 16 ; r++) if (r < ECS) sum += dv [r] ;
-                part [(par * NW) * PM2 + lane] = sum ;      // part[par] is dead after the block reduction
-                prow [par * PM2 + lane] = r0 ;
-            }
-            else if (w == 1)
-            {
-                double sum = 0 ;
-                if (la)
+                for (unsigned r = 0 ; r < PANEL_XR_CTAS ; r++)
                 {
-                    double dv [16] ;
-#pragma unroll
-                    for (unsigned r = 0 ; r < 16 ; r++)
-                        dv [r] = (r < 8 || ECS > 8) ? cluster.map_shared_rank (&X, (r < ECS) ? r : 0)->dotb [lane] : 0.0 ;
-#pragma unroll
-                    for (unsigned r = 0 ; r < 16 ; r++) if (r < ECS) sum += dv [r] ;
+                    dv [r] = (r < ECS) ? rec [r * PM2 + lane] : 0.0 ;
+                    db [r] = (la && r < ECS) ? rec [r * PM2 + PANEL_MAX + lane] : 0.0 ;
                 }
-                r1 = have1 ? cluster.map_shared_rank (&X, owner1)->rowg1 [lane] : 0.0 ;
-                part [(par * NW) * PM2 + PANEL_MAX + lane] = sum ;
-                prow [par * PM2 + PANEL_MAX + lane] = r1 ;
+                sA = dv [0] ; sB = db [0] ;
+#pragma unroll
+                for (unsigned r = 1 ; r < PANEL_XR_CTAS ; r++) if (r < ECS) { sA += dv [r] ; sB += db [r] ; }
             }
-            __syncthreads () ;
-            sA = part [(par * NW) * PM2 + lane] ; sB = part [(par * NW) * PM2 + PANEL_MAX + lane] ;
-            r0 = prow [par * PM2 + lane] ; r1 = prow [par * PM2 + PANEL_MAX + lane] ;
+            r0 = rws [lane] ;
+            r1 = have1 ? rws [PANEL_MAX + lane] : 0.0 ;
         }
         PT_MARK (2) ;
         // ---- H_k: dlarfg on F(g:t-1,k) -------------------------------------------------------------
@@ -723,14 +718,16 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
         double ss = __shfl_sync (STMQR_FULL_MASK, s, c) ;
         if (ss == 0.0 && x0g1 != 0.0) ss = 1e-300 ;         // (underflowed square of a non-zero entry, see the marker above)
         const double alpha = __shfl_sync (STMQR_FULL_MASK, r0, c) ;
-        double beta = alpha, tau = 0, scale = 0 ;
+        double beta = alpha, tau = 0, scale = 0, rinv = 0 ;
         bool rare = false ;
         if (t - g > 1)
         {
             double nrm ;
             if (ss > 1e-280 && ss < 1e280 && fabs (alpha) < 1e140)
             {
-                nrm = sqrt (fma (alpha, alpha, ss)) ;           // hypot (alpha, ||x||)
+                const double q = fma (alpha, alpha, ss) ;
+                rinv = rsqrt (q) ;
+                nrm = q * rinv ;                                // hypot (alpha, ||x||)
             }
             else if (ss == 0)
             {
@@ -788,8 +785,19 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
             if (ss != 0)
             {
                 beta = -copysign (nrm, alpha) ;
-                tau = (beta - alpha) / beta ;
-                scale = 1.0 / (alpha - beta) ;
+                if (rinv != 0)
+                {
+                    // regular path: tau = (beta-alpha)/beta = 1 + |alpha|/nrm and 1/(alpha-beta) =
+                    // sign(alpha) / (|alpha| + nrm) from the reciprocal square root: one reciprocal instead
+                    // of two divisions behind the square root (this scalar chain is serial in every step)
+                    tau = fma (fabs (alpha), rinv, 1.0) ;
+                    scale = copysign (1.0 / (fabs (alpha) + nrm), alpha) ;
+                }
+                else
+                {
+                    tau = (beta - alpha) / beta ;
+                    scale = 1.0 / (alpha - beta) ;
+                }
                 // safety net (overflow of the norm or of 1/(alpha-beta)): never emit a non-finite reflector
                 if (!(fabs (tau) <= 2.0) || !(fabs (scale) < 1e300)) { beta = alpha ; tau = 0 ; scale = 0 ; }
             }
@@ -823,9 +831,12 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
                 const double mag = B_c1 + fabs (m1) + m2 ;
                 if (ss1 >= LA_THETA * mag && ss1 > 1e-280 && mag < 1e280 && fabs (alpha1) < 1e140)
                 {
-                    beta1 = -copysign (sqrt (fma (alpha1, alpha1, ss1)), alpha1) ;
-                    tau1 = (beta1 - alpha1) / beta1 ;
-                    scale1 = 1.0 / (alpha1 - beta1) ;
+                    const double q1 = fma (alpha1, alpha1, ss1) ;
+                    const double rinv1 = rsqrt (q1) ;
+                    const double nrm1 = q1 * rinv1 ;
+                    beta1 = -copysign (nrm1, alpha1) ;
+                    tau1 = fma (fabs (alpha1), rinv1, 1.0) ;
+                    scale1 = copysign (1.0 / (fabs (alpha1) + nrm1), alpha1) ;
                     ok1 = (fabs (tau1) <= 2.0) && (fabs (scale1) < 1e300) ;
                 }
             }
@@ -993,52 +1004,60 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
 #pragma unroll 4
         for (I32 i = lane ; i < nloc ; i += 32) dst [i] = src [i] ;
     }
-    if (NW == 16 && leader && nv > 8 && k2 < fn)
+    if (leader && nv > 1 && k2 < fn)
     {
-        // dlarft without its 496-step dependent chain (FP64 latency): T^-1 = D^-1 + striu(V'V)
-        // (D = diag(tau)), so with N = -D striu(V'V) (nilpotent) T = (I - N)^-1 D and
-        // (I - N)^-1 = (I + N)(I + N^2)(I + N^4)(I + N^8)(I + N^16): a few 32x32 products that all
-        // threads share.  Column i of T is zero when tau_i = 0, as dlarft leaves it.
-        __syncthreads () ;
+        // dlarft by recursive doubling instead of its 496-step dependent chain: for a block reflector
+        // split as [V1 V2], T = [T11 T12 ; 0 T22] with T12 = -T11 (V1'V2) T22.  Start from the 1 x 1
+        // blocks T(i,i) = tau_i and merge neighbouring blocks of size B = 1, 2, 4, 8, 16; every merge is
+        // two small triangular products, one output entry per thread, dependent chains of length B.
+        // Column i of T comes out zero when tau_i = 0, as dlarft leaves it.
+        __syncthreads () ;                               // the slab was read by the write-back above
         constexpr int LT = PANEL_MAX + 1 ;
-        double *Qm = P, *Pm = P + PANEL_MAX * LT ;      // host guarantees slab_cap >= 2*32*33
+        double *Tm = P, *Wm = P + PANEL_MAX * LT ;      // host guarantees slab_cap >= 2*32*33
         for (int e = tid ; e < PANEL_MAX * PANEL_MAX ; e += nt)
         {
             const int j = e & 31, i = e >> 5 ;
-            Qm [j + i * LT] = (j < i && i < nv) ? -taus [j] * Gs [j + i * LT] : 0.0 ;
-            Pm [j + i * LT] = (j == i) ? 1.0 : 0.0 ;
+            Tm [j + i * LT] = (j == i && i < nv) ? taus [i] : 0.0 ;
         }
         __syncthreads () ;
-        for (int span = 1 ; span < nv ; span *= 2)
+        for (int B = 1 ; B < nv ; B *= 2)
         {
-            // P <- P (I + Q), Q <- Q Q  (Q = N^span); both from the old P and Q
-            double pn [2], qn [2] ;
-#pragma unroll
-            for (int a = 0 ; a < 2 ; a++)
+            // W = (V1'V2) T22 :  W(r,c) = sum_{l = s+B .. c} G(r,l) T(l,c),   r in [s,s+B), c in [s+B,s+2B)
+            for (int e = tid ; e < 16 * B ; e += nt)
             {
-                const int e = tid + a * nt ;
-                const int j = e & 31, i = e >> 5 ;
-                double p0 = 0, p1 = 0, p2 = 0, p3 = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0 ;
-#pragma unroll
-                for (int l = 0 ; l < PANEL_MAX ; l += 4)
+                const int blk = e / (B * B), rr = (e / B) % B, cc = e % B ;
+                const int s0 = blk * 2 * B, r = s0 + rr, c = s0 + B + cc ;
+                if (c < nv)
                 {
-                    const double b0 = Qm [l + i * LT], b1 = Qm [l + 1 + i * LT], b2 = Qm [l + 2 + i * LT],
-                        b3 = Qm [l + 3 + i * LT] ;
-                    p0 = fma (Pm [j + l * LT], b0, p0) ;       p1 = fma (Pm [j + (l+1) * LT], b1, p1) ;
-                    p2 = fma (Pm [j + (l+2) * LT], b2, p2) ;   p3 = fma (Pm [j + (l+3) * LT], b3, p3) ;
-                    q0 = fma (Qm [j + l * LT], b0, q0) ;       q1 = fma (Qm [j + (l+1) * LT], b1, q1) ;
-                    q2 = fma (Qm [j + (l+2) * LT], b2, q2) ;   q3 = fma (Qm [j + (l+3) * LT], b3, q3) ;
+                    double a0 = 0, a1 = 0 ;
+                    int l = s0 + B ;
+                    for ( ; l + 1 <= c ; l += 2)
+                    {
+                        a0 = fma (Gs [r + l * LT], Tm [l + c * LT], a0) ;
+                        a1 = fma (Gs [r + (l+1) * LT], Tm [(l+1) + c * LT], a1) ;
+                    }
+                    if (l <= c) a0 = fma (Gs [r + l * LT], Tm [l + c * LT], a0) ;
+                    Wm [r + c * LT] = a0 + a1 ;
                 }
-                pn [a] = Pm [j + i * LT] + ((p0 + p1) + (p2 + p3)) ;
-                qn [a] = (q0 + q1) + (q2 + q3) ;
             }
             __syncthreads () ;
-#pragma unroll
-            for (int a = 0 ; a < 2 ; a++)
+            // T12 = -T11 W :  T(r,c) = -sum_{l = r .. s+B-1} T(r,l) W(l,c)
+            for (int e = tid ; e < 16 * B ; e += nt)
             {
-                const int e = tid + a * nt ;
-                const int j = e & 31, i = e >> 5 ;
-                Pm [j + i * LT] = pn [a] ; Qm [j + i * LT] = qn [a] ;
+                const int blk = e / (B * B), rr = (e / B) % B, cc = e % B ;
+                const int s0 = blk * 2 * B, r = s0 + rr, c = s0 + B + cc ;
+                if (c < nv)
+                {
+                    double a0 = 0, a1 = 0 ;
+                    int l = r ;
+                    for ( ; l + 1 < s0 + B ; l += 2)
+                    {
+                        a0 = fma (Tm [r + l * LT], Wm [l + c * LT], a0) ;
+                        a1 = fma (Tm [r + (l+1) * LT], Wm [(l+1) + c * LT], a1) ;
+                    }
+                    if (l < s0 + B) a0 = fma (Tm [r + l * LT], Wm [l + c * LT], a0) ;
+                    Tm [r + c * LT] = -(a0 + a1) ;
+                }
             }
             __syncthreads () ;
         }
@@ -1047,7 +1066,7 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
         for (int e = tid ; e < nv * nv ; e += nt)
         {
             const int j = e % nv, i = e / nv ;
-            Tg [j + i * PANEL_MAX] = (j <= i) ? Pm [j + i * LT] * taus [i] : 0.0 ;
+            Tg [j + i * PANEL_MAX] = (j <= i) ? Tm [j + i * LT] : 0.0 ;
         }
         for (int q = tid ; q < nv ; q += nt) N.pnl_cols [slotp * PANEL_MAX + q] = cols [q] ;
         panel_epilogue<false> (L, S, N, slot, f, k2, parity, leader, nv, g, g1, out_of_rows, flops, Gs, Gs, taus, cols, tq) ;
@@ -1074,6 +1093,10 @@ __global__ void __launch_bounds__ (NT, MINB) k_panel_cluster (LevelArgs L, DSym 
     __shared__ double rg [PANEL_MAX] ;
     __shared__ I32 cols [PANEL_MAX], tq [PANEL_MAX] ;
     constexpr int NW = NT / 32 ;
+    // records pushed by the cluster's CTAs (panel_columns_smem): behind the scratch, only allocated by the
+    // host when the launch has clusters of more than one CTA
+    double *xrec = slab + slab_cap + panel_scratch_doubles (NW) ;
+    double *xrows = xrec + 2 * PANEL_XR_CTAS * 2 * PANEL_MAX ;
     // global-mode scratch (V'V / T, taus) lives behind the slab like the shared-memory mode's
     double *Gs = slab + slab_cap + 4 * NW * PANEL_MAX + 4 * PANEL_MAX + 2 * NW ;
     double *Tsh = Gs ;
@@ -1134,7 +1157,7 @@ __global__ void __launch_bounds__ (NT, MINB) k_panel_cluster (LevelArgs L, DSym 
         __syncthreads () ;
         GridComm nogrid {} ;
         panel_columns_smem<NW, false> (cluster, nogrid, ECS, slab_cap, ldp, L, S, N, slot, f, k1, k2, parity, lrow0, nloc, g1,
-            RL, rend, xch, cols, tq) ;
+            RL, rend, xch, xrec, xrows, cols, tq) ;
     }
     else
     {
@@ -1215,7 +1238,7 @@ __global__ void __launch_bounds__ (512, 1) k_panel_grid (LevelArgs L, DSym S, DN
         gc.ctr = ctr + 128 ; gc.G = ECS ; gc.cr = cr ; gc.epoch = 0 ;
         gc.ll = N.gridll + (I64) slot * (2 * 148 * 128) ; gc.tagbase = seq * 64u ;
         panel_columns_smem<NW, true> (cluster, gc, ECS, slab_cap, ldp, L, S, N, slot, f, k1, k2, parity, lrow0, nloc, g1,
-            RL, rend, xch, cols, tq) ;
+            RL, rend, xch, nullptr, nullptr, cols, tq) ;
     }
     else if (cr == 0 && tid == 0)
     {

@@ -188,7 +188,7 @@ struct stmqr_handle_s
     bool check_hit = false ;                // STMQR_B200_CHECK: a non-finite value was already reported
     unsigned grid_seq = 0 ;                 // launch sequence number of k_panel_grid (tags of its exchange lines)
     int nsm = 148 ;                         // SMs of the device (k_panel_grid: one CTA per SM)
-    int cluster_max = 8 ;                   // largest panel cluster (8 portable; 16 non-portable, no gain measured)
+    int cluster_max = 8 ;                   // largest panel cluster (the portable size; 16 measured no gain)
     I32 cluster_rows = 160 ;                // do not split slabs below this many rows
     I32 small_cap = 4096 ;                  // shared-memory doubles up to which a front takes k_front_small (0: off)
     I32 small_cap_used = 0 ;                // the value the current plan was made with
@@ -578,7 +578,7 @@ int stmqr_b200_create (int device, stmqr_handle *out)
     if (const char *e = getenv ("STMQR_B200_PANEL128_ROWS")) h->panel128_rows = std::max (0, atoi (e)) ;
     if (const char *e = getenv ("STMQR_B200_UPDATE_RSF")) h->update_rsf_max = std::max (1, std::min (8, atoi (e))) ;
     if (const char *e = getenv ("STMQR_B200_LOOKAHEAD_ELEMS")) h->lookahead_elems = std::max (1LL, atoll (e)) ;
-    if (const char *e = getenv ("STMQR_B200_CLUSTER_MAX")) h->cluster_max = std::max (1, std::min (16, atoi (e))) ;
+    if (const char *e = getenv ("STMQR_B200_CLUSTER_MAX")) h->cluster_max = std::max (1, std::min (PANEL_XR_CTAS, atoi (e))) ;
     if (const char *e = getenv ("STMQR_B200_CLUSTER_ROWS")) h->cluster_rows = std::max (32, atoi (e)) ;
     if (const char *e = getenv ("STMQR_B200_FLAGS")) h->opt.reserved = (int32_t) strtol (e, nullptr, 0) ;
     int prio_lo = 0, prio_hi = 0 ;
@@ -596,9 +596,9 @@ int stmqr_b200_create (int device, stmqr_handle *out)
         cudaEventCreateWithFlags (&h->evW, cudaEventDisableTiming) == cudaSuccess &&
         cudaHostAlloc ((void **) &h->pin_lvl, 4 * sizeof (I32), cudaHostAllocDefault) == cudaSuccess &&
         cudaFuncSetAttribute (k_panel_cluster<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (4)) * (int) sizeof (double)) == cudaSuccess &&
+            (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (4) + PANEL_XR_DOUBLES) * (int) sizeof (double)) == cudaSuccess &&
         cudaFuncSetAttribute (k_panel_cluster<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (8)) * (int) sizeof (double)) == cudaSuccess &&
+            (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (8) + PANEL_XR_DOUBLES) * (int) sizeof (double)) == cudaSuccess &&
         cudaFuncSetAttribute (k_panel_cluster<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (16)) * (int) sizeof (double)) == cudaSuccess &&
         cudaFuncSetAttribute (k_panel_cluster<128, 6>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
@@ -1099,7 +1099,7 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
         int pthreads = (rowsPerCta >= 64) ? 256 : 128 ;
         // many short fronts: 4-warp CTAs, up to 5-6 of them per SM (tunable: STMQR_B200_PANEL128_ROWS)
         if (rowsPerCta <= h->panel128_rows && (I64) nbig >= 2 * (I64) h->nsm) pthreads = 128 ;
-        if (((h->opt.reserved >> 16) & 0xff) >= 16 && rowsPerCta >= 256) pthreads = 512 ;
+        if (((h->opt.reserved >> 16) & 0xff) >= 16 && rowsPerCta >= 256 && CS == 1) pthreads = 512 ;
         if ((h->opt.reserved >> 16) & 0xff) pthreads = std::min (pthreads, 32 * ((h->opt.reserved >> 16) & 0xff)) ;   // tuning
         // number of fronts of the level with more than k columns (sorted by # columns descending)
         auto active_at = [&] (I32 k, I32 hi) -> I32 {
@@ -1137,7 +1137,7 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
             cudaLaunchConfig_t cfg = {} ;
             cfg.gridDim = dim3 ((unsigned) active * CS, 1, 1) ;
             cfg.blockDim = dim3 (pthreads, 1, 1) ;
-            cfg.dynamicSmemBytes = (size_t) (slabCap + panel_scratch_doubles (pthreads / 32)) * sizeof (double) ;
+            cfg.dynamicSmemBytes = (size_t) (slabCap + panel_scratch_doubles (pthreads / 32) + (CS > 1 ? PANEL_XR_DOUBLES : 0)) * sizeof (double) ;
             cfg.stream = st ;
             cudaLaunchAttribute at [1] ;
             at [0].id = cudaLaunchAttributeClusterDimension ;
@@ -1412,6 +1412,7 @@ int stmqr_b200_factorize_hpinv_b (stmqr_handle h, stmqr_numeric_info *info)
         cudaMemcpy (dbg, N.dbg, sizeof (dbg), cudaMemcpyDeviceToHost) ;
         fprintf (stderr, "panel rare (rescale) path taken %llu times: ss==0 %llu, 0<ss<=1e-280 %llu, ss>=1e280 %llu, nan %llu, |alpha|<=1e-120 %llu, alpha==0 %llu, |alpha|>=1e140 %llu\n",
             dbg [63], dbg [62], dbg [61], dbg [60], dbg [59], dbg [58], dbg [57], dbg [56]) ;
+        fprintf (stderr, "panel look-ahead: %llu steps took two columns, %llu candidates fell back to one\n", dbg [54], dbg [55]) ;
         const char *nm [8] = {"dots", "bar", "reduce+xchg", "scalar", "update", "endsync", "epilogue", "looptop"} ;
         for (int b = 0 ; b < 48 ; b += 8)
         {

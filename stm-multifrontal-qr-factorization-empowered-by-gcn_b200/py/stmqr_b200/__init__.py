@@ -105,6 +105,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    path = os.environ.get("STMQR_B200_LIB", path)       # (instrumented builds of the same library, tools/)
     if not os.path.exists(path):
         raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(the B200 engine has no CPU fallback)")

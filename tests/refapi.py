@@ -482,6 +482,19 @@ def a_norm(A: sq.Csc) -> float:
 
 R_TOL = 1e-10   # relative to ||A||_F (BASELINE.json north_star)
 
+# Inputs on which the CPU reference does not reproduce ITS OWN R to 1e-10 * ||A||: recorded with
+# tools/oracle_self_noise.py (reference serial tree vs TPSM tasks vs threaded BLAS, same container):
+#   ex18 (COLAMD, rank 5666/5669, a pivot within 0.28 of tol): 3.9e-10 and 4.1e-10 between its own runs
+#   lns_3937 (COLAMD, rank 1822/3908, ||A|| = 1.4e12, a pivot within 1.1e-3 of tol): 3.7e-12 between its own
+#       runs, 1.5e-10 between the reference and the plain-C restatement (dlarfg without OpenBLAS' blocking)
+# Every other bundled matrix, including the rank-deficient cvxqp3 (2.7e-13 / 6.0e-13) and dwt_992 (3.9e-17),
+# is held to R_TOL.  The bound for the two exceptions is 10x the largest recorded difference.
+R_TOL_BY_INPUT = {"ex18": 4.2e-9, "lns_3937": 1.6e-9}
+
+
+def r_tol_for(name: str) -> float:
+    return R_TOL_BY_INPUT.get(name, R_TOL)
+
 
 def assert_numeric_parity(sym, A, got: sq.Numeric, want: sq.Numeric, what=""):
     bad = structural_equal(got, want, sym)

@@ -80,14 +80,11 @@ def test_oracle_matches_reference_live(oracle, name, order):
     got = oracle.factorize(sym, At, ttol, ntol)
     bad = R.structural_equal(got, want, sym)
     assert not bad, bad
-    # rank-deficient, badly scaled inputs amplify rounding legitimately:
-    # R is compared at the documented tolerance only for full-rank inputs with a comfortable
-    # tol margin; rank-deficient ones (noise-direction reflections) get a looser bound.
+    # R at the north_star tolerance, rank-deficient inputs included; the two inputs on which the
+    # reference does not reproduce its own R to that tolerance get the recorded bound (refapi.R_TOL_BY_INPUT)
     d = R.compare_R(sym, got, want, R.a_norm(At))
-    if got.min_tol_margin > 1e-2 and got.rank == sym.n:
-        assert d <= R.R_TOL, d
-    else:
-        assert d <= 1e-6, d
+    print(f"{name}: rank {got.rank}/{sym.n}, tol margin {got.min_tol_margin:.2e}, max |dR| / ||A|| = {d:.3e}")
+    assert d <= R.r_tol_for(name), d
     assert got.flops == ref.qr_info(QR)["flopcount"]
     ref.free_qr(QR)
     ref.free_sparse(A)
