@@ -140,8 +140,10 @@ typedef struct
     int32_t reserved ;               /* A/B switches for tests and tuning (0 = production path): bit 0 no
                                         look-ahead, bit 1 no two-level (128-column) blocking, bit 2 no
                                         k_panel_grid, bit 3 no small-front kernel (read by analyze),
-                                        bit 4 non-persistent K = 128 apply; bits 8-15 ring stages of
-                                        k_update_dmma (2/4), bits 16-23 max warps per panel CTA      */
+                                        bit 4 non-persistent K = 128 apply, bit 5 one column per panel
+                                        exchange, bit 6 no recycling of the contribution-block arena (read
+                                        by analyze); bits 8-15 ring stages of k_update_dmma (2/4),
+                                        bits 16-23 max warps per panel CTA                            */
 } stmqr_options ;
 
 int  stmqr_b200_device_count (void) ;
@@ -209,6 +211,26 @@ int  stmqr_b200_partition_fronts (const stmqr_symbolic_view *sym, int nparts, in
                                   int32_t *is_top) ;
 int  stmqr_b200_set_partition (stmqr_handle h, int nparts, int mypart, const int32_t *owner,
                                const int32_t *is_top) ;
+
+/* Host-only planner (no device needed): a handle on which stmqr_b200_analyze / stmqr_b200_set_partition
+ * only compute the plan -- etree level schedule, arena sizes, the recycled contribution-block offsets --
+ * and account for the device memory the plan would take.  Every other call fails with STMQR_ERR_NO_DEVICE /
+ * STMQR_ERR_INVALID.  Replaces the reference's stack sizing (Stack_maxstack, SparseQR_analyze.c:1061-1161)
+ * as the place where a caller learns whether a problem fits. */
+typedef struct
+{
+    int64_t nlevels ;
+    int64_t F_doubles ;              /* front arena: the widest etree level (bound sizes)                */
+    int64_t C_doubles ;              /* contribution-block arena with recycling (high-water mark)        */
+    int64_t C_doubles_unrecycled ;   /* sum of the bounds of all blocks (what it would be without)       */
+    int64_t R_doubles ;              /* packed R+H arena (symbolic bound)                                */
+    int64_t device_bytes ;           /* everything the handle allocates                                  */
+    int64_t nparts, mypart ;
+} stmqr_plan_info ;
+int  stmqr_b200_create_planner (stmqr_handle *out) ;
+/* Coff, Csize [nf] (offset and bound size of every contribution block in the arena, doubles), level [nf]
+ * (etree level of every front); any of them may be NULL. */
+int  stmqr_b200_plan_info (stmqr_handle h, stmqr_plan_info *out, int64_t *Coff, int64_t *Csize, int32_t *level) ;
 
 #define STMQR_ARRAY_HM    0   /* int32 [nf] */
 #define STMQR_ARRAY_HR    1   /* int32 [nf] */

@@ -36,6 +36,8 @@ static sparse_csc *g_tap_A = NULL ;        /* copy of the matrix given to qr_fac
 static double g_tap_tol = 0 ;
 static Long g_tap_ntol = 0 ;
 static double g_last_fac_seconds = 0 ;
+typedef void (*rh_probe_fn) (void *QRsym) ;
+static rh_probe_fn g_probe = NULL ;
 extern void openblas_set_num_threads (int) ;
 
 static double now_s (void)
@@ -55,6 +57,15 @@ qr_numeric *qr_factorize (sparse_csc **Ahandle, Long freeA, double tol, Long nto
         g_tap_A = SparseCore_copy_sparse (*Ahandle, cc) ;
         g_tap_tol = tol ;
         g_tap_ntol = ntol ;
+    }
+    if (g_backend == 2)
+    {
+        /* symbolic-only probe: hand the symbolic object to the registered callback and stop.  SparseQR then
+         * frees everything and returns NULL (used by tools/ to plan large configurations without running them). */
+        if (g_probe) g_probe ((void *) QRsym) ;
+        if (freeA) SparseCore_free_sparse (Ahandle, cc) ;
+        cc->status = SPARSE_INVALID ;
+        return NULL ;
     }
     qr_factorize_fn fn = NULL ;
     if (g_backend == 1) fn = g_dropin ;
@@ -218,9 +229,14 @@ void rh_qr_info (void *QRv, double *out /* [12] */)
     out [9] = QR->QRnum->maxfm ; out [10] = QR->QRnum->ns ; out [11] = QR->QRnum->ntasks ;
 }
 
-void rh_sym_view (void *QRv, stmqr_symbolic_view *v)
+void rh_set_probe (rh_probe_fn fn) { g_probe = fn ; }
+
+static void sym_view_of (qr_symbolic *S, stmqr_symbolic_view *v) ;
+void rh_sym_view (void *QRv, stmqr_symbolic_view *v) { sym_view_of (((SparseQR_factorization *) QRv)->QRsym, v) ; }
+void rh_symbolic_view (void *QRsymv, stmqr_symbolic_view *v) { sym_view_of ((qr_symbolic *) QRsymv, v) ; }
+
+static void sym_view_of (qr_symbolic *S, stmqr_symbolic_view *v)
 {
-    qr_symbolic *S = ((SparseQR_factorization *) QRv)->QRsym ;
     v->m = S->m ; v->n = S->n ; v->anz = S->anz ; v->nf = S->nf ; v->maxfn = S->maxfn ;
     v->rjsize = S->rjsize ; v->hisize = S->hisize ;
     v->do_rank_detection = S->do_rank_detection ; v->keepH = S->keepH ;

@@ -16,7 +16,9 @@
 #include <condition_variable>
 #include <deque>
 #include <functional>
+#include <map>
 #include <mutex>
+#include <set>
 #include <string>
 #include <thread>
 #include <vector>
@@ -152,6 +154,7 @@ constexpr int STREAM_MAX_LEVELS = 8192 ;
 struct stmqr_handle_s
 {
     int device = 0 ;
+    bool host_only = false ;                // planner handle: no device, analyze / set_partition only compute the plan
     cudaStream_t stream = nullptr ;         // main stream: set-up, assembly, panels, packing
     cudaStream_t stream2 = nullptr ;        // trailing updates (look-ahead: overlaps the next panel)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr ;
@@ -167,6 +170,7 @@ struct stmqr_handle_s
     std::vector<I32> h_Super, h_Rp, h_Hip, h_FmB ;
     LevelSet ls_all, ls_sub, ls_top ;
     std::vector<I32> h_parent, h_owner, h_istop ;   // etree parent; GPU partition (set_partition)
+    std::vector<I32> h_Child, h_Childp ;
     int nparts = 1, mypart = 0 ;
     // streamed download (stmqr_b200_factorize_streamed): the R+H blocks of a level go to the host while
     // the next levels are factorized
@@ -186,6 +190,8 @@ struct stmqr_handle_s
     double *stream_dst = nullptr ;
     I32 *pin_lvl = nullptr ;                // pinned: actual max # rows of the level being processed
     bool check_hit = false ;                // STMQR_B200_CHECK: a non-finite value was already reported
+    std::vector<cudaEvent_t> evLevelT ;     // STMQR_B200_LEVEL_TIMES=1: one timing event per etree level (real, overlapped schedule)
+    std::vector<std::string> lvlNote ;
     unsigned grid_seq = 0 ;                 // launch sequence number of k_panel_grid (tags of its exchange lines)
     int nsm = 148 ;                         // SMs of the device (k_panel_grid: one CTA per SM)
     int cluster_max = 8 ;                   // largest panel cluster (the portable size; 16 measured no gain)
@@ -200,8 +206,11 @@ struct stmqr_handle_s
     I32 grid_rows = 6100 ;                  // levels with taller fronts take k_panel_grid
     unsigned char *d_owned = nullptr ;
     double cur_tol = -1 ; I64 cur_ntol = 0 ;
-    std::vector<I64> h_Foff, h_Coff ;
+    std::vector<I64> h_Foff, h_Coff, h_Csize ;      // h_Csize: bound on the packed size of each contribution block
     I64 Fcap = 0, Ccap = 0, Rcap = 0 ;
+    I64 Ccap_all = 0 ;                              // sum of all bounds (what an arena without recycling would need)
+    I64 *d_Coff = nullptr ;                         // device copy of h_Coff (DSym.Coff)
+    I64 C_alloc = 0 ;                               // doubles currently allocated for N.C
     I32 maxLevelWidth = 0 ;
 
     std::vector<void *> allocs ;
@@ -252,6 +261,7 @@ template <typename T> int dev_alloc (stmqr_handle h, T **p, size_t count)
 {
     *p = nullptr ;
     size_t bytes = std::max<size_t> (count, 1) * sizeof (T) ;
+    if (h->host_only) { h->device_bytes += bytes ; return STMQR_OK ; }     // planner: only account for it
     cudaError_t e = cudaMalloc ((void **) p, bytes) ;
     if (e != cudaSuccess)
     {
@@ -268,7 +278,7 @@ template <typename T> int upload (stmqr_handle h, T **dst, const std::vector<T> 
 {
     int s = dev_alloc (h, dst, src.size ()) ;
     if (s != STMQR_OK) return s ;
-    if (!src.empty ())
+    if (!src.empty () && !h->host_only)
     {
         cudaError_t e = cudaMemcpyAsync (*dst, src.data (), src.size () * sizeof (T),
             cudaMemcpyHostToDevice, h->stream) ;
@@ -280,7 +290,7 @@ template <typename T> int upload (stmqr_handle h, T **dst, const std::vector<T> 
 
 void free_all (stmqr_handle h)
 {
-    for (void *p : h->allocs) cudaFree (p) ;
+    if (!h->host_only) for (void *p : h->allocs) cudaFree (p) ;
     h->allocs.clear () ;
     h->device_bytes = 0 ;
     h->analyzed = h->have_matrix = h->factorized = false ;
@@ -480,6 +490,114 @@ int partition_fronts (I64 nf, const int64_t *Childp, const int64_t *Child, const
     return STMQR_OK ;
 }
 
+// -------------------------------------------------------------------------------------------------
+// Contribution-block arena with recycling.  The reference keeps the C blocks on its stacks and pops
+// a child's block as soon as the parent is assembled (qr_kernel, SparseQR_factorize.c:907-972).
+// Here the lifetime of every block is known from the level schedule alone: block c is written by the
+// pack of level(c) and last read by the assembly of level(parent(c)), which precedes the pack of that
+// level on the engine's stream.  So the offsets are planned once on the host by replaying the level
+// sequence through a best-fit free list (sizes are the symbolic bounds: deterministic, no device-side
+// allocator, no synchronisation), and the arena is as large as the high-water mark of that replay
+// instead of the sum over all fronts (lap3d 96^3: 50 GB of bounds).
+// -------------------------------------------------------------------------------------------------
+class ArenaReplay
+{
+public:
+    I64 high = 0 ;
+    I64 alloc (I64 size)
+    {
+        size = (size + 1) & ~(I64) 1 ;                      // 16-byte granules
+        if (size <= 0) return 0 ;
+        auto it = by_size.lower_bound (std::make_pair (size, (I64) -1)) ;      // best fit, lowest offset among equals
+        if (it == by_size.end ())
+        {
+            // grow at the top (merging with a free block that touches the top)
+            I64 off = high ;
+            if (!by_off.empty ())
+            {
+                auto last = std::prev (by_off.end ()) ;
+                if (last->first + last->second == high)
+                {
+                    off = last->first ;
+                    by_size.erase (std::make_pair (last->second, last->first)) ;
+                    by_off.erase (last) ;
+                }
+            }
+            high = off + size ;
+            return off ;
+        }
+        const I64 bsz = it->first, off = it->second ;
+        by_size.erase (it) ;
+        by_off.erase (off) ;
+        if (bsz > size) insert (off + size, bsz - size) ;
+        return off ;
+    }
+    void release (I64 off, I64 size)
+    {
+        size = (size + 1) & ~(I64) 1 ;
+        if (size <= 0) return ;
+        auto nx = by_off.lower_bound (off) ;
+        if (nx != by_off.end () && off + size == nx->first)
+        {
+            size += nx->second ;
+            by_size.erase (std::make_pair (nx->second, nx->first)) ;
+            nx = by_off.erase (nx) ;
+        }
+        if (nx != by_off.begin ())
+        {
+            auto pv = std::prev (nx) ;
+            if (pv->first + pv->second == off)
+            {
+                off = pv->first ; size += pv->second ;
+                by_size.erase (std::make_pair (pv->second, pv->first)) ;
+                by_off.erase (pv) ;
+            }
+        }
+        insert (off, size) ;
+    }
+private:
+    void insert (I64 off, I64 size) { by_off [off] = size ; by_size.insert (std::make_pair (size, off)) ; }
+    std::map<I64, I64> by_off ;
+    std::set<std::pair<I64, I64>> by_size ;
+} ;
+
+// Replays `phases` (level sets in processing order) and assigns Coff.  `received`: fronts whose block
+// arrives from another GPU before phase `recv_before` starts (cut children of the top of the tree).
+void plan_contribution_arena (const std::vector<const LevelSet *> &phases, size_t recv_before,
+    const std::vector<I32> &received, const std::vector<I32> &Childp, const std::vector<I32> &Child,
+    const std::vector<I64> &Csize, std::vector<I64> &Coff, I64 &cap)
+{
+    ArenaReplay A ;
+    std::vector<unsigned char> live (Coff.size (), 0) ;
+    std::fill (Coff.begin (), Coff.end (), (I64) 0) ;
+    for (size_t ph = 0 ; ph < phases.size () ; ph++)
+    {
+        if (ph == recv_before)
+            for (I32 c : received) if (Csize [c] > 0 && !live [c]) { Coff [c] = A.alloc (Csize [c]) ; live [c] = 1 ; }
+        const LevelSet &LS = *phases [ph] ;
+        for (const Level &Lv : LS.levels)
+        {
+            // assembly of the level: the children's blocks are consumed ...
+            for (I32 i = 0 ; i < Lv.count ; i++)
+            {
+                const I32 f = LS.fronts [Lv.first + i] ;
+                for (I32 q = Childp [f] ; q < Childp [f+1] ; q++)
+                {
+                    const I32 c = Child [q] ;
+                    if (live [c]) { A.release (Coff [c], Csize [c]) ; live [c] = 0 ; }
+                }
+            }
+            // ... then the level's own blocks are packed
+            for (I32 i = 0 ; i < Lv.count ; i++)
+            {
+                const I32 f = LS.fronts [Lv.first + i] ;
+                if (Csize [f] > 0 && !live [f]) { Coff [f] = A.alloc (Csize [f]) ; live [f] = 1 ; }
+            }
+        }
+    }
+    cap = A.high + 2 ;
+}
+
 constexpr I32 SMALL_CLASS_ELEMS [2] = {2048, 1024} ;     // boundaries between the shared-memory classes
 
 // shared-memory doubles of a front in k_front_small, or 0 if the front is not eligible
@@ -635,6 +753,7 @@ int stmqr_b200_create (int device, stmqr_handle *out)
 void stmqr_b200_destroy (stmqr_handle h)
 {
     if (!h) return ;
+    if (h->host_only) { delete h ; return ; }
     cudaSetDevice (h->device) ;
     free_all (h) ;
     if (h->ev0) cudaEventDestroy (h->ev0) ;
@@ -688,7 +807,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
 {
     if (!h || !sym) return STMQR_ERR_INVALID ;
     auto t0 = std::chrono::steady_clock::now () ;
-    cudaSetDevice (h->device) ;
+    if (!h->host_only) cudaSetDevice (h->device) ;
     free_all (h) ;
     h->err.clear () ;
     const I64 m = sym->m, n = sym->n, nf = sym->nf, anz = sym->anz, rjsize = sym->rjsize,
@@ -753,7 +872,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
             }
         }
     }
-    h->h_Foff.assign ((size_t) nf, 0) ; h->h_Coff.assign ((size_t) nf, 0) ;
+    h->h_Foff.assign ((size_t) nf, 0) ; h->h_Coff.assign ((size_t) nf, 0) ; h->h_Csize.assign ((size_t) nf, 0) ;
     // ---- contribution-block arena (bound sizes) and R+H arena bound ------------------------------
     // csize bound: qr_analyze's Cm[f] rows by cn columns (SparseQR_analyze.c:536-550).
     // R+H bound per front: sum_j min (max (j+1, Stair_j), fm) with the bound staircase (:559-573).
@@ -766,7 +885,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
             const I64 fp = Super [f+1] - Super [f], fn = Rp [f+1] - Rp [f] ;
             const I64 cn = fn - fp, cm = std::min<I64> (CmB [f], cn) ;
             const I64 csize = (cm * (cm + 1)) / 2 + cm * (cn - cm) ;
-            h->h_Coff [f] = coff ;
+            h->h_Csize [f] = csize ;
             coff += (csize + 1) & ~(I64) 1 ;
             // staircase bound
             for (I64 j = 0 ; j < fn ; j++) Fmap [Rj [Rp [f] + j]] = (I32) j ;
@@ -790,7 +909,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
             if (fm > FmB [f]) FmB [f] = (I32) fm ;     // never trust a smaller bound
             rcap += rh ;
         }
-        h->Ccap = coff ;
+        h->Ccap_all = coff ;
         h->Rcap = rcap + 16 ;
     }
 
@@ -858,14 +977,27 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     UPLOAD (p, Cj) ; S.Cj = p ;         UPLOAD (p, Sjf) ; S.Sjf = p ;
     I64 *p64 ;
     UPLOAD (p64, h->h_Foff) ; S.Foff = p64 ;
-    UPLOAD (p64, h->h_Coff) ; S.Coff = p64 ;
+    h->h_Child = Child ; h->h_Childp = Childp ;
+    {
+        // contribution-block offsets: replay of the level schedule (one GPU: every level of the tree)
+        std::vector<const LevelSet *> phases {&h->ls_all} ;
+        plan_contribution_arena (phases, phases.size (), std::vector<I32> (), Childp, Child, h->h_Csize, h->h_Coff, h->Ccap) ;
+        if (h->opt.reserved & 64)
+        {
+            // A/B switch: no recycling, every block has its own place (round-1 layout)
+            I64 coff = 0 ;
+            for (I64 f = 0 ; f < nf ; f++) { h->h_Coff [f] = coff ; coff += (h->h_Csize [f] + 1) & ~(I64) 1 ; }
+            h->Ccap = coff + 2 ;
+        }
+    }
+    UPLOAD (p64, h->h_Coff) ; S.Coff = p64 ; h->d_Coff = p64 ;
     UPLOAD (h->ls_all.d_fronts, h->ls_all.fronts) ;
     h->d_owned = nullptr ; h->N.owned = nullptr ;
 
     DNum &N = h->N ;
     ALLOC (N.Sx, anz) ;
     ALLOC (N.F, h->Fcap) ;
-    ALLOC (N.C, h->Ccap) ;
+    ALLOC (N.C, h->Ccap) ; h->C_alloc = h->Ccap ;
     ALLOC (N.R, h->Rcap) ;
     ALLOC (N.HTau, rjsize) ;
     // per-slot panel outputs: 2 parities (look-ahead), 4 on the levels that take the two-level path
@@ -896,11 +1028,14 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
         ALLOC (N.gridrec, gslots * 2 * 148 * 64) ;
         ALLOC (N.gridred, gslots * 2 * 148) ;
         ALLOC (N.gridll, gslots * 2 * 148 * 128) ;
-        CK (cudaMemsetAsync (N.gridll, 0, gslots * 2 * 148 * 128 * sizeof (int4), h->stream)) ;
         ALLOC (N.gridctr, gslots * GRID_CTR_STRIDE) ;
         ALLOC (N.griderr, 1) ;
-        CK (cudaMemsetAsync (N.gridctr, 0, gslots * GRID_CTR_STRIDE * sizeof (unsigned), h->stream)) ;
-        CK (cudaMemsetAsync (N.griderr, 0, sizeof (I32), h->stream)) ;
+        if (!h->host_only)
+        {
+            CK (cudaMemsetAsync (N.gridll, 0, gslots * 2 * 148 * 128 * sizeof (int4), h->stream)) ;
+            CK (cudaMemsetAsync (N.gridctr, 0, gslots * GRID_CTR_STRIDE * sizeof (unsigned), h->stream)) ;
+            CK (cudaMemsetAsync (N.griderr, 0, sizeof (I32), h->stream)) ;
+        }
     }
     ALLOC (N.stair, rjsize) ;
     ALLOC (N.Cmap, rjsize) ;
@@ -935,7 +1070,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
         ALLOC (h->d_capA, h->h_capOff [nf]) ;
         ALLOC (h->d_capF, h->h_capOff [nf]) ;
     }
-    CK (cudaStreamSynchronize (h->stream)) ;
+    if (!h->host_only) CK (cudaStreamSynchronize (h->stream)) ;
     h->analyzed = true ;
     memset (&h->stats, 0, sizeof (h->stats)) ;
     h->stats.ms_plan = std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now () - t0).count () ;
@@ -949,6 +1084,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
 int stmqr_b200_upload_matrix (stmqr_handle h, const stmqr_csc_view *A)
 {
     if (!h || !A || !h->analyzed) return fail (h, STMQR_ERR_INVALID, "upload_matrix: analyze first") ;
+    if (h->host_only) return fail (h, STMQR_ERR_NO_DEVICE, "upload_matrix: planner handle (no device)") ;
     cudaSetDevice (h->device) ;
     if (A->nrow != h->m || A->ncol != h->n || !A->p || (A->p [A->ncol] > 0 && (!A->i || !A->x)))
         return fail (h, STMQR_ERR_INVALID, "upload_matrix: matrix does not match the analysis") ;
@@ -982,7 +1118,7 @@ int stmqr_b200_upload_matrix (stmqr_handle h, const stmqr_csc_view *A)
 // host interleaves the exchange of the cut contribution blocks and the merges, see py/stmqr_b200/dist.py)
 int stmqr_b200_factorize_begin (stmqr_handle h, double tol, int64_t ntol)
 {
-    if (!h || !h->analyzed || !h->have_matrix)
+    if (!h || !h->analyzed || !h->have_matrix || h->host_only)
         return fail (h, STMQR_ERR_INVALID, "factorize: analyze and upload_matrix first") ;
     cudaSetDevice (h->device) ;
     cudaStream_t st = h->stream ;
@@ -1031,6 +1167,16 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
     const int nc_update = (h->opt.reserved >> 8) & 0xff ;   // 0 auto, 2 or 4: ring stages of the update kernel
     const int PB = (h->opt.panel > 0 && h->opt.panel <= PANEL_MAX) ? h->opt.panel : PANEL_MAX ;
     long long levelno = -1 ;
+    static const bool level_times = getenv ("STMQR_B200_LEVEL_TIMES") != nullptr ;
+    auto mark_level = [&] (const std::string &note) {
+        if (!level_times) return ;
+        cudaEvent_t e ;
+        cudaEventCreate (&e) ;
+        cudaEventRecord (e, st) ;
+        h->evLevelT.push_back (e) ; h->lvlNote.push_back (note) ;
+    } ;
+    if (level_times && part != 2) { for (cudaEvent_t e : h->evLevelT) cudaEventDestroy (e) ; h->evLevelT.clear () ; h->lvlNote.clear () ; }
+    mark_level ("start") ;
     for (const Level &Lv : LS.levels)
     {
         levelno++ ;
@@ -1346,6 +1492,8 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
         }
         LAUNCH (5, k_level_alloc<<<1, 1024, 0, st>>> (fr, Lv.count, N)) ;
         LAUNCH (6, k_pack<<<dim3 (Lv.count, nsl), 256, 0, st>>> (fr, S, N)) ;
+        mark_level ("level " + std::to_string (levelno) + ": " + std::to_string (Lv.count) + " fronts (" + std::to_string (nbig) +
+            " tiled), max " + std::to_string (Lv.maxFm) + " x " + std::to_string (Lv.maxfn) + (Lv.wide ? " wide" : "")) ;
         if (h->streaming && h->stream_levels >= (int) h->evLvl.size ()) h->stream_overflow = true ;
         if (h->streaming && !h->stream_overflow)
         {
@@ -1424,6 +1572,16 @@ int stmqr_b200_factorize_hpinv_b (stmqr_handle h, stmqr_numeric_info *info)
     }
 #endif
     if ((I64) rcur > h->Rcap) return fail (h, STMQR_ERR_INVALID, "factorize: R+H arena bound exceeded") ;
+    if (h->evLevelT.size () > 1)
+    {
+        for (size_t i = 1 ; i < h->evLevelT.size () ; i++)
+        {
+            float t = 0 ;
+            if (h->lvlNote [i] == "start") continue ;
+            cudaEventElapsedTime (&t, h->evLevelT [i-1], h->evLevelT [i]) ;
+            fprintf (stderr, "STMQR_B200_LEVEL_TIMES %8.3f ms  %s\n", t, h->lvlNote [i].c_str ()) ;
+        }
+    }
     float ms = 0 ;
     cudaEventElapsedTime (&ms, h->ev0, h->ev1) ;
     h->stats.ms_numeric = ms ;
@@ -1607,7 +1765,7 @@ int stmqr_b200_set_partition (stmqr_handle h, int nparts, int mypart, const int3
 {
     if (!h || !h->analyzed || nparts < 1 || mypart < 0 || mypart >= nparts || !owner || !is_top)
         return fail (h, STMQR_ERR_INVALID, "set_partition: analyze first; 0 <= mypart < nparts") ;
-    cudaSetDevice (h->device) ;
+    if (!h->host_only) cudaSetDevice (h->device) ;
     const I64 nf = h->nf ;
     h->nparts = nparts ; h->mypart = mypart ;
     h->h_owner.assign (owner, owner + nf) ; h->h_istop.assign (is_top, is_top + nf) ;
@@ -1628,7 +1786,83 @@ int stmqr_b200_set_partition (stmqr_handle h, int nparts, int mypart, const int3
     UPLOAD (h->ls_top.d_fronts, h->ls_top.fronts) ;
     if (nparts > 1) { UPLOAD (h->d_owned, owned) ; h->N.owned = h->d_owned ; }
     else { h->d_owned = nullptr ; h->N.owned = nullptr ; }
-    CK (cudaStreamSynchronize (h->stream)) ;
+    if (!(h->opt.reserved & 64))
+    {
+        // contribution-block offsets for THIS GPU's schedule: its subtrees level by level, then (part 0) the
+        // blocks of the cut children owned by other GPUs arrive, then the top of the tree level by level
+        std::vector<I32> received ;
+        if (mypart == 0)
+            for (I64 f = 0 ; f < nf ; f++)
+                if (is_top [f])
+                    for (I32 q = h->h_Childp [f] ; q < h->h_Childp [f+1] ; q++)
+                    {
+                        const I32 c = h->h_Child [q] ;
+                        if (!is_top [c] && owner [c] != 0) received.push_back (c) ;
+                    }
+        std::vector<const LevelSet *> phases {&h->ls_sub, &h->ls_top} ;
+        I64 cap = 0 ;
+        if (nparts == 1) { phases.assign (1, &h->ls_all) ; }
+        plan_contribution_arena (phases, (nparts == 1) ? phases.size () : 1, received, h->h_Childp, h->h_Child,
+            h->h_Csize, h->h_Coff, cap) ;
+        h->Ccap = cap ;
+        if (h->host_only)
+        {
+            h->device_bytes += (size_t) std::max<I64> (0, cap - h->C_alloc) * sizeof (double) ;
+            h->C_alloc = std::max (h->C_alloc, cap) ;
+        }
+        else if (cap > h->C_alloc)
+        {
+            // (another schedule can have a higher high-water mark than the one-GPU schedule)
+            for (auto &pp : h->allocs) if (pp == (void *) h->N.C) { cudaFree (pp) ; pp = nullptr ; }
+            h->device_bytes -= (size_t) h->C_alloc * sizeof (double) ;
+            h->N.C = nullptr ;
+            double *nc = nullptr ;
+            if (cudaMalloc ((void **) &nc, (size_t) cap * sizeof (double)) != cudaSuccess)
+                return fail (h, STMQR_ERR_OUT_OF_MEMORY, "set_partition: contribution-block arena") ;
+            for (auto &pp : h->allocs) if (pp == nullptr) { pp = (void *) nc ; break ; }
+            h->N.C = nc ; h->C_alloc = cap ;
+            h->device_bytes += (size_t) cap * sizeof (double) ;
+        }
+        if (!h->host_only) CK (cudaMemcpyAsync (h->d_Coff, h->h_Coff.data (), (size_t) nf * sizeof (I64), cudaMemcpyHostToDevice, h->stream)) ;
+    }
+    if (!h->host_only) CK (cudaStreamSynchronize (h->stream)) ;
+    return STMQR_OK ;
+}
+
+// ---- host-only planner: the plan (level schedule, arenas, partition) without a device ------------------
+int stmqr_b200_create_planner (stmqr_handle *out)
+{
+    if (!out) return STMQR_ERR_INVALID ;
+    stmqr_handle h = new stmqr_handle_s ;
+    h->host_only = true ;
+    if (const char *e = getenv ("STMQR_B200_GRID_ROWS")) h->grid_rows = std::max (256, atoi (e)) ;
+    if (const char *e = getenv ("STMQR_B200_WIDE_ROWS")) h->wide_rows = std::max (256, atoi (e)) ;
+    if (const char *e = getenv ("STMQR_B200_SMALL_ELEMS")) h->small_cap = std::max (0, std::min (5600, atoi (e))) ;
+    *out = h ;
+    return STMQR_OK ;
+}
+
+int stmqr_b200_plan_info (stmqr_handle h, stmqr_plan_info *out, int64_t *Coff, int64_t *Csize, int32_t *level)
+{
+    if (!h || !h->analyzed || !out) return STMQR_ERR_INVALID ;
+    out->nlevels = (int64_t) h->ls_all.levels.size () ;
+    out->F_doubles = h->Fcap ; out->C_doubles = h->Ccap ; out->C_doubles_unrecycled = h->Ccap_all ;
+    out->R_doubles = h->Rcap ; out->device_bytes = (int64_t) h->device_bytes ;
+    out->nparts = h->nparts ; out->mypart = h->mypart ;
+    for (I64 f = 0 ; f < h->nf ; f++)
+    {
+        if (Coff) Coff [f] = h->h_Coff [f] ;
+        if (Csize) Csize [f] = h->h_Csize [f] ;
+    }
+    if (level)
+    {
+        I32 l = 0 ;
+        for (const Level &Lv : h->ls_all.levels)
+        {
+            for (I32 i = 0 ; i < Lv.count ; i++) level [h->ls_all.fronts [Lv.first + i]] = l ;
+            l++ ;
+        }
+    }
     return STMQR_OK ;
 }
 

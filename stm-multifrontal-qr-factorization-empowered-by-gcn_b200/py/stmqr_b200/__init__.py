@@ -84,6 +84,11 @@ class FrontRegions(C.Structure):
                 ("cm", C.c_int64), ("hr", C.c_int64), ("hm", C.c_int64)]
 
 
+class PlanInfo(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in ("nlevels", "F_doubles", "C_doubles", "C_doubles_unrecycled", "R_doubles",
+                                         "device_bytes", "nparts", "mypart")]
+
+
 ARRAY_HM, ARRAY_HR, ARRAY_CM, ARRAY_RDEAD, ARRAY_W = range(5)
 
 EXPORTS = (
@@ -95,6 +100,7 @@ EXPORTS = (
     "stmqr_b200_factorize_hpinv_b", "stmqr_b200_sync", "stmqr_b200_partition_fronts",
     "stmqr_b200_set_partition", "stmqr_b200_device_array", "stmqr_b200_front_regions",
     "stmqr_b200_rh_bound", "stmqr_b200_factorize_streamed", "stmqr_b200_stream_begin", "stmqr_b200_stream_end",
+    "stmqr_b200_create_planner", "stmqr_b200_plan_info",
 )
 
 _lib = None
@@ -145,6 +151,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.stmqr_b200_rh_bound.argtypes = [C.c_void_p, _i64p]
     lib.stmqr_b200_factorize_streamed.argtypes = [C.c_void_p, C.POINTER(CscView), C.c_double, C.c_int64, _f64p,
                                                   C.c_int64, C.POINTER(NumericInfo)]
+    lib.stmqr_b200_create_planner.argtypes = [C.POINTER(C.c_void_p)]
+    lib.stmqr_b200_plan_info.argtypes = [C.c_void_p, C.POINTER(PlanInfo), _i64p, _i64p, C.POINTER(C.c_int32)]
     _lib = lib
     return lib
 
@@ -407,6 +415,17 @@ class Engine:
                                                   C.byref(fm), C.byref(fn)), "get_front")
         return buf[: fm.value * fn.value].reshape((fn.value, fm.value)).T  # column-major -> (fm, fn)
 
+    def plan_info(self):
+        """-> (PlanInfo, Coff[nf], Csize[nf], level[nf]): arena sizes of the current plan, offset / bound size of
+        every contribution block in the recycled arena, etree level of every front"""
+        nf = max(self.sym.nf, 1)
+        info = PlanInfo()
+        coff, csize, level = np.zeros(nf, np.int64), np.zeros(nf, np.int64), np.zeros(nf, np.int32)
+        self._check(self.lib.stmqr_b200_plan_info(self.h, C.byref(info), coff.ctypes.data_as(_i64p),
+                                                  csize.ctypes.data_as(_i64p),
+                                                  level.ctypes.data_as(C.POINTER(C.c_int32))), "plan_info")
+        return info, coff[: self.sym.nf], csize[: self.sym.nf], level[: self.sym.nf]
+
     def close(self):
         if self.h:
             self.lib.stmqr_b200_destroy(self.h)
@@ -417,3 +436,16 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+
+class Planner(Engine):
+    """Host-only handle (no GPU needed): analyze / set_partition compute the plan -- level schedule, arena sizes,
+    recycled contribution-block offsets -- and account for the device memory it would take."""
+
+    def __init__(self):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        st = self.lib.stmqr_b200_create_planner(C.byref(self.h))
+        if st != STMQR_OK:
+            raise EngineError(f"stmqr_b200_create_planner failed: {ERRORS.get(st, st)}")
+        self.sym = None

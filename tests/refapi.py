@@ -240,6 +240,35 @@ class Reference:
         return float(self.L.rh_default_tol(self.cc, A))
 
     # ---- factorization through the reference's SparseQR()
+    def analyze_only(self, A, ordering_arg: int, tol: float) -> sq.Symbolic:
+        """the reference's symbolic phase alone (ordering + qr_analyze): SparseQR() is stopped at its
+        qr_factorize call, which hands us the symbolic object.  No numeric work at all."""
+        got = []
+        view_fn = self.L.rh_symbolic_view
+        view_fn.argtypes = [C.c_void_p, C.POINTER(sq.SymbolicView)]
+
+        @C.CFUNCTYPE(None, C.c_void_p)
+        def probe(symp):
+            v = sq.SymbolicView()
+            view_fn(symp, C.byref(v))
+            got.append(sq.Symbolic.from_view(v))
+
+        self.L.rh_set_probe.argtypes = [C.c_void_p]
+        self.L.rh_set_probe(C.cast(probe, C.c_void_p))
+        assert self.L.rh_set_backend(2, None) == 0
+        try:
+            self.L.rh_set_blas_threads(1)
+            self.L.rh_clear_status(self.cc)
+            QR = self.L.rh_sparseqr(self.cc, A, ordering_arg, tol, 1.0, 0)
+            assert not QR
+        finally:
+            self.L.rh_set_backend(0, None)
+            self.L.rh_set_probe(None)
+            self.L.rh_clear_status(self.cc)
+        if not got:
+            raise RuntimeError("analyze_only: qr_factorize was never reached")
+        return got[-1]
+
     def set_backend(self, backend: str):
         if backend == "reference":
             assert self.L.rh_set_backend(0, None) == 0

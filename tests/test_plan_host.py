@@ -1,0 +1,94 @@
+"""Host logic of the plan (no GPU): the recycled contribution-block arena.  A block lives from the pack of its
+front's etree level to the assembly of its parent's level; the offsets planned by stmqr_b200_analyze /
+stmqr_b200_set_partition must never let two blocks that are alive at the same time overlap, on one GPU and for
+every part of a partitioned tree (the reference pops a child's block off its stack after the parent's assembly,
+SparseQR_factorize.c:907-972)."""
+import numpy as np
+import pytest
+
+import refapi as R
+import stmqr_b200 as sq
+
+
+def parents(sym):
+    par = np.full(sym.nf, -1, np.int64)
+    for f in range(sym.nf):
+        for q in range(int(sym.Childp[f]), int(sym.Childp[f + 1])):
+            par[int(sym.Child[q])] = f
+    return par
+
+
+def check_no_overlap(sym, coff, csize, level, alive):
+    """alive: fronts whose block is held on this GPU.  Intervals [level(c), level(parent)] in schedule time."""
+    par = parents(sym)
+    ev = []
+    for c in np.nonzero(alive)[0]:
+        if csize[c] <= 0:
+            continue
+        birth = int(level[c])
+        death = int(level[par[c]]) if par[c] >= 0 else 10 ** 9
+        ev.append((int(coff[c]), int(coff[c] + csize[c]), birth, death, int(c)))
+    ev.sort()
+    # sweep over address order: compare each block with the following blocks that start before it ends
+    for i, (a0, a1, b, d, c) in enumerate(ev):
+        j = i + 1
+        while j < len(ev) and ev[j][0] < a1:
+            _, _, b2, d2, c2 = ev[j]
+            # the parent's assembly (death) precedes the pack of the same level (birth of that level's blocks)
+            assert d <= b2 or d2 <= b, f"blocks of fronts {c} and {c2} overlap while both are alive"
+            j += 1
+
+
+@pytest.mark.parametrize("case", ["dwt_992_metis", "lap2d_24_metis", "lap3d_8_metis", "tall_600x150_colamd"])
+def test_recycled_arena_single_gpu(case):
+    sym, A, tol, ntol, _ = R.load_golden(case)
+    p = sq.Planner()
+    p.analyze(sym)
+    info, coff, csize, level = p.plan_info()
+    assert info.C_doubles <= info.C_doubles_unrecycled + 2
+    assert (coff + csize <= info.C_doubles).all()
+    check_no_overlap(sym, coff, csize, level, np.ones(sym.nf, bool))
+    # every child is on a lower level than its parent
+    par = parents(sym)
+    assert all(level[c] < level[par[c]] for c in range(sym.nf) if par[c] >= 0)
+    assert info.device_bytes > 0
+    p.close()
+
+
+@pytest.mark.parametrize("case,nparts", [("lap2d_24_metis", 2), ("lap3d_8_metis", 4), ("dwt_992_metis", 3)])
+def test_recycled_arena_partitioned(case, nparts):
+    sym, A, tol, ntol, _ = R.load_golden(case)
+    owner, is_top = sq.partition_fronts(sym, nparts)
+    par = parents(sym)
+    for part in range(nparts):
+        p = sq.Planner()
+        p.analyze(sym)
+        p.set_partition(nparts, part, owner, is_top)
+        info, coff, csize, level = p.plan_info()
+        assert info.nparts == nparts and info.mypart == part
+        # schedule time on this GPU: its subtrees by level, then (part 0) the top of the tree by level
+        nlev = int(level.max()) + 1 if sym.nf else 1
+        when = np.where(is_top.astype(bool), nlev + 1 + level, level)
+        mine = owner == part
+        # blocks received from other GPUs (cut children of the top) are placed when the top phase starts
+        recv = np.zeros(sym.nf, bool)
+        if part == 0:
+            for c in range(sym.nf):
+                if par[c] >= 0 and is_top[par[c]] and not is_top[c] and owner[c] != 0:
+                    recv[c] = True
+        when = np.where(recv, nlev, when)
+        alive = mine | recv
+        assert (coff[alive] + csize[alive] <= info.C_doubles).all()
+        check_no_overlap(sym, coff, csize, when, alive)
+        p.close()
+
+
+def test_planner_has_no_compute_path():
+    sym, A, tol, ntol, _ = R.load_golden("lap2d_16_notol")
+    p = sq.Planner()
+    p.analyze(sym)
+    with pytest.raises(sq.EngineError):
+        p.upload_matrix(A)
+    with pytest.raises(sq.EngineError):
+        p.factorize_resident(tol, ntol)
+    p.close()
