@@ -160,6 +160,18 @@ int  stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym) ;
  * (replaces qr_stranspose2, SparseQR_factorize.c:755-785). */
 int  stmqr_b200_upload_matrix (stmqr_handle h, const stmqr_csc_view *A) ;
 
+/* Values-only refactorization: new values on the pattern given to the last
+ * stmqr_b200_upload_matrix.  The first factorization of a pattern leaves the map "entry p of A -> slot of S"
+ * on the device (the search of qr_stranspose2, SparseQR_factorize.c:755-785, is purely symbolic), so only
+ * 8 bytes per entry cross the bus and S is built by one scatter.  The caller vouches that Ap/Ai are
+ * unchanged.  stmqr_b200_factorize / _factorize_streamed do the same on their own whenever the handle holds
+ * a pattern of the same shape: values first, and the caller's Ap/Ai are uploaded beside the numeric phase and
+ * compared with the resident pattern on the device (a mismatch repeats the call through the full path;
+ * STMQR_B200_SPECULATIVE=0 turns this off). */
+int  stmqr_b200_upload_values (stmqr_handle h, const double *Ax, int64_t nnz) ;
+int  stmqr_b200_refactorize_values (stmqr_handle h, const double *Ax, int64_t nnz, double tol, int64_t ntol,
+                                    stmqr_numeric_info *info) ;
+
 /* Numeric factorization of the resident matrix: per etree level, front set-up (qr_fsize
  * :1066), assembly (qr_assemble :1151), front QR (qr_front :1383, qr_larftb :1851) and
  * packing (qr_cpack :1639, qr_rhpack :1691), then the row permutation (qr_hpinv :991).
@@ -252,6 +264,24 @@ typedef struct
 } stmqr_front_regions ;
 int  stmqr_b200_front_regions (stmqr_handle h, int64_t f, int64_t cm, int64_t hr, int64_t hm,
                                stmqr_front_regions *out) ;
+
+/* ---- the consumers next to the path, on the resident factorization -----------------
+ * Q-apply and R-solve that read the packed R+H blocks where the factorization left them in HBM, so a
+ * least-squares solve does not download the factor at all.  They replace, for factorizations without
+ * column singletons (the multifrontal part), the reference's
+ *     QR_qmult (QR_QTX / QR_QX)           STMMQR/src/qr/SparseQR.c:1838-2110 (qr_private_Happly :1706,
+ *                                          qr_private_get_H_vectors :1455, row permutation HPinv)
+ *     qr_rsolve                           STMMQR/src/qr/SparseQR.c:2218-2465 (QR_solve systems
+ *                                          QR_RX_EQUALS_B: use_Qfill = 0, QR_RETX_EQUALS_B: use_Qfill = 1)
+ * All matrices are host arrays, column major: X, Y m-by-nx (ld = m); B m-by-nrhs (ld = m, rows >= rank
+ * are ignored); the solution n-by-nrhs (ld = n).  Dead columns get the basic solution x_j = 0.
+ * The etree is walked level by level (all fronts of a level in one launch). */
+int  stmqr_b200_qmult (stmqr_handle h, int method /* 0: Y = Q'X, 1: Y = QX */, int64_t nx,
+                       const double *X, double *Y) ;
+int  stmqr_b200_rsolve (stmqr_handle h, int use_Qfill, int64_t nrhs, const double *B, double *X) ;
+/* x = E * (R \ (Q'b)): min ||Ax - b|| as qrtest.c:11-53 does it with QR_qmult + QR_solve; device_ms
+ * (optional) receives the device time including the two host<->device copies of b and x. */
+int  stmqr_b200_solve_ls (stmqr_handle h, int64_t nrhs, const double *B, double *X, double *device_ms) ;
 
 int  stmqr_b200_get_stats (stmqr_handle h, stmqr_stats *out) ;
 

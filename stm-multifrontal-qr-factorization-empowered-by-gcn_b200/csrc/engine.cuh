@@ -25,6 +25,7 @@ struct DSym
     const I32 *Hip ;        // [nf+1]
     const I32 *PLinv ;      // [m]
     const I32 *Qinv ;       // [n]   column j of A is column Qinv[j] of S
+    const I32 *Qfill ;      // [n]   column k of S is column Qfill[k] of A (identity if the analysis has none)
     const I32 *Cj ;         // [rjsize] for entry p of Rj at local position >= fp of front c:
                             //          index of that column inside the PARENT front (Fmap of
                             //          qr_fsize/qr_assemble, precomputed: it is purely symbolic)

@@ -11,10 +11,15 @@ namespace stmqr {
 // serial scatter through a running row cursor.  Here one thread per entry of A finds its slot by
 // binary search of the permuted column inside the (ascending) row of S: no atomics, deterministic.
 // Duplicate entries of A (legal in a sparse_csc) land in consecutive slots in storage order, exactly
-// as the reference's cursor places them (the later one then wins in qr_assemble, :1199-1203).
+// as the reference's cursor places them (the later one then wins in qr_assemble, :1199-1203).  (Through
+// SparseQR() the case cannot arise: the reference's own analysis refuses a matrix with duplicate entries
+// with SPARSE_INVALID -- measured with oracle/_ref, "HNUCHOL error: all methods failed",
+// SparseChol_analyze.c:640 -- so this only matters to callers of the C ABI with their own symbolic object.)
 // ---------------------------------------------------------------------------------------------
+// slot [p] (optional): the slot of S that entry p of A goes to -- the whole search is symbolic, so a
+// refactorization with new values on the same pattern is a plain scatter (k_scatter_values).
 __global__ void k_build_S (I32 n, const I64 *__restrict__ Ap, const I64 *__restrict__ Ai,
-    const double *__restrict__ Ax, DSym S, double *__restrict__ Sx, I32 *err)
+    const double *__restrict__ Ax, DSym S, double *__restrict__ Sx, I32 *__restrict__ slot, I32 *err)
 {
     // one warp per column of A keeps the reads of Ai/Ax coalesced
     const int lane = threadIdx.x & 31 ;
@@ -45,13 +50,43 @@ __global__ void k_build_S (I32 n, const I64 *__restrict__ Ap, const I64 *__restr
                     I32 d = 0 ;
                     for (I64 q = p1 ; q < p ; q++) d += (Ai [q] == ai) ;
                     lo += d ;
-                    if (!(lo < S.Sp [row+1] && S.Sj [lo] == col)) { atomicExch (err, 1) ; continue ; }
+                    if (!(lo < S.Sp [row+1] && S.Sj [lo] == col)) { atomicExch (err, 1) ; if (slot) slot [p] = -1 ; continue ; }
                 }
                 Sx [lo] = Ax [p] ;
+                if (slot) slot [p] = lo ;
             }
-            else atomicExch (err, 1) ;
+            else { atomicExch (err, 1) ; if (slot) slot [p] = -1 ; }
         }
     }
+}
+
+// Values-only refactorization (same pattern, new values): Sx [slot [p]] = Ax [p].  Coalesced reads of Ax
+// and slot, 8-byte scattered writes (every slot of S is written exactly once when A has no duplicates;
+// with duplicates the later entry wins, as in the reference, because slots of duplicates are distinct).
+__global__ void k_scatter_values (I64 nnz, const double *__restrict__ Ax, const I32 *__restrict__ slot,
+    double *__restrict__ Sx)
+{
+    I64 p = (I64) blockIdx.x * blockDim.x + threadIdx.x ;
+    const I64 stride = (I64) gridDim.x * blockDim.x ;
+    for ( ; p < nnz ; p += stride)
+    {
+        const I32 sl = slot [p] ;
+        if (sl >= 0) Sx [sl] = Ax [p] ;
+    }
+}
+
+// The pattern of the matrix handed to a speculative values-only refactorization, compared on the device
+// with the resident pattern while the numeric phase runs: *differs != 0 if any column pointer or row
+// index changed (the host then repeats the factorization through the full path).
+__global__ void k_compare_pattern (I64 ncol1, I64 nnz, const I64 *__restrict__ Ap, const I64 *__restrict__ Ai,
+    const I64 *__restrict__ Bp, const I64 *__restrict__ Bi, I32 *differs)
+{
+    I64 p = (I64) blockIdx.x * blockDim.x + threadIdx.x ;
+    const I64 stride = (I64) gridDim.x * blockDim.x ;
+    bool bad = false ;
+    for (I64 q = p ; q < ncol1 ; q += stride) bad |= (Ap [q] != Bp [q]) ;
+    for (I64 q = p ; q < nnz ; q += stride) bad |= (Ai [q] != Bi [q]) ;
+    if (bad) atomicExch (differs, 1) ;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -29,6 +29,7 @@
 #include "kernels_update.cuh"
 #include "kernels_wide.cuh"
 #include "kernels_small.cuh"
+#include "kernels_solve.cuh"
 #include "kernels_peak.cuh"
 
 using namespace stmqr ;
@@ -228,11 +229,29 @@ struct stmqr_handle_s
     I64 *d_Ap = nullptr, *d_Ai = nullptr ;
     double *d_Ax = nullptr ;
     I64 a_ncol = 0, a_nnz_cap = 0 ;
+    // values-only refactorization: entry p of A -> slot of S (filled by k_build_S), valid for the resident
+    // pattern d_Ap/d_Ai; scratch for the pattern of a speculative call and its verdict
+    I32 *d_slot = nullptr ;
+    bool slot_valid = false ;               // d_slot matches d_Ap/d_Ai
+    bool values_only = false ;              // the next factorize_begin scatters d_Ax through d_slot
+    I64 *d_vAp = nullptr, *d_vAi = nullptr ;
+    I32 *d_vdiff = nullptr ;
+    cudaStream_t streamV = nullptr ;        // uploads + compares the caller's pattern beside the numeric phase
+    bool verify_pending = false, pattern_mismatch = false ;
+    int speculative = 1 ;                   // STMQR_B200_SPECULATIVE=0: always upload the pattern first
+    I64 n_values_only = 0, n_pattern_mismatch = 0 ;
     // int64 staging for the download
     I64 *d_HPinv64 = nullptr, *d_Hii64 = nullptr, *d_wide = nullptr ;
     // debug capture
     double *d_capA = nullptr, *d_capF = nullptr ;
     std::vector<I64> h_capOff ;
+
+    // device Q-apply / R-solve on the resident factorization (kernels_solve.cuh)
+    I32 *d_hcol = nullptr, *d_nh = nullptr ;        // Householder table, rebuilt after every factorization
+    bool htable_valid = false ;
+    double *d_solveZ = nullptr, *d_solveX = nullptr, *d_solveW = nullptr, *d_solveIO = nullptr ;
+    I64 solveZ_cap = 0, solveX_cap = 0, solveIO_cap = 0 ;
+    double ms_solve = 0 ;
 
     stmqr_numeric_info info {} ;
     stmqr_stats stats {} ;
@@ -295,6 +314,11 @@ void free_all (stmqr_handle h)
     h->device_bytes = 0 ;
     h->analyzed = h->have_matrix = h->factorized = false ;
     h->d_Ap = h->d_Ai = nullptr ; h->d_Ax = nullptr ; h->a_ncol = h->a_nnz_cap = 0 ;
+    h->d_slot = nullptr ; h->d_vAp = h->d_vAi = nullptr ; h->d_vdiff = nullptr ;
+    h->slot_valid = h->values_only = false ;
+    h->d_hcol = h->d_nh = nullptr ; h->htable_valid = false ;
+    h->d_solveZ = h->d_solveX = h->d_solveW = h->d_solveIO = nullptr ;
+    h->solveZ_cap = h->solveX_cap = h->solveIO_cap = 0 ;
 }
 
 bool narrow (const int64_t *src, I64 count, std::vector<I32> &dst)
@@ -663,6 +687,46 @@ void filter_levels (const LevelSet &all, const std::vector<unsigned char> &keep,
     }
 }
 
+// ---- speculative values-only refactorization ---------------------------------------------------------
+// A caller of the reference API (qr_factorize, SparseQR.c:349,371) hands over the whole matrix every time,
+// although in a refactorization loop only the values change.  When the handle still holds a pattern of the
+// same shape (and the A -> S slot map the first factorization left behind), only the values are uploaded
+// before the numeric phase starts; the caller's Ap/Ai travel on a second stream WHILE the fronts are being
+// factorized and are compared with the resident pattern on the device.  A mismatch (new pattern with the
+// same counts) costs one repeated factorization through the full path; a match saves 16 of the 24 bytes
+// per entry of host-to-device traffic on the critical path.
+bool can_speculate (stmqr_handle h, const stmqr_csc_view *A)
+{
+    return h->speculative && h->analyzed && h->slot_valid && h->d_Ax && A && A->p && A->ncol == h->a_ncol &&
+        A->nrow == h->m && A->p [A->ncol] == h->anz && h->anz > 0 ;
+}
+
+int issue_pattern_check (stmqr_handle h, const stmqr_csc_view *A)
+{
+    if (!h->streamV) CK (cudaStreamCreateWithFlags (&h->streamV, cudaStreamNonBlocking)) ;
+    CK (cudaMemsetAsync (h->d_vdiff, 0, sizeof (I32), h->streamV)) ;
+    CK (cudaMemcpyAsync (h->d_vAp, A->p, (size_t) (A->ncol + 1) * sizeof (I64), cudaMemcpyHostToDevice, h->streamV)) ;
+    CK (cudaMemcpyAsync (h->d_vAi, A->i, (size_t) h->anz * sizeof (I64), cudaMemcpyHostToDevice, h->streamV)) ;
+    k_compare_pattern<<<grid_for (h->anz, 256), 256, 0, h->streamV>>> (A->ncol + 1, h->anz, h->d_Ap, h->d_Ai,
+        h->d_vAp, h->d_vAi, h->d_vdiff) ;
+    h->verify_pending = true ;
+    return STMQR_OK ;
+}
+
+// waits for the comparison; -> pattern_mismatch
+int finish_pattern_check (stmqr_handle h)
+{
+    h->pattern_mismatch = false ;
+    if (!h->verify_pending) return STMQR_OK ;
+    h->verify_pending = false ;
+    I32 diff = 1 ;
+    CK (cudaMemcpyAsync (&diff, h->d_vdiff, sizeof (I32), cudaMemcpyDeviceToHost, h->streamV)) ;
+    CK (cudaStreamSynchronize (h->streamV)) ;
+    h->pattern_mismatch = (diff != 0) ;
+    if (h->pattern_mismatch) { h->n_pattern_mismatch++ ; h->slot_valid = false ; }
+    return STMQR_OK ;
+}
+
 } // namespace
 
 // =================================================================================================
@@ -699,6 +763,7 @@ int stmqr_b200_create (int device, stmqr_handle *out)
     if (const char *e = getenv ("STMQR_B200_CLUSTER_MAX")) h->cluster_max = std::max (1, std::min (PANEL_XR_CTAS, atoi (e))) ;
     if (const char *e = getenv ("STMQR_B200_CLUSTER_ROWS")) h->cluster_rows = std::max (32, atoi (e)) ;
     if (const char *e = getenv ("STMQR_B200_FLAGS")) h->opt.reserved = (int32_t) strtol (e, nullptr, 0) ;
+    if (const char *e = getenv ("STMQR_B200_SPECULATIVE")) h->speculative = atoi (e) ;
     int prio_lo = 0, prio_hi = 0 ;
     bool ok = cudaSetDevice (device) == cudaSuccess &&
         cudaDeviceGetStreamPriorityRange (&prio_lo, &prio_hi) == cudaSuccess &&
@@ -777,6 +842,7 @@ void stmqr_b200_destroy (stmqr_handle h)
         if (h->evPin [i]) cudaEventDestroy (h->evPin [i]) ;
     }
     if (h->streamCopy) cudaStreamDestroy (h->streamCopy) ;
+    if (h->streamV) cudaStreamDestroy (h->streamV) ;
     if (h->stream2) cudaStreamDestroy (h->stream2) ;
     if (h->stream) cudaStreamDestroy (h->stream) ;
     delete h ;
@@ -835,12 +901,13 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
         narrow (sym->Hip, nf+1, Hip) && narrow (sym->PLinv, m, PLinv) &&
         narrow (sym->Fm, nf, FmB) && narrow (sym->Cm, nf, CmB) ;
     if (!ok) return fail (h, STMQR_ERR_TOO_LARGE, "analyze: symbolic value exceeds int32") ;
-    std::vector<I32> Qinv ((size_t) n) ;
+    std::vector<I32> Qinv ((size_t) n), Qfill32 ((size_t) n) ;
     for (I64 k = 0 ; k < n ; k++)
     {
         I64 j = sym->Qfill ? sym->Qfill [k] : k ;
         if (j < 0 || j >= n) return fail (h, STMQR_ERR_INVALID, "analyze: Qfill is not a permutation") ;
         Qinv [(size_t) j] = (I32) k ;
+        Qfill32 [(size_t) k] = (I32) j ;
     }
 
     // ---- parent of each front, etree levels (all fronts of a level are independent) --------------
@@ -973,7 +1040,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     UPLOAD (p, Super) ; S.Super = p ;   UPLOAD (p, Rp) ; S.Rp = p ;       UPLOAD (p, Rj) ; S.Rj = p ;
     UPLOAD (p, Sleft) ; S.Sleft = p ;   UPLOAD (p, Sp) ; S.Sp = p ;       UPLOAD (p, Sj) ; S.Sj = p ;
     UPLOAD (p, Child) ; S.Child = p ;   UPLOAD (p, Childp) ; S.Childp = p ; UPLOAD (p, Hip) ; S.Hip = p ;
-    UPLOAD (p, PLinv) ; S.PLinv = p ;   UPLOAD (p, Qinv) ; S.Qinv = p ;
+    UPLOAD (p, PLinv) ; S.PLinv = p ;   UPLOAD (p, Qinv) ; S.Qinv = p ;     UPLOAD (p, Qfill32) ; S.Qfill = p ;
     UPLOAD (p, Cj) ; S.Cj = p ;         UPLOAD (p, Sjf) ; S.Sjf = p ;
     I64 *p64 ;
     UPLOAD (p64, h->h_Foff) ; S.Foff = p64 ;
@@ -1059,6 +1126,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     ALLOC (N.lvlstat, 4) ;
     ALLOC (N.base1, nf) ; ALLOC (N.base2, nf) ;
     ALLOC (h->d_err, 1) ;
+    ALLOC (h->d_hcol, rjsize) ; ALLOC (h->d_nh, nf) ;
     ALLOC (h->d_HPinv64, m) ;
     ALLOC (h->d_Hii64, hisize) ;
     ALLOC (h->d_wide, rjsize + 2 * nf + 2) ;
@@ -1095,8 +1163,13 @@ int stmqr_b200_upload_matrix (stmqr_handle h, const stmqr_csc_view *A)
         ALLOC (h->d_Ap, A->ncol + 1) ;
         ALLOC (h->d_Ai, nnz) ;
         ALLOC (h->d_Ax, nnz) ;
+        ALLOC (h->d_slot, nnz) ;
+        ALLOC (h->d_vAp, A->ncol + 1) ;
+        ALLOC (h->d_vAi, nnz) ;
+        ALLOC (h->d_vdiff, 1) ;
         h->a_ncol = A->ncol ; h->a_nnz_cap = nnz ;
     }
+    h->slot_valid = false ; h->values_only = false ;        // a new pattern: k_build_S refills the slot map
     CK (cudaEventRecord (h->ev0, h->stream)) ;
     CK (cudaMemcpyAsync (h->d_Ap, A->p, (A->ncol + 1) * sizeof (I64), cudaMemcpyHostToDevice, h->stream)) ;
     if (nnz > 0)
@@ -1110,6 +1183,28 @@ int stmqr_b200_upload_matrix (stmqr_handle h, const stmqr_csc_view *A)
     cudaEventElapsedTime (&ms, h->ev0, h->ev1) ;
     h->stats.ms_h2d = ms ;
     h->have_matrix = true ;
+    return STMQR_OK ;
+}
+
+// New values on the RESIDENT pattern (the matrix last given to upload_matrix, whose A -> S slot map the
+// first factorization left on the device): 8 bytes per entry go to the device instead of 24, and S is built
+// by a scatter instead of a search.  The caller vouches that Ap/Ai are unchanged.
+int stmqr_b200_upload_values (stmqr_handle h, const double *Ax, int64_t nnz)
+{
+    if (!h || !h->analyzed || h->host_only) return fail (h, STMQR_ERR_INVALID, "upload_values: analyze first") ;
+    if (!h->d_Ax || !h->slot_valid || nnz != h->anz || (nnz > 0 && !Ax))
+        return fail (h, STMQR_ERR_INVALID, "upload_values: no resident pattern with this many entries (upload_matrix + one factorization first)") ;
+    cudaSetDevice (h->device) ;
+    CK (cudaEventRecord (h->ev0, h->stream)) ;
+    if (nnz > 0) CK (cudaMemcpyAsync (h->d_Ax, Ax, nnz * sizeof (double), cudaMemcpyHostToDevice, h->stream)) ;
+    CK (cudaEventRecord (h->ev1, h->stream)) ;
+    CK (cudaStreamSynchronize (h->stream)) ;
+    float ms = 0 ;
+    cudaEventElapsedTime (&ms, h->ev0, h->ev1) ;
+    h->stats.ms_h2d = ms ;
+    h->have_matrix = true ;
+    h->values_only = true ;
+    h->n_values_only++ ;
     return STMQR_OK ;
 }
 
@@ -1127,6 +1222,7 @@ int stmqr_b200_factorize_begin (stmqr_handle h, double tol, int64_t ntol)
     h->cur_tol = tol ; h->cur_ntol = ntol ;
     h->launches = 0 ;
     h->factorized = false ;
+    h->htable_valid = false ;
     CK (cudaEventRecord (h->ev0, st)) ;
     CK (cudaMemsetAsync (N.Rdead, 0, std::max<I64> (h->n, 1), st)) ;
     CK (cudaMemsetAsync (N.rcursor, 0, sizeof (unsigned long long), st)) ;
@@ -1149,7 +1245,15 @@ int stmqr_b200_factorize_begin (stmqr_handle h, double tol, int64_t ntol)
     }
     if (h->anz > 0)
     {
-        LAUNCH (0, k_build_S<<<grid_for (h->n * 32, 256), 256, 0, st>>> ((I32) h->n, h->d_Ap, h->d_Ai, h->d_Ax, S, N.Sx, h->d_err)) ;
+        if (h->values_only && h->slot_valid)
+        {
+            LAUNCH (0, k_scatter_values<<<grid_for (h->anz, 256), 256, 0, st>>> (h->anz, h->d_Ax, h->d_slot, N.Sx)) ;
+        }
+        else
+        {
+            LAUNCH (0, k_build_S<<<grid_for (h->n * 32, 256), 256, 0, st>>> ((I32) h->n, h->d_Ap, h->d_Ai, h->d_Ax, S, N.Sx, h->d_slot, h->d_err)) ;
+            h->slot_valid = true ;          // (an entry outside the pattern raises d_err: the factorization fails, and
+        }                                   //  upload_matrix resets the flag before the next pattern)
     }
     return STMQR_OK ;
 }
@@ -1428,6 +1532,7 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
         else
         {
             I32 active = active_at (0, nbig) ;
+            bool rest_pending [2] = {false, false} ;        // a rest-of-the-trailing-matrix update in flight on stream2
             if (active > 0) { LAUNCH (3, CK (launch_panel (active, 0, 0))) ; }
             for (I32 j = 0 ; active > 0 ; j++)
             {
@@ -1439,14 +1544,21 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
                 const I32 par = j & 1 ;
                 if (lookahead)
                 {
-                    // update the next panel's columns first, then let the next panel (main stream,
-                    // high priority) overlap the rest of this trailing update (second stream)
-                    CK (cudaEventRecord (h->evP [par], st)) ;
-                    CK (cudaStreamWaitEvent (st2, h->evP [par], 0)) ;
-                    launch_update (st2, active2, k2, std::min<I32> (k2 + PB, Lv.maxfn), par) ; h->launches++ ;
-                    CK (cudaEventRecord (h->evN [par], st2)) ;
-                    if (k2 + PB < Lv.maxfn) { launch_update (st2, active2, k2 + PB, Lv.maxfn, par) ; h->launches++ ; }
-                    CK (cudaStreamWaitEvent (st, h->evN [par], 0)) ;
+                    // The critical chain panel j -> update of the next panel's 32 columns -> panel j+1 stays on
+                    // the main stream (no event hop between streams on it); the rest of the trailing update
+                    // runs on the second stream beside panel j+1.  The rest update of step j also writes the
+                    // columns of the narrow update of step j+1 and reads the panel buffers of parity j & 1 that
+                    // panel j+2 overwrites: the main stream waits for it before the next narrow update.
+                    if (k2 + PB < Lv.maxfn)
+                    {
+                        CK (cudaEventRecord (h->evP [par], st)) ;
+                        CK (cudaStreamWaitEvent (st2, h->evP [par], 0)) ;
+                        launch_update (st2, active2, k2 + PB, Lv.maxfn, par) ; h->launches++ ;
+                        CK (cudaEventRecord (h->evN [par], st2)) ;
+                        rest_pending [par] = true ;
+                    }
+                    if (rest_pending [par ^ 1]) { CK (cudaStreamWaitEvent (st, h->evN [par ^ 1], 0)) ; rest_pending [par ^ 1] = false ; }
+                    launch_update (st, active2, k2, std::min<I32> (k2 + PB, Lv.maxfn), par) ; h->launches++ ;
                 }
                 else
                 {
@@ -1459,6 +1571,7 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
             {
                 CK (cudaEventRecord (h->evW, st2)) ;
                 CK (cudaStreamWaitEvent (st, h->evW, 0)) ;
+                (void) rest_pending ;
             }
         }
         if (h->debug_capture)
@@ -1645,7 +1758,30 @@ int stmqr_b200_sync (stmqr_handle h)
 int stmqr_b200_factorize (stmqr_handle h, const stmqr_csc_view *A, double tol, int64_t ntol,
     stmqr_numeric_info *info)
 {
-    int s = stmqr_b200_upload_matrix (h, A) ;
+    if (!h) return STMQR_ERR_INVALID ;
+    int s ;
+    if (can_speculate (h, A))
+    {
+        // values first, the pattern beside the numeric phase (see issue_pattern_check)
+        if ((s = stmqr_b200_upload_values (h, A->x, h->anz)) != STMQR_OK) return s ;
+        if ((s = stmqr_b200_factorize_begin (h, tol, ntol)) != STMQR_OK) return s ;
+        if ((s = stmqr_b200_factorize_levels (h, 0)) != STMQR_OK) return s ;
+        if ((s = stmqr_b200_factorize_hpinv_a (h)) != STMQR_OK) return s ;
+        if ((s = issue_pattern_check (h, A)) != STMQR_OK) return s ;
+        s = stmqr_b200_factorize_hpinv_b (h, info) ;
+        const int sv = finish_pattern_check (h) ;
+        if (sv != STMQR_OK) return sv ;
+        if (!h->pattern_mismatch) return s ;
+    }
+    s = stmqr_b200_upload_matrix (h, A) ;
+    if (s != STMQR_OK) return s ;
+    return stmqr_b200_factorize_resident (h, tol, ntol, info) ;
+}
+
+int stmqr_b200_refactorize_values (stmqr_handle h, const double *Ax, int64_t nnz, double tol, int64_t ntol,
+    stmqr_numeric_info *info)
+{
+    int s = stmqr_b200_upload_values (h, Ax, nnz) ;
     if (s != STMQR_OK) return s ;
     return stmqr_b200_factorize_resident (h, tol, ntol, info) ;
 }
@@ -1709,7 +1845,23 @@ int stmqr_b200_factorize_streamed (stmqr_handle h, const stmqr_csc_view *A, doub
     double *stack, int64_t capacity, stmqr_numeric_info *info)
 {
     if (!h || !stack || capacity < 1) return fail (h, STMQR_ERR_INVALID, "factorize_streamed: no destination") ;
-    int s = stmqr_b200_upload_matrix (h, A) ;
+    int s ;
+    if (can_speculate (h, A))
+    {
+        if ((s = stmqr_b200_upload_values (h, A->x, h->anz)) != STMQR_OK) return s ;
+        if ((s = stmqr_b200_stream_begin (h, stack, capacity)) != STMQR_OK) return s ;
+        if ((s = stmqr_b200_factorize_begin (h, tol, ntol)) == STMQR_OK &&
+            (s = stmqr_b200_factorize_levels (h, 0)) == STMQR_OK &&
+            (s = stmqr_b200_factorize_hpinv_a (h)) == STMQR_OK &&
+            (s = issue_pattern_check (h, A)) == STMQR_OK)
+            s = stmqr_b200_factorize_hpinv_b (h, info) ;
+        const int sv = finish_pattern_check (h) ;
+        const int s2 = stmqr_b200_stream_end (h) ;
+        if (sv != STMQR_OK) return sv ;
+        if (!h->pattern_mismatch) return (s != STMQR_OK) ? s : s2 ;
+        // the pattern changed: everything streamed so far belongs to the wrong matrix; start over
+    }
+    s = stmqr_b200_upload_matrix (h, A) ;
     if (s != STMQR_OK) return s ;
     if ((s = stmqr_b200_stream_begin (h, stack, capacity)) != STMQR_OK) return s ;
     if ((s = stmqr_b200_factorize_begin (h, tol, ntol)) == STMQR_OK &&
@@ -1912,6 +2064,170 @@ int stmqr_b200_front_regions (stmqr_handle h, int64_t f, int64_t cm, int64_t hr,
     out->C_doubles = (c * (c + 1)) / 2 + c * (cn - c) ;
     out->Hii = N.Hii + h->h_Hip [f] + v [1] ;
     out->Hii_ints = c ;
+    return STMQR_OK ;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Q-apply and R-solve on the resident factorization (kernels_solve.cuh)
+// -------------------------------------------------------------------------------------------------
+namespace {
+
+int solve_ready (stmqr_handle h, const char *what)
+{
+    if (!h || !h->factorized || h->host_only) return fail (h, STMQR_ERR_INVALID, std::string (what) + ": factorize first") ;
+    if (h->nparts > 1) return fail (h, STMQR_ERR_INVALID, std::string (what) + ": needs the whole factorization on one GPU") ;
+    cudaSetDevice (h->device) ;
+    if (!h->htable_valid)
+    {
+        if (h->nf > 0) k_htable<<<grid_for (h->nf * 32, 256, 1 << 22), 256, 0, h->stream>>> (h->S, h->N, h->d_hcol, h->d_nh) ;
+        CK (cudaGetLastError ()) ;
+        h->htable_valid = true ;
+    }
+    return STMQR_OK ;
+}
+
+// grows a device scratch array (outside the plan's allocation list: it survives until destroy / re-analyze)
+int grow (stmqr_handle h, double **p, I64 *cap, I64 need)
+{
+    if (need <= *cap) return STMQR_OK ;
+    if (*p) { for (auto &q : h->allocs) if (q == (void *) *p) q = nullptr ; cudaFree (*p) ; h->device_bytes -= (size_t) *cap * sizeof (double) ; *p = nullptr ; *cap = 0 ; }
+    ALLOC (*p, need) ;
+    *cap = need ;
+    return STMQR_OK ;
+}
+
+// Z <- Q'Z or QZ, Z m-by-nx on the device in the factorization's row order
+int device_qapply (stmqr_handle h, int method, I64 nx, double *Z)
+{
+    const LevelSet &LS = h->ls_all ;
+    const I64 nl = (I64) LS.levels.size () ;
+    for (I64 li = 0 ; li < nl ; li++)
+    {
+        const Level &Lv = LS.levels [(size_t) ((method == 0) ? li : (nl - 1 - li))] ;
+        const I32 *fr = LS.d_fronts + Lv.first ;
+        const I32 nsm = Lv.count - Lv.nbig ;
+        for (I64 c0 = 0 ; c0 < nx ; )
+        {
+            const bool four = (nx - c0 >= 4) ;
+            if (Lv.nbig > 0)
+            {
+                if (four) k_qapply<256, 4><<<Lv.nbig, 256, 0, h->stream>>> (fr, Lv.nbig, h->S, h->N, h->d_Hii64, h->d_hcol, h->d_nh, method, (I32) c0, Z) ;
+                else k_qapply<256, 1><<<Lv.nbig, 256, 0, h->stream>>> (fr, Lv.nbig, h->S, h->N, h->d_Hii64, h->d_hcol, h->d_nh, method, (I32) c0, Z) ;
+            }
+            if (nsm > 0)
+            {
+                const int g = (nsm + 7) / 8 ;
+                if (four) k_qapply<32, 4><<<g, 256, 0, h->stream>>> (fr + Lv.nbig, nsm, h->S, h->N, h->d_Hii64, h->d_hcol, h->d_nh, method, (I32) c0, Z) ;
+                else k_qapply<32, 1><<<g, 256, 0, h->stream>>> (fr + Lv.nbig, nsm, h->S, h->N, h->d_Hii64, h->d_hcol, h->d_nh, method, (I32) c0, Z) ;
+            }
+            c0 += four ? 4 : 1 ;
+        }
+    }
+    CK (cudaGetLastError ()) ;
+    return STMQR_OK ;
+}
+
+// X <- R \ B or E (R \ B); B m-by-nrhs (device), X n-by-nrhs (device, overwritten), W n-by-nrhs scratch
+int device_rsolve (stmqr_handle h, int use_Qfill, I64 nrhs, const double *B, double *X, double *W)
+{
+    CK (cudaMemsetAsync (X, 0, (size_t) std::max<I64> (h->n * nrhs, 1) * sizeof (double), h->stream)) ;
+    const LevelSet &LS = h->ls_all ;
+    const I32 *Qf = use_Qfill ? h->S.Qfill : nullptr ;
+    for (I64 li = (I64) LS.levels.size () - 1 ; li >= 0 ; li--)
+    {
+        const Level &Lv = LS.levels [(size_t) li] ;
+        const I32 *fr = LS.d_fronts + Lv.first ;
+        const I32 nsm = Lv.count - Lv.nbig ;
+        for (I64 c0 = 0 ; c0 < nrhs ; )
+        {
+            const bool four = (nrhs - c0 >= 4) ;
+            if (Lv.nbig > 0)
+            {
+                if (four) k_rsolve<256, 4><<<Lv.nbig, 256, 0, h->stream>>> (fr, Lv.nbig, h->S, h->N, h->d_hcol, Qf, h->info.rank, (I32) c0, B, X, W) ;
+                else k_rsolve<256, 1><<<Lv.nbig, 256, 0, h->stream>>> (fr, Lv.nbig, h->S, h->N, h->d_hcol, Qf, h->info.rank, (I32) c0, B, X, W) ;
+            }
+            if (nsm > 0)
+            {
+                const int g = (nsm + 7) / 8 ;
+                if (four) k_rsolve<32, 4><<<g, 256, 0, h->stream>>> (fr + Lv.nbig, nsm, h->S, h->N, h->d_hcol, Qf, h->info.rank, (I32) c0, B, X, W) ;
+                else k_rsolve<32, 1><<<g, 256, 0, h->stream>>> (fr + Lv.nbig, nsm, h->S, h->N, h->d_hcol, Qf, h->info.rank, (I32) c0, B, X, W) ;
+            }
+            c0 += four ? 4 : 1 ;
+        }
+    }
+    CK (cudaGetLastError ()) ;
+    return STMQR_OK ;
+}
+
+} // namespace
+
+int stmqr_b200_qmult (stmqr_handle h, int method, int64_t nx, const double *X, double *Y)
+{
+    int s = solve_ready (h, "qmult") ;
+    if (s != STMQR_OK) return s ;
+    if ((method != 0 && method != 1) || nx < 0 || (nx > 0 && (!X || !Y))) return fail (h, STMQR_ERR_INVALID, "qmult: bad arguments") ;
+    if (nx == 0 || h->m == 0) return STMQR_OK ;
+    const I64 cnt = h->m * nx ;
+    if ((s = grow (h, &h->d_solveZ, &h->solveZ_cap, cnt)) != STMQR_OK) return s ;
+    if ((s = grow (h, &h->d_solveIO, &h->solveIO_cap, std::max (cnt, h->n * nx))) != STMQR_OK) return s ;
+    cudaStream_t st = h->stream ;
+    CK (cudaEventRecord (h->ev2, st)) ;
+    CK (cudaMemcpyAsync (h->d_solveIO, X, (size_t) cnt * sizeof (double), cudaMemcpyHostToDevice, st)) ;
+    // Q'X works on Z (HPinv [i], :) = X (i, :), QX on X itself and permutes at the end (:2004-2048)
+    if (method == 0) k_permute_rows<<<grid_for (cnt, 256), 256, 0, st>>> (h->m, nx, h->d_HPinv64, h->d_solveIO, h->d_solveZ, 1) ;
+    else CK (cudaMemcpyAsync (h->d_solveZ, h->d_solveIO, (size_t) cnt * sizeof (double), cudaMemcpyDeviceToDevice, st)) ;
+    if ((s = device_qapply (h, method, nx, h->d_solveZ)) != STMQR_OK) return s ;
+    const double *res = h->d_solveZ ;
+    if (method == 1) { k_permute_rows<<<grid_for (cnt, 256), 256, 0, st>>> (h->m, nx, h->d_HPinv64, h->d_solveZ, h->d_solveIO, 0) ; res = h->d_solveIO ; }
+    CK (cudaMemcpyAsync (Y, res, (size_t) cnt * sizeof (double), cudaMemcpyDeviceToHost, st)) ;
+    CK (cudaEventRecord (h->ev3, st)) ;
+    CK (cudaStreamSynchronize (st)) ;
+    float ms = 0 ; cudaEventElapsedTime (&ms, h->ev2, h->ev3) ; h->ms_solve = ms ;
+    return STMQR_OK ;
+}
+
+int stmqr_b200_rsolve (stmqr_handle h, int use_Qfill, int64_t nrhs, const double *B, double *X)
+{
+    int s = solve_ready (h, "rsolve") ;
+    if (s != STMQR_OK) return s ;
+    if (nrhs < 0 || (nrhs > 0 && (!B || !X))) return fail (h, STMQR_ERR_INVALID, "rsolve: bad arguments") ;
+    if (nrhs == 0 || h->n == 0) return STMQR_OK ;
+    if ((s = grow (h, &h->d_solveIO, &h->solveIO_cap, std::max (h->m, h->n) * nrhs)) != STMQR_OK) return s ;
+    if ((s = grow (h, &h->d_solveX, &h->solveX_cap, 2 * h->n * nrhs)) != STMQR_OK) return s ;
+    cudaStream_t st = h->stream ;
+    CK (cudaEventRecord (h->ev2, st)) ;
+    CK (cudaMemcpyAsync (h->d_solveIO, B, (size_t) (h->m * nrhs) * sizeof (double), cudaMemcpyHostToDevice, st)) ;
+    if ((s = device_rsolve (h, use_Qfill, nrhs, h->d_solveIO, h->d_solveX, h->d_solveX + h->n * nrhs)) != STMQR_OK) return s ;
+    CK (cudaMemcpyAsync (X, h->d_solveX, (size_t) (h->n * nrhs) * sizeof (double), cudaMemcpyDeviceToHost, st)) ;
+    CK (cudaEventRecord (h->ev3, st)) ;
+    CK (cudaStreamSynchronize (st)) ;
+    float ms = 0 ; cudaEventElapsedTime (&ms, h->ev2, h->ev3) ; h->ms_solve = ms ;
+    return STMQR_OK ;
+}
+
+// x = E * (R \ (Q'b)): the least-squares solve of qrtest.c:11-53 (QR_qmult (QR_QTX) + QR_solve
+// (QR_RETX_EQUALS_B)) without the factor ever leaving the device
+int stmqr_b200_solve_ls (stmqr_handle h, int64_t nrhs, const double *B, double *X, double *device_ms)
+{
+    int s = solve_ready (h, "solve_ls") ;
+    if (s != STMQR_OK) return s ;
+    if (nrhs < 0 || (nrhs > 0 && (!B || !X))) return fail (h, STMQR_ERR_INVALID, "solve_ls: bad arguments") ;
+    if (nrhs == 0 || h->n == 0 || h->m == 0) return STMQR_OK ;
+    const I64 cnt = h->m * nrhs ;
+    if ((s = grow (h, &h->d_solveZ, &h->solveZ_cap, cnt)) != STMQR_OK) return s ;
+    if ((s = grow (h, &h->d_solveIO, &h->solveIO_cap, std::max (h->m, h->n) * nrhs)) != STMQR_OK) return s ;
+    if ((s = grow (h, &h->d_solveX, &h->solveX_cap, 2 * h->n * nrhs)) != STMQR_OK) return s ;
+    cudaStream_t st = h->stream ;
+    CK (cudaEventRecord (h->ev2, st)) ;
+    CK (cudaMemcpyAsync (h->d_solveIO, B, (size_t) cnt * sizeof (double), cudaMemcpyHostToDevice, st)) ;
+    k_permute_rows<<<grid_for (cnt, 256), 256, 0, st>>> (h->m, nrhs, h->d_HPinv64, h->d_solveIO, h->d_solveZ, 1) ;
+    if ((s = device_qapply (h, 0, nrhs, h->d_solveZ)) != STMQR_OK) return s ;
+    if ((s = device_rsolve (h, 1, nrhs, h->d_solveZ, h->d_solveX, h->d_solveX + h->n * nrhs)) != STMQR_OK) return s ;
+    CK (cudaMemcpyAsync (X, h->d_solveX, (size_t) (h->n * nrhs) * sizeof (double), cudaMemcpyDeviceToHost, st)) ;
+    CK (cudaEventRecord (h->ev3, st)) ;
+    CK (cudaStreamSynchronize (st)) ;
+    float ms = 0 ; cudaEventElapsedTime (&ms, h->ev2, h->ev3) ; h->ms_solve = ms ;
+    if (device_ms) *device_ms = ms ;
     return STMQR_OK ;
 }
 

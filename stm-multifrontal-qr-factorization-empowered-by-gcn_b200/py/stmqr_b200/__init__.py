@@ -101,6 +101,8 @@ EXPORTS = (
     "stmqr_b200_set_partition", "stmqr_b200_device_array", "stmqr_b200_front_regions",
     "stmqr_b200_rh_bound", "stmqr_b200_factorize_streamed", "stmqr_b200_stream_begin", "stmqr_b200_stream_end",
     "stmqr_b200_create_planner", "stmqr_b200_plan_info",
+    "stmqr_b200_upload_values", "stmqr_b200_refactorize_values",
+    "stmqr_b200_qmult", "stmqr_b200_rsolve", "stmqr_b200_solve_ls",
 )
 
 _lib = None
@@ -151,6 +153,12 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.stmqr_b200_rh_bound.argtypes = [C.c_void_p, _i64p]
     lib.stmqr_b200_factorize_streamed.argtypes = [C.c_void_p, C.POINTER(CscView), C.c_double, C.c_int64, _f64p,
                                                   C.c_int64, C.POINTER(NumericInfo)]
+    lib.stmqr_b200_upload_values.argtypes = [C.c_void_p, _f64p, C.c_int64]
+    lib.stmqr_b200_refactorize_values.argtypes = [C.c_void_p, _f64p, C.c_int64, C.c_double, C.c_int64,
+                                                  C.POINTER(NumericInfo)]
+    lib.stmqr_b200_qmult.argtypes = [C.c_void_p, C.c_int, C.c_int64, _f64p, _f64p]
+    lib.stmqr_b200_rsolve.argtypes = [C.c_void_p, C.c_int, C.c_int64, _f64p, _f64p]
+    lib.stmqr_b200_solve_ls.argtypes = [C.c_void_p, C.c_int64, _f64p, _f64p, _f64p]
     lib.stmqr_b200_create_planner.argtypes = [C.POINTER(C.c_void_p)]
     lib.stmqr_b200_plan_info.argtypes = [C.c_void_p, C.POINTER(PlanInfo), _i64p, _i64p, C.POINTER(C.c_int32)]
     _lib = lib
@@ -414,6 +422,45 @@ class Engine:
         self._check(self.lib.stmqr_b200_get_front(self.h, f, which, buf.ctypes.data_as(_f64p), cap,
                                                   C.byref(fm), C.byref(fn)), "get_front")
         return buf[: fm.value * fn.value].reshape((fn.value, fm.value)).T  # column-major -> (fm, fn)
+
+    # ---- values-only refactorization and the device-side consumers (Q-apply, R-solve)
+    def refactorize_values(self, Ax, tol: float, ntol: int) -> NumericInfo:
+        """new values on the resident pattern (the matrix of the last upload_matrix / factorize)"""
+        Ax = np.ascontiguousarray(Ax, np.float64)
+        info = NumericInfo()
+        self._check(self.lib.stmqr_b200_refactorize_values(self.h, Ax.ctypes.data_as(_f64p), Ax.size, tol, ntol,
+                                                           C.byref(info)), "refactorize_values")
+        return info
+
+    @staticmethod
+    def _cols(X):
+        X = np.asfortranarray(X, dtype=np.float64)
+        return X.reshape(-1, 1, order="F") if X.ndim == 1 else X
+
+    def qmult(self, method: int, X) -> np.ndarray:
+        """Y = Q'X (method 0) or QX (method 1) from the factorization resident on the device"""
+        X = self._cols(X)
+        Y = np.zeros_like(X, order="F")
+        self._check(self.lib.stmqr_b200_qmult(self.h, method, X.shape[1], X.ctypes.data_as(_f64p),
+                                              Y.ctypes.data_as(_f64p)), "qmult")
+        return Y
+
+    def rsolve(self, B, permuted: bool = True) -> np.ndarray:
+        """X = E*(R\\B) (permuted) or R\\B; B is m-by-nrhs"""
+        B = self._cols(B)
+        X = np.zeros((self.sym.n, B.shape[1]), order="F")
+        self._check(self.lib.stmqr_b200_rsolve(self.h, int(permuted), B.shape[1], B.ctypes.data_as(_f64p),
+                                               X.ctypes.data_as(_f64p)), "rsolve")
+        return X
+
+    def solve_ls(self, B):
+        """x = E*(R\\(Q'b)) on the device -> (X n-by-nrhs, device milliseconds incl. the copies of b and x)"""
+        B = self._cols(B)
+        X = np.zeros((self.sym.n, B.shape[1]), order="F")
+        ms = C.c_double()
+        self._check(self.lib.stmqr_b200_solve_ls(self.h, B.shape[1], B.ctypes.data_as(_f64p),
+                                                 X.ctypes.data_as(_f64p), C.byref(ms)), "solve_ls")
+        return X, ms.value
 
     def plan_info(self):
         """-> (PlanInfo, Coff[nf], Csize[nf], level[nf]): arena sizes of the current plan, offset / bound size of
