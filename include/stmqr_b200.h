@@ -283,6 +283,17 @@ int  stmqr_b200_rsolve (stmqr_handle h, int use_Qfill, int64_t nrhs, const doubl
  * (optional) receives the device time including the two host<->device copies of b and x. */
 int  stmqr_b200_solve_ls (stmqr_handle h, int64_t nrhs, const double *B, double *X, double *device_ms) ;
 
+/* ---- the explicit factor ------------------------------------------------------------
+ * R of the resident factorization as a compressed-column matrix, extracted on the device: replaces
+ * qr_rcount / qr_rconvert (STMMQR/src/qr/SparseLQ.c:102-297, :299-520) in the configuration SparseQR()'s
+ * getR path uses for the multifrontal part (n1rows = 0, n2 = n, getT = 0; Ra/Rap branch).  Columns are in the
+ * order of S (apply Qfill for A's order), inside a column the entries are ordered as the reference appends
+ * them (by front, then by row), exact zeros are dropped, only rows < econ are kept.
+ *   rcount:   Rp [n+1] = column pointers (may be NULL), *nnzR = Rp [n]
+ *   rconvert: Rp [n+1], Ri [nnzR], Rx [nnzR]   (call rcount first to size Ri/Rx) */
+int  stmqr_b200_rcount (stmqr_handle h, int64_t econ, int64_t *Rp, int64_t *nnzR) ;
+int  stmqr_b200_rconvert (stmqr_handle h, int64_t econ, int64_t *Rp, int64_t *Ri, double *Rx) ;
+
 int  stmqr_b200_get_stats (stmqr_handle h, stmqr_stats *out) ;
 
 /* FP64 peak microbenchmarks on the handle's device, used as roofline denominators (the driver's

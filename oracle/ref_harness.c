@@ -229,6 +229,29 @@ void rh_qr_info (void *QRv, double *out /* [12] */)
     out [9] = QR->QRnum->maxfm ; out [10] = QR->QRnum->ns ; out [11] = QR->QRnum->ntasks ;
 }
 
+/* R of the multifrontal part as CSC through the reference's own qr_rcount / qr_rconvert (SparseLQ.c:102,299;
+ * n1rows = 0, n2 = n, getT = 0).  Pass Ri = Rx = NULL to get the column pointers / nnz only.  Returns nnz(R). */
+long rh_rconvert (void *QRv, long econ, int64_t *Rp_out, int64_t *Ri, double *Rx)
+{
+    SparseQR_factorization *QR = (SparseQR_factorization *) QRv ;
+    qr_symbolic *S = QR->QRsym ;
+    Long n = S->n ;
+    Long *Ra = (Long *) calloc ((size_t) n + 1, sizeof (Long)) ;
+    Long nh = 0 ;
+    qr_rcount (S, QR->QRnum, 0, econ, n, 0, Ra, NULL, NULL, &nh) ;
+    Long tot = 0 ;
+    for (Long j = 0 ; j < n ; j++) { Long c = Ra [j] ; Ra [j] = tot ; tot += c ; }
+    Ra [n] = tot ;
+    if (Rp_out) for (Long j = 0 ; j <= n ; j++) Rp_out [j] = Ra [j] ;
+    if (Ri && Rx)
+    {
+        /* qr_rconvert advances the column pointers while it fills (Rap [j]++) */
+        qr_rconvert (S, QR->QRnum, 0, econ, n, 0, Ra, (Long *) Ri, Rx, NULL, NULL, NULL, NULL, NULL, NULL, NULL) ;
+    }
+    free (Ra) ;
+    return (long) tot ;
+}
+
 void rh_set_probe (rh_probe_fn fn) { g_probe = fn ; }
 
 static void sym_view_of (qr_symbolic *S, stmqr_symbolic_view *v) ;

@@ -448,6 +448,11 @@ __global__ void k_scan_i64 (I64 *a, I64 *b, I32 n)
     __syncthreads () ;
     block_exclusive_scan<I64> (b, n, sh) ;
 }
+__global__ void k_scan1_i64 (I64 *a, I32 n)
+{
+    __shared__ I64 sh [34] ;
+    block_exclusive_scan<I64> (a, n, sh) ;
+}
 __global__ void k_hpinv_rows (DSym S, DNum N)
 {
     // one warp per front

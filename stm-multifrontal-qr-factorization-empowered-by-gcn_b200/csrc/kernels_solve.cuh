@@ -21,7 +21,10 @@ namespace stmqr {
 // HStair[k] - (q+1) entries below it, stored in column k of the packed block behind the R part (q+1
 // entries for a pivot column, Hr[f] for a non-pivot column).  One warp per front.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_htable (DSym S, DNum N, I32 *__restrict__ hcol, I32 *__restrict__ nh)
+// rlen [Rp[f] + k] (optional) = # entries of the R part of column k of the packed block (qr_rhpack: the rows
+// above the Householder vector): live pivot column = # live pivots up to and including it, dead pivot column =
+// # live pivots before it, non-pivot column = Hr[f].
+__global__ void k_htable (DSym S, DNum N, I32 *__restrict__ hcol, I32 *__restrict__ nh, I32 *__restrict__ rlen)
 {
     const int lane = threadIdx.x & 31 ;
     const I32 f = (I32) (((I64) blockIdx.x * blockDim.x + threadIdx.x) >> 5) ;
@@ -31,7 +34,8 @@ __global__ void k_htable (DSym S, DNum N, I32 *__restrict__ hcol, I32 *__restric
     const I32 fm = N.Hm [f] ;
     const I32 *st = N.stair + p1 ;
     I32 q = 0 ;                     // vectors so far = rm while in the pivot columns, = h afterwards
-    for (I32 base = 0 ; base < fn && q < fm ; base += 32)
+    I32 base = 0 ;
+    for ( ; base < fn && q < fm ; base += 32)
     {
         const I32 k = base + lane ;
         bool is = false ;
@@ -44,9 +48,18 @@ __global__ void k_htable (DSym S, DNum N, I32 *__restrict__ hcol, I32 *__restric
         const I32 mine = q + __popc (mask & ((1u << lane) - 1u)) ;
         // the loop of the reference stops once h (= vectors so far) reaches fm
         if (is && mine < fm) hcol [p1 + mine] = k ;
+        if (rlen && k < fp) rlen [p1 + k] = min (fm, mine + (is ? 1 : 0)) ;
         q = min (fm, q + __popc (mask)) ;
     }
     if (lane == 0) nh [f] = q ;
+    if (rlen)
+    {
+        // non-pivot columns: Hr entries; pivot columns the scan above did not reach (the rows ran out before
+        // them, so they are dead): Hr entries as well
+        const I32 rm = N.Hr [f] ;
+        for (I32 k = lane ; k < fn ; k += 32)
+            if (k >= fp || k >= base) rlen [p1 + k] = rm ;
+    }
 }
 
 // group = the threads that work on one front: a whole CTA (GROUP = blockDim.x) or one warp (GROUP = 32)
@@ -233,6 +246,88 @@ __global__ void __launch_bounds__ (GROUP == 32 ? 256 : GROUP) k_rsolve (const I3
             }
         }
         group_sync<GROUP> () ;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// R as a compressed-column matrix from the packed blocks (qr_rcount / qr_rconvert, STMMQR/src/qr/
+// SparseLQ.c:102-297, :299-520, the Ra/Rap branch: n1rows = 0, n2 = n, getT = 0).  The reference walks
+// the fronts in order and appends to every column through a running cursor, so inside a column the
+// entries are ordered by front, then by row; exact zeros are dropped (:235, :460).  Here:
+//   k_rcount      one warp per (front, column): # non-zeros of its R part with row < econ
+//   k_rcol_scan   one warp per column of R: exclusive running sum of those counts over the fronts that
+//                 hold the column, in front order, through the transpose of Rj (built at analyze time:
+//                 purely symbolic) -> where each front's piece starts inside the column, column totals
+//   (scan of the column totals -> Rp)
+//   k_rfill       one warp per (front, column): ballot-compacts the non-zeros into its piece
+// ---------------------------------------------------------------------------------------------
+__global__ void k_rcount (DSym S, DNum N, const I32 *__restrict__ posfront, const I32 *__restrict__ rlen,
+    I64 rjsize, I64 econ, I32 *__restrict__ cnt)
+{
+    const int lane = threadIdx.x & 31 ;
+    const I64 p = ((I64) blockIdx.x * blockDim.x + threadIdx.x) >> 5 ;
+    if (p >= rjsize) return ;
+    const I32 f = posfront [p] ;
+    const I32 len = rlen [p] ;
+    const I64 row1 = N.base1 [f] ;
+    const double *Rk = N.R + N.Roff [f] + N.colp [p] ;
+    I32 c = 0 ;
+    for (I32 i = lane ; i < len ; i += 32) c += (Rk [i] != 0.0 && row1 + i < econ) ? 1 : 0 ;
+    c = warp_sum_i (c) ;
+    if (lane == 0) cnt [p] = c ;
+}
+
+__global__ void k_rcol_scan (I64 n, const I32 *__restrict__ RjTp, const I32 *__restrict__ RjTi,
+    const I32 *__restrict__ cnt, I32 *__restrict__ off, I64 *__restrict__ colcount)
+{
+    const int lane = threadIdx.x & 31 ;
+    const I64 j = ((I64) blockIdx.x * blockDim.x + threadIdx.x) >> 5 ;
+    if (j >= n) return ;
+    I32 run = 0 ;
+    for (I32 b = RjTp [j] ; b < RjTp [j+1] ; b += 32)
+    {
+        const I32 e = b + lane ;
+        const I32 p = (e < RjTp [j+1]) ? RjTi [e] : -1 ;
+        const I32 c = (p >= 0) ? cnt [p] : 0 ;
+        I32 inc = c ;
+#pragma unroll
+        for (int o = 1 ; o < 32 ; o <<= 1)
+        {
+            const I32 u = __shfl_up_sync (STMQR_FULL_MASK, inc, o) ;
+            if (lane >= o) inc += u ;
+        }
+        if (p >= 0) off [p] = run + inc - c ;
+        run += __shfl_sync (STMQR_FULL_MASK, inc, 31) ;
+    }
+    if (lane == 0) colcount [j] = run ;
+}
+
+__global__ void k_rfill (DSym S, DNum N, const I32 *__restrict__ posfront, const I32 *__restrict__ rlen,
+    const I32 *__restrict__ off, const I64 *__restrict__ Rp_out, I64 rjsize, I64 econ,
+    I64 *__restrict__ Ri, double *__restrict__ Rx)
+{
+    const int lane = threadIdx.x & 31 ;
+    const I64 p = ((I64) blockIdx.x * blockDim.x + threadIdx.x) >> 5 ;
+    if (p >= rjsize) return ;
+    const I32 f = posfront [p] ;
+    const I32 len = rlen [p] ;
+    const I64 row1 = N.base1 [f] ;
+    const I32 j = S.Rj [p] ;
+    const double *Rk = N.R + N.Roff [f] + N.colp [p] ;
+    I64 dst = Rp_out [j] + off [p] ;
+    for (I32 b = 0 ; b < len ; b += 32)
+    {
+        const I32 i = b + lane ;
+        const double v = (i < len) ? Rk [i] : 0.0 ;
+        const bool nz = (i < len) && (v != 0.0) && (row1 + i < econ) ;
+        const unsigned mask = __ballot_sync (STMQR_FULL_MASK, nz) ;
+        if (nz)
+        {
+            const I64 q = dst + __popc (mask & ((1u << lane) - 1u)) ;
+            Ri [q] = row1 + i ;
+            Rx [q] = v ;
+        }
+        dst += __popc (mask) ;
     }
 }
 

@@ -248,6 +248,11 @@ struct stmqr_handle_s
 
     // device Q-apply / R-solve on the resident factorization (kernels_solve.cuh)
     I32 *d_hcol = nullptr, *d_nh = nullptr ;        // Householder table, rebuilt after every factorization
+    I32 *d_rlen = nullptr, *d_rcnt = nullptr, *d_roff = nullptr ;   // [rjsize] R part length / non-zeros / offset in its column
+    I32 *d_posfront = nullptr ;                     // [rjsize] front of every position of Rj
+    I32 *d_RjTp = nullptr, *d_RjTi = nullptr ;      // transpose of Rj: positions of every column, in front order
+    I64 *d_Rcolp = nullptr ;                        // [n+1] column pointers of the extracted R
+    I64 rcount_econ = -1, rcount_nnz = -1 ;         // what the resident counts were made for
     bool htable_valid = false ;
     double *d_solveZ = nullptr, *d_solveX = nullptr, *d_solveW = nullptr, *d_solveIO = nullptr ;
     I64 solveZ_cap = 0, solveX_cap = 0, solveIO_cap = 0 ;
@@ -317,6 +322,8 @@ void free_all (stmqr_handle h)
     h->d_slot = nullptr ; h->d_vAp = h->d_vAi = nullptr ; h->d_vdiff = nullptr ;
     h->slot_valid = h->values_only = false ;
     h->d_hcol = h->d_nh = nullptr ; h->htable_valid = false ;
+    h->d_rlen = h->d_rcnt = h->d_roff = h->d_posfront = h->d_RjTp = h->d_RjTi = nullptr ; h->d_Rcolp = nullptr ;
+    h->rcount_econ = h->rcount_nnz = -1 ;
     h->d_solveZ = h->d_solveX = h->d_solveW = h->d_solveIO = nullptr ;
     h->solveZ_cap = h->solveX_cap = h->solveIO_cap = 0 ;
 }
@@ -1127,6 +1134,23 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     ALLOC (N.base1, nf) ; ALLOC (N.base2, nf) ;
     ALLOC (h->d_err, 1) ;
     ALLOC (h->d_hcol, rjsize) ; ALLOC (h->d_nh, nf) ;
+    {
+        // transpose of Rj (column of R -> its positions in Rj, ascending = in front order) and the front of
+        // every position: symbolic inputs of the device R extraction (k_rcol_scan, k_rcount, k_rfill)
+        std::vector<I32> RjTp ((size_t) n + 1, 0), RjTi ((size_t) std::max<I64> (rjsize, 1)), posfront ((size_t) std::max<I64> (rjsize, 1)) ;
+        for (I64 pz = 0 ; pz < rjsize ; pz++) RjTp [(size_t) Rj [pz] + 1]++ ;
+        for (I64 j = 0 ; j < n ; j++) RjTp [(size_t) j + 1] += RjTp [(size_t) j] ;
+        std::vector<I32> cur (RjTp.begin (), RjTp.end () - 1) ;
+        for (I64 f = 0 ; f < nf ; f++)
+            for (I32 pz = Rp [f] ; pz < Rp [f+1] ; pz++)
+            {
+                posfront [pz] = (I32) f ;
+                RjTi [cur [Rj [pz]]++] = pz ;
+            }
+        UPLOAD (h->d_RjTp, RjTp) ; UPLOAD (h->d_RjTi, RjTi) ; UPLOAD (h->d_posfront, posfront) ;
+        ALLOC (h->d_rlen, rjsize) ; ALLOC (h->d_rcnt, rjsize) ; ALLOC (h->d_roff, rjsize) ;
+        ALLOC (h->d_Rcolp, n + 2) ;
+    }
     ALLOC (h->d_HPinv64, m) ;
     ALLOC (h->d_Hii64, hisize) ;
     ALLOC (h->d_wide, rjsize + 2 * nf + 2) ;
@@ -1223,6 +1247,7 @@ int stmqr_b200_factorize_begin (stmqr_handle h, double tol, int64_t ntol)
     h->launches = 0 ;
     h->factorized = false ;
     h->htable_valid = false ;
+    h->rcount_econ = h->rcount_nnz = -1 ;
     CK (cudaEventRecord (h->ev0, st)) ;
     CK (cudaMemsetAsync (N.Rdead, 0, std::max<I64> (h->n, 1), st)) ;
     CK (cudaMemsetAsync (N.rcursor, 0, sizeof (unsigned long long), st)) ;
@@ -2079,7 +2104,7 @@ int solve_ready (stmqr_handle h, const char *what)
     cudaSetDevice (h->device) ;
     if (!h->htable_valid)
     {
-        if (h->nf > 0) k_htable<<<grid_for (h->nf * 32, 256, 1 << 22), 256, 0, h->stream>>> (h->S, h->N, h->d_hcol, h->d_nh) ;
+        if (h->nf > 0) k_htable<<<grid_for (h->nf * 32, 256, 1 << 22), 256, 0, h->stream>>> (h->S, h->N, h->d_hcol, h->d_nh, h->d_rlen) ;
         CK (cudaGetLastError ()) ;
         h->htable_valid = true ;
     }
@@ -2228,6 +2253,57 @@ int stmqr_b200_solve_ls (stmqr_handle h, int64_t nrhs, const double *B, double *
     CK (cudaStreamSynchronize (st)) ;
     float ms = 0 ; cudaEventElapsedTime (&ms, h->ev2, h->ev3) ; h->ms_solve = ms ;
     if (device_ms) *device_ms = ms ;
+    return STMQR_OK ;
+}
+
+// -------------------------------------------------------------------------------------------------
+// R as a compressed-column matrix (qr_rcount / qr_rconvert on the device, kernels_solve.cuh)
+// -------------------------------------------------------------------------------------------------
+int stmqr_b200_rcount (stmqr_handle h, int64_t econ, int64_t *Rp_out, int64_t *nnzR)
+{
+    int s = solve_ready (h, "rcount") ;
+    if (s != STMQR_OK) return s ;
+    if (econ < 0) return fail (h, STMQR_ERR_INVALID, "rcount: econ < 0") ;
+    cudaStream_t st = h->stream ;
+    const I64 rj = h->rjsize, n = h->n ;
+    if (h->rcount_econ != econ)
+    {
+        if (rj > 0) k_rcount<<<(unsigned) ((rj * 32 + 255) / 256), 256, 0, st>>> (h->S, h->N, h->d_posfront, h->d_rlen, rj, econ, h->d_rcnt) ;
+        if (n > 0) k_rcol_scan<<<(unsigned) ((n * 32 + 255) / 256), 256, 0, st>>> (n, h->d_RjTp, h->d_RjTi, h->d_rcnt, h->d_roff, h->d_Rcolp) ;
+        // column totals -> column pointers: exclusive scan over n+1 entries (the last one is the total)
+        CK (cudaMemsetAsync (h->d_Rcolp + n, 0, sizeof (I64), st)) ;
+        k_scan1_i64<<<1, 1024, 0, st>>> (h->d_Rcolp, (I32) (n + 1)) ;
+        I64 tot = 0 ;
+        CK (cudaMemcpyAsync (&tot, h->d_Rcolp + n, sizeof (I64), cudaMemcpyDeviceToHost, st)) ;
+        CK (cudaStreamSynchronize (st)) ;
+        CK (cudaGetLastError ()) ;
+        h->rcount_econ = econ ; h->rcount_nnz = tot ;
+    }
+    if (Rp_out) { CK (cudaMemcpy (Rp_out, h->d_Rcolp, (size_t) (n + 1) * sizeof (I64), cudaMemcpyDeviceToHost)) ; }
+    if (nnzR) *nnzR = h->rcount_nnz ;
+    return STMQR_OK ;
+}
+
+int stmqr_b200_rconvert (stmqr_handle h, int64_t econ, int64_t *Rp_out, int64_t *Ri, double *Rx)
+{
+    int64_t nnz = 0 ;
+    int s = stmqr_b200_rcount (h, econ, Rp_out, &nnz) ;
+    if (s != STMQR_OK) return s ;
+    if (nnz > 0 && (!Ri || !Rx)) return fail (h, STMQR_ERR_INVALID, "rconvert: no destination") ;
+    if (nnz == 0) return STMQR_OK ;
+    cudaStream_t st = h->stream ;
+    // the extracted factor is staged on the device: Ri in the I64 scratch of the download, Rx in a solve buffer
+    I64 *dRi = nullptr ;
+    if ((s = grow (h, &h->d_solveIO, &h->solveIO_cap, 2 * nnz)) != STMQR_OK) return s ;
+    double *dRx = h->d_solveIO ;
+    dRi = (I64 *) (h->d_solveIO + nnz) ;
+    k_rfill<<<(unsigned) ((h->rjsize * 32 + 255) / 256), 256, 0, st>>> (h->S, h->N, h->d_posfront, h->d_rlen, h->d_roff, h->d_Rcolp,
+        h->rjsize, econ, dRi, dRx) ;
+    CK (cudaGetLastError ()) ;
+    CK (cudaStreamSynchronize (st)) ;
+    { int s1 = ensure_copy_pipeline (h) ; if (s1 != STMQR_OK) return s1 ; }
+    if ((s = d2h_pipelined (h, Ri, dRi, (size_t) nnz * sizeof (I64))) != STMQR_OK) return s ;
+    if ((s = d2h_pipelined (h, Rx, dRx, (size_t) nnz * sizeof (double))) != STMQR_OK) return s ;
     return STMQR_OK ;
 }
 

@@ -102,7 +102,7 @@ EXPORTS = (
     "stmqr_b200_rh_bound", "stmqr_b200_factorize_streamed", "stmqr_b200_stream_begin", "stmqr_b200_stream_end",
     "stmqr_b200_create_planner", "stmqr_b200_plan_info",
     "stmqr_b200_upload_values", "stmqr_b200_refactorize_values",
-    "stmqr_b200_qmult", "stmqr_b200_rsolve", "stmqr_b200_solve_ls",
+    "stmqr_b200_qmult", "stmqr_b200_rsolve", "stmqr_b200_solve_ls", "stmqr_b200_rcount", "stmqr_b200_rconvert",
 )
 
 _lib = None
@@ -159,6 +159,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.stmqr_b200_qmult.argtypes = [C.c_void_p, C.c_int, C.c_int64, _f64p, _f64p]
     lib.stmqr_b200_rsolve.argtypes = [C.c_void_p, C.c_int, C.c_int64, _f64p, _f64p]
     lib.stmqr_b200_solve_ls.argtypes = [C.c_void_p, C.c_int64, _f64p, _f64p, _f64p]
+    lib.stmqr_b200_rcount.argtypes = [C.c_void_p, C.c_int64, _i64p, _i64p]
+    lib.stmqr_b200_rconvert.argtypes = [C.c_void_p, C.c_int64, _i64p, _i64p, _f64p]
     lib.stmqr_b200_create_planner.argtypes = [C.POINTER(C.c_void_p)]
     lib.stmqr_b200_plan_info.argtypes = [C.c_void_p, C.POINTER(PlanInfo), _i64p, _i64p, C.POINTER(C.c_int32)]
     _lib = lib
@@ -461,6 +463,19 @@ class Engine:
         self._check(self.lib.stmqr_b200_solve_ls(self.h, B.shape[1], B.ctypes.data_as(_f64p),
                                                  X.ctypes.data_as(_f64p), C.byref(ms)), "solve_ls")
         return X, ms.value
+
+    def rconvert(self, econ: int = None):
+        """R of the resident factorization as CSC in the column order of S -> (Rp[n+1], Ri, Rx), extracted on the
+        device (qr_rcount / qr_rconvert); only rows < econ (default m)"""
+        econ = self.sym.m if econ is None else int(econ)
+        Rp = np.zeros(self.sym.n + 1, np.int64)
+        nnz = C.c_int64()
+        self._check(self.lib.stmqr_b200_rcount(self.h, econ, Rp.ctypes.data_as(_i64p), C.byref(nnz)), "rcount")
+        Ri = np.zeros(max(int(nnz.value), 1), np.int64)
+        Rx = np.zeros(max(int(nnz.value), 1))
+        self._check(self.lib.stmqr_b200_rconvert(self.h, econ, Rp.ctypes.data_as(_i64p), Ri.ctypes.data_as(_i64p),
+                                                 Rx.ctypes.data_as(_f64p)), "rconvert")
+        return Rp, Ri[: nnz.value], Rx[: nnz.value]
 
     def plan_info(self):
         """-> (PlanInfo, Coff[nf], Csize[nf], level[nf]): arena sizes of the current plan, offset / bound size of

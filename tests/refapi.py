@@ -366,6 +366,17 @@ class Reference:
         assert st == 0, st
         return X
 
+    def rconvert(self, QR, econ: int, n: int):
+        """R of the multifrontal part as CSC (Rp, Ri, Rx) through the reference's qr_rcount / qr_rconvert"""
+        self.L.rh_rconvert.argtypes = [C.c_void_p, C.c_long, _i64p, _i64p, _f64p]
+        self.L.rh_rconvert.restype = C.c_long
+        Rp = np.zeros(n + 1, np.int64)
+        nnz = int(self.L.rh_rconvert(QR, econ, Rp.ctypes.data_as(_i64p), None, None))
+        Ri = np.zeros(max(nnz, 1), np.int64)
+        Rx = np.zeros(max(nnz, 1))
+        self.L.rh_rconvert(QR, econ, Rp.ctypes.data_as(_i64p), Ri.ctypes.data_as(_i64p), Rx.ctypes.data_as(_f64p))
+        return Rp, Ri[:nnz], Rx[:nnz]
+
     def check_error(self, A, QR) -> float:
         return float(self.L.rh_check_error(self.cc, A, QR))
 

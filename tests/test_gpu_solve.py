@@ -144,3 +144,42 @@ def test_values_only_refactorization_matches_oracle(engine, oracle, case):
     got4 = engine.download(engine.factorize(A3, tol, ntol))
     want4 = oracle.factorize(sym, A, tol, ntol)
     R.assert_numeric_parity(sym, A, got4, want4, case + " reordered entries")
+
+
+@pytest.mark.parametrize("name,order", [("dwt_992", 2), ("t2d_q9", 2), ("epb1", 1), ("cvxqp3", 1)])
+def test_device_rconvert_matches_reference(name, order):
+    """R as a compressed-column matrix extracted on the device == the reference's own qr_rcount / qr_rconvert
+    applied to the same factorization (the drop-in's qr_numeric on the host; the engine is deterministic, so a
+    second engine holds the identical factor): column pointers, row indices and values bit for bit, including
+    the order inside a column, the dropped exact zeros and the econ cut; rank-deficient inputs included."""
+    if not R.have_reference():
+        pytest.skip("needs oracle/_ref")
+    ref = R.Reference()
+    A = ref.read_mtx(os.path.join(R.DATA_DIR, name + ".mtx"))
+    tol = ref.default_tol(A)
+    ref.set_backend("b200")
+    QR = ref.sparseqr(A, order, tol, grain=1.0, tap=True)
+    assert ref.qr_info(QR)["n1cols"] == 0
+    sym = ref.symbolic(QR)
+    At, ttol, ntol = ref.tapped()
+    e = sq.Engine(0)
+    e.analyze(sym)
+    info = e.factorize(At, ttol, ntol)
+    for econ in (sym.m, max(1, int(info.rank) // 2)):
+        Rp, Ri, Rx = e.rconvert(econ)
+        Rp0, Ri0, Rx0 = ref.rconvert(QR, econ, sym.n)
+        assert np.array_equal(Rp, Rp0), (name, econ)
+        assert np.array_equal(Ri, Ri0), (name, econ)
+        assert np.array_equal(Rx, Rx0), (name, econ)
+    # the extracted R is the R of the factorization: R'R = (AP)'(AP) on the live columns (full-rank inputs)
+    if int(info.rank) == sym.n:
+        import scipy.sparse as sp
+        Rp, Ri, Rx = e.rconvert()
+        Rm = sp.csc_matrix((Rx, Ri, Rp), shape=(sym.m, sym.n))
+        S = At.to_scipy()[:, sym.Qfill[: sym.n]] if sym.arrays.get("Qfill") is not None else At.to_scipy()
+        G1, G2 = (Rm.T @ Rm), (S.T @ S)
+        assert abs(G1 - G2).max() <= 1e-10 * abs(G2).max()
+    e.close()
+    ref.free_qr(QR); ref.free_sparse(A)
+    ref.set_backend("reference")
+    ref.close()
