@@ -199,6 +199,81 @@ def run_reference_arm(args):
     emit(line)
 
 
+def multi_gpu_parity_check(D, sq, R, local, rank, world):
+    """Before anything is timed: golden inputs factorized over the REAL ranks through the C data plane (NCCL),
+    gathered on rank 0 and compared with the reference's golden output (integer structure bit-exact, R to the
+    north_star tolerance).  -> "ok" (rank 0) or raises."""
+    import torch
+    import torch.distributed as dist
+    done = []
+    for case in ("dwt_992_metis", "lap3d_8_metis", "tall_600x150_colamd"):
+        sym, A, tol, ntol, want = R.load_golden(case)
+        e = sq.Engine(local)
+        e.analyze(sym)
+        e.upload_matrix(A)
+        df = D.DistFactorization(e, sym, torch.device("cuda", local))
+        info = df.factorize(tol, ntol)
+        num = e.download(info)
+        got = D.gather_numeric(sym, df.owner, num, info)
+        if rank == 0:
+            d = R.assert_numeric_parity(sym, A, got, want, f"{case} over {world} ranks (NCCL)")
+            assert got.flops == want.flops
+            done.append(f"{case}: fronts per rank {np.bincount(df.owner, minlength=world).tolist()}, "
+                        f"max|dR|/|A| {d:.1e}")
+        e.close()
+        dist.barrier()
+    return "ok (" + "; ".join(done) + ")" if rank == 0 else "ok"
+
+
+def extra_leg(args, sq, torch, dist, rank, world, local, workload):
+    """A second, GPU-only workload in the same process (resident numeric phase, no CPU arm): the 3-D Laplacian
+    the north_star names for the 1 -> 8 GPU scaling, next to the headline workload."""
+    import refapi as R
+    desc, mat, order = make_workload(workload)
+    ref = R.Reference()
+    A = ref.csc_from_arrays(*mat)
+    tol = ref.default_tol(A)
+    t0 = time.time()
+    sym = ref.analyze_only(A, order, tol)               # the reference's symbolic phase alone (no numeric work)
+    t_sym = time.time() - t0
+    At = ref.csc_to_numpy(A)
+    eng = sq.Engine(local)
+    eng.analyze(sym)
+    eng.upload_matrix(At)
+    ntol = sym.n
+    pf = None
+    if world > 1:
+        from stmqr_b200 import dist as D
+        pf = D.DistFactorization(eng, sym, torch.device("cuda", local))
+    ms = []
+    info = None
+    for s in range(1 + args.leg_steps):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        info = pf.factorize(tol, ntol) if pf is not None else eng.factorize_resident(tol, ntol)
+        if s >= 1:
+            ms.append(eng.stats().ms_numeric)
+    t = float(np.mean(ms))
+    rh = float(info.rh_size)
+    dev_bytes = float(eng.stats().device_bytes)
+    if dist is not None:
+        tt = torch.tensor([t, dev_bytes], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t, dev_bytes = float(tt[0].item()), float(tt[1].item())
+        tt = torch.tensor([rh], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        rh = float(tt.item())
+    out = {"workload": workload, "description": desc, "ms_per_step": t, "value": float(info.flops) / t * 1e-6,
+           "unit": UNIT, "steps": args.leg_steps, "warmup": 1, "flops_per_step": float(info.flops),
+           "rank": int(info.rank), "fronts": sym.nf, "rh_doubles": rh, "device_bytes_max_per_gpu": dev_bytes,
+           "symbolic_s": t_sym, "timing": "CUDA events on every rank's engine stream, max over ranks"}
+    eng.close()
+    ref.free_sparse(A)
+    ref.close()
+    return out
+
+
 def run_b200_arm(args):
     import torch
     import stmqr_b200 as sq
@@ -234,11 +309,13 @@ def run_b200_arm(args):
     eng.upload_matrix(At)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
     pf = None
+    parity = None
     if world > 1:
-        # the etree partitioned over the ranks: subtrees in parallel, cut contribution blocks to
-        # rank 0 over NCCL send/recv, top of the tree on rank 0 (stmqr_b200/dist.py)
+        # every front on its owner GPU, the data plane in C (csrc/multigpu.cuh): contribution blocks + row ids
+        # over ncclSend/ncclRecv per etree level, max-merges with ncclAllReduce, all on the engine's stream
         from stmqr_b200 import dist as D
-        pf = D.PartitionedFactorization(D.TorchComm(torch.device("cuda", local)), {rank: eng}, sym)
+        parity = multi_gpu_parity_check(D, sq, R, local, rank, world)     # real ranks, real NCCL, golden inputs
+        pf = D.DistFactorization(eng, sym, torch.device("cuda", local))
 
     def factor_step():
         """one numeric factorization of the resident matrix -> (NumericInfo of this rank, ms)"""
@@ -246,10 +323,8 @@ def run_b200_arm(args):
             inf = eng.factorize_resident(ttol, ntol)
             return inf, eng.stats().ms_numeric            # CUDA events on the engine's stream
         barrier()
-        t0 = time.perf_counter()
-        inf = pf.factorize(ttol, ntol)[rank]
-        barrier()
-        return inf, (time.perf_counter() - t0) * 1e3      # several streams + NCCL: wall clock between syncs
+        inf = pf.factorize(ttol, ntol)
+        return inf, eng.stats().ms_numeric                # events on this rank's stream (waits for peers included)
 
     # ---------------- value: A resident in HBM, device time ----------------------------------
     for _ in range(args.warmup):
@@ -297,25 +372,39 @@ def run_b200_arm(args):
     front_ms = float(cls_ms[3] + cls_ms[4])
     classes = dict(zip(sq.KERNEL_CLASSES, [round(float(x), 4) for x in cls_ms]))
     dom = int(np.argmax(cls_ms))
+    ms_step = t_dev / args.steps * 1e3                 # the TIMED step (look-ahead overlap on, no per-launch events)
+    other_ms = float(cls_ms[0] + cls_ms[7]) + asm_ms   # build_S, hpinv and assembly/pack: serial on the main stream
+    # DRAM traffic per launch of the dominant kernel comes from an ncu --set full capture of this workload, if one
+    # has been summarised under profiles/ (profiles/dram_traffic.json: workload -> kernel, bytes, source); never a
+    # constant in this file
+    traffic = traffic_src = traffic_kernel = None
+    tj = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(tj):
+        with open(tj) as f:
+            ent = json.load(f).get(args.workload)
+        if ent:
+            traffic, traffic_src, traffic_kernel = ent.get("dram_bytes_per_launch"), ent.get("source"), ent.get("kernel")
     if dom in (3, 4):
-        # front QR: panel + WY update kernels; algorithmic flops = the reference's count
-        ach = flops / (front_ms * 1e-3) * 1e-12
-        # DRAM traffic of the dominant kernel from one `ncu --set full` capture (profiles/): a top-level
-        # k_panel_cluster launch of lap2d_1024 reads 1.49 MB and writes nothing (slabs in shared memory,
-        # front in L2); null for other workloads (not captured)
-        traffic = 1489152 if args.workload == "lap2d_1024" else None        # bytes per launch
-        traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum of one top-level k_panel_cluster<256,2> launch, "
-                       "profiles/r01_u_ncu_full_k_panel_cluster_lap2d_1024_raw.csv") if traffic else None
-        roof = {"bound": "tensor", "kernel": "front QR (k_panel + k_update)", "achieved": ach, "peak": dmma_tf,
-                "unit": "TFLOP/s", "frac": ach / dmma_tf if dmma_tf else None, "traffic": traffic,
+        # front QR (panel + WY update kernels); algorithmic flops = the reference's count.  Denominator: the timed
+        # step minus the serial assembly/pack/hpinv kernels (measured in the profile steps) = the wall time the
+        # front-QR kernels occupy in the real, overlapped schedule
+        front_timed = max(ms_step - other_ms, 1e-6)
+        ach = flops / (front_timed * 1e-3) * 1e-12
+        roof = {"bound": "tensor", "kernel": "front QR (k_panel_* + k_update_dmma / k_wide_*)", "achieved": ach,
+                "peak": dmma_tf, "unit": "TFLOP/s", "frac": ach / dmma_tf if dmma_tf else None, "traffic": traffic,
+                "how": "reference flop count / (timed ms_per_step - assembly, pack, build_S, hpinv ms of the profile steps)",
+                "front_qr_ms_timed": front_timed, "whole_step_tflops": flops / (ms_step * 1e-3) * 1e-12,
+                "whole_step_frac": flops / (ms_step * 1e-3) * 1e-12 / dmma_tf if dmma_tf else None,
                 "peak_source": "FP64 mma.sync (DMMA) register-loop microbenchmark run in this process "
                                "(stmqr_b200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
-                "avg_launch_ms": front_ms / max(1.0, float(cls_n[3] + cls_n[4])), "traffic_source": traffic_src}
+                "avg_launch_ms": front_ms / max(1.0, float(cls_n[3] + cls_n[4])), "traffic_source": traffic_src,
+                "traffic_kernel": traffic_kernel}
     else:
         ach = float(s2.bytes_assemble) / (asm_ms * 1e-3) * 1e-9
         roof = {"bound": "hbm", "kernel": "assembly+pack (k_front_setup, k_assemble, k_front_finish, k_pack)",
                 "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "traffic_kernel": traffic_kernel,
+                "peak_source": peak_src,
                 "avg_launch_ms": asm_ms / max(1.0, float(cls_n[1] + cls_n[2] + cls_n[5] + cls_n[6]))}
     roof["class_ms"] = classes
     roof["assembly_gbs"] = float(s2.bytes_assemble) / (asm_ms * 1e-3) * 1e-9 if asm_ms > 0 else None
@@ -325,7 +414,26 @@ def run_b200_arm(args):
     roof["fp64_dfma_peak_tflops"] = dfma_tf
     eng.set_options(panel=args.panel, profile_phases=0)
 
-    if pf is None:
+    # ---------------- factorize + solve without downloading the factor ----------------
+    solve = None
+    if pf is None and sym.m == sym.n:
+        rng = np.random.default_rng(5)
+        bvec = rng.standard_normal(sym.m)
+        eng.factorize_resident(ttol, ntol)
+        xs, ms_solve = eng.solve_ls(bvec)                   # warm-up (builds the Householder table)
+        xs, ms_solve = eng.solve_ls(bvec)
+        Ssp = At.to_scipy()
+        res = float(np.linalg.norm(Ssp @ xs[:, 0] - bvec) / max(np.linalg.norm(bvec), 1e-300))
+        solve = {"what": "x = E*(R\\(Q'b)) on the device from the resident R+H (stmqr_b200_solve_ls), 1 right-hand side",
+                 "ms": ms_solve, "relative_residual": res,
+                 "bytes_not_downloaded": int(info.rh_size) * 8}
+    legs = {}
+    if args.leg and args.leg != args.workload:
+        if pf is None:
+            eng.close()
+            eng = None
+        legs[args.leg] = extra_leg(args, sq, torch, dist, rank, world, local, args.leg)
+    if pf is None and eng is not None:
         eng.close()                                   # the e2e leg below uses the drop-in's own handle
 
     # ---------------- e2e: host sparse_csc in, host qr_numeric out -----------------------------
@@ -345,7 +453,7 @@ def run_b200_arm(args):
                 t0 = time.perf_counter()
                 eng.upload_matrix(At)
                 stack = eng.stream_begin()                  # this rank's R+H blocks go to the host level by level
-                inf = pf.factorize(ttol, ntol)[rank]
+                inf = pf.factorize(ttol, ntol)
                 eng.stream_end()
                 eng.download(inf, stack=stack[: max(int(inf.rh_size), 1)])
                 barrier()
@@ -403,11 +511,12 @@ def run_b200_arm(args):
                            "rh_doubles": rh_total, "tol": ttol,
                            "l2": "256 MiB device buffer written between timed steps (L2 flush)",
                            "multi_gpu": ("single" if world == 1 else
-                                         f"etree partitioned over {world} GPUs: {int(pf.is_top.sum())} top fronts on "
-                                         f"rank 0, {len(pf.cut)} cut contribution blocks over NCCL send/recv, "
-                                         f"fronts per rank {np.bincount(pf.owner, minlength=world).tolist()}"),
+                                         f"every front on its owner GPU ({world} GPUs, fronts per rank "
+                                         f"{np.bincount(pf.owner, minlength=world).tolist()}); contribution blocks + row "
+                                         f"ids move after the child's etree level over ncclSend/ncclRecv issued by the C "
+                                         f"library on the engine stream, merges by ncclAllReduce; no host sync between levels"),
                            "timing": ("CUDA events on the engine stream" if world == 1 else
-                                      "wall clock between barrier+synchronize (engine streams + NCCL), max over ranks"),
+                                      "CUDA events on every rank's engine stream after a barrier (waits for peers included), max over ranks"),
                            "device_bytes": int(st.device_bytes)},
                 "e2e": ({"value": flops * len(e2e_s) / t_e2e * 1e-9, "unit": UNIT,
                          "ms_per_step": t_e2e / len(e2e_s) * 1e3, "h2d_bytes_per_step": h2d,
@@ -420,7 +529,8 @@ def run_b200_arm(args):
                          "first_call_with_plan_s": setup["first_factorize_s"],
                          "plan_ms": float(st.ms_plan)} if t_e2e else None),
                 "gpu_launches": launches * args.steps,
-                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "solve": solve, "legs": legs,
+                "parity_check": parity,
                 "stats": {"ms_h2d": float(st.ms_h2d), "ms_d2h": float(st.ms_d2h),
                           "launches_per_step": launches}}
         emit(line)
@@ -437,6 +547,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="lap2d_1024")
     ap.add_argument("--panel", type=int, default=0)
+    ap.add_argument("--leg", default="lap3d_96",
+                    help="second, GPU-only workload measured in the same run (the 3-D Laplacian of the scaling target); '' = none")
+    ap.add_argument("--leg-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cpu-tree-tasks", action="store_true",
                     help="skip the reference's TPSM tree-task mode in the CPU baseline probe")

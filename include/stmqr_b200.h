@@ -244,6 +244,25 @@ int  stmqr_b200_create_planner (stmqr_handle *out) ;
  * (etree level of every front); any of them may be NULL. */
 int  stmqr_b200_plan_info (stmqr_handle h, stmqr_plan_info *out, int64_t *Coff, int64_t *Csize, int32_t *level) ;
 
+/* ---- general ownership + the C data plane (csrc/multigpu.cuh) ---------------------------------------------
+ * Every front has an owner GPU (stmqr_b200_map_fronts: subtrees below the cut as partition_fronts deals them,
+ * a front above the cut on the GPU of its heaviest child, so the upper levels spread over the GPUs too).  Each
+ * GPU walks the etree levels over its own fronts; after level l the contribution blocks (+ row ids + Cm/Hr/Hm)
+ * of the level-l fronts whose parent lives elsewhere move there, in symbolic-bound sizes, ordered on the
+ * engine's stream: no handshake, no host synchronisation.  At the end Hm|Hr|Cm, Rdead and the row permutation
+ * are merged with element-wise max all-reduces.  Transports: NCCL (one process per GPU; libnccl is dlopen'ed)
+ * and peer copies between handles of one process (one host thread per handle). */
+int  stmqr_b200_map_fronts (const stmqr_symbolic_view *sym, int nparts, int32_t *owner) ;
+int  stmqr_b200_set_ownership (stmqr_handle h, int nparts, int mypart, const int32_t *owner) ;
+int  stmqr_b200_nccl_unique_id (void *id128) ;                 /* rank 0; ship the 128 bytes to the others */
+int  stmqr_b200_comm_init (stmqr_handle h, int nranks, int rank, const void *id128) ;
+int  stmqr_b200_peer_group_create (stmqr_handle *handles, int n, void **group) ;
+void stmqr_b200_peer_group_destroy (void *group) ;
+/* one GPU's share; all GPUs of the group call it at the same time */
+int  stmqr_b200_factorize_dist (stmqr_handle h, double tol, int64_t ntol, stmqr_numeric_info *info) ;
+/* every handle of a peer group, one host thread each; infos [n] (may be NULL) */
+int  stmqr_b200_factorize_multi (void *group, double tol, int64_t ntol, stmqr_numeric_info *infos) ;
+
 #define STMQR_ARRAY_HM    0   /* int32 [nf] */
 #define STMQR_ARRAY_HR    1   /* int32 [nf] */
 #define STMQR_ARRAY_CM    2   /* int32 [nf] */

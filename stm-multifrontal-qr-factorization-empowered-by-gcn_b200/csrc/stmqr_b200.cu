@@ -43,6 +43,7 @@ struct Level
 {
     I32 first ;         // offset into the level-ordered front list
     I32 count ;
+    I32 glevel ;        // etree level (distance from the leaves) in the whole tree
     I32 maxfn ;         // max # columns in the level
     I64 maxFelems ;     // max bound Fm*fn in the level
     I32 maxFm ;         // max bound Fm in the level
@@ -258,6 +259,14 @@ struct stmqr_handle_s
     I64 solveZ_cap = 0, solveX_cap = 0, solveIO_cap = 0 ;
     double ms_solve = 0 ;
 
+    // multi-GPU (multigpu.cuh): every front has an owner, the fronts of this GPU by level, the blocks that move
+    void *transport = nullptr ;                     // Transport *
+    LevelSet ls_mine ;
+    std::vector<I32> h_level ;                      // etree level of every front
+    std::vector<std::vector<int>> xedges ;          // per etree level: indices into xall of the edges leaving that level
+    std::vector<I32> xall_c, xall_src, xall_dst ;   // all transfer edges (child front, owner of child, owner of parent)
+    void *xptr = nullptr ;                          // PeerTransport: the array this handle contributes to the running all-reduce
+
     stmqr_numeric_info info {} ;
     stmqr_stats stats {} ;
     I64 launches = 0 ;
@@ -268,6 +277,8 @@ struct stmqr_handle_s
     long long curtag = 0 ;
     size_t evused = 0 ;
 } ;
+
+#include "multigpu.cuh"
 
 namespace {
 
@@ -687,7 +698,7 @@ void filter_levels (const LevelSet &all, const std::vector<unsigned char> &keep,
             if (keep [f]) v.push_back (f) ;
         }
         if (v.empty ()) continue ;
-        Level L ; L.first = (I32) out.fronts.size () ;
+        Level L ; L.first = (I32) out.fronts.size () ; L.glevel = Lv.glevel ;
         finish_level (L, v, Rp, FmB, small_cap, wide_rows) ;
         for (I32 f : v) out.fronts.push_back (f) ;
         out.levels.push_back (L) ;
@@ -731,6 +742,151 @@ int finish_pattern_check (stmqr_handle h)
     CK (cudaStreamSynchronize (h->streamV)) ;
     h->pattern_mismatch = (diff != 0) ;
     if (h->pattern_mismatch) { h->n_pattern_mismatch++ ; h->slot_valid = false ; }
+    return STMQR_OK ;
+}
+
+// ---- transports (multigpu.cuh) ---------------------------------------------------------------------
+int NcclTransport::exchange (stmqr_handle h, const std::vector<XEdge> &edges, I32 glevel)
+{
+    (void) glevel ;
+    std::vector<I32> sl, rl ;
+    for (const XEdge &e : edges) { if (e.src == me) sl.push_back (e.c) ; if (e.dst == me) rl.push_back (e.c) ; }
+    if (sl.empty () && rl.empty ()) return STMQR_OK ;
+    cudaStream_t st = h->stream ;
+    int s = ensure ((I64) std::max (sl.size (), rl.size ())) ;
+    if (s != STMQR_OK) return s ;
+    I32 *d_sl = d_list, *d_rl = d_list + cap ;
+    // (pageable source: the copy is staged before the call returns, the vectors may die afterwards)
+    if (!sl.empty ()) CK (cudaMemcpyAsync (d_sl, sl.data (), sl.size () * sizeof (I32), cudaMemcpyHostToDevice, st)) ;
+    if (!rl.empty ()) CK (cudaMemcpyAsync (d_rl, rl.data (), rl.size () * sizeof (I32), cudaMemcpyHostToDevice, st)) ;
+    if (!sl.empty ()) k_xpack<<<(unsigned) ((sl.size () + 127) / 128), 128, 0, st>>> (d_sl, (I32) sl.size (), h->N, d_send) ;
+    if (!ok (g_nccl.GroupStart (), "ncclGroupStart")) return STMQR_ERR_CUDA ;
+    size_t is = 0, ir = 0 ;
+    for (const XEdge &e : edges)
+    {
+        const I32 c = e.c ;
+        const size_t cd = (size_t) h->h_Csize [c], hi = (size_t) (h->h_Hip [c+1] - h->h_Hip [c]) ;
+        if (e.src == me)
+        {
+            if (cd > 0 && !ok (g_nccl.Send (h->N.C + h->h_Coff [c], cd, ncclDouble, e.dst, comm, st), "ncclSend")) return STMQR_ERR_CUDA ;
+            if (hi > 0 && !ok (g_nccl.Send (h->N.Hii + h->h_Hip [c], hi, ncclInt32, e.dst, comm, st), "ncclSend")) return STMQR_ERR_CUDA ;
+            if (!ok (g_nccl.Send (d_send + 3 * is, 3, ncclInt32, e.dst, comm, st), "ncclSend")) return STMQR_ERR_CUDA ;
+            is++ ;
+        }
+        else if (e.dst == me)
+        {
+            if (cd > 0 && !ok (g_nccl.Recv (h->N.C + h->h_Coff [c], cd, ncclDouble, e.src, comm, st), "ncclRecv")) return STMQR_ERR_CUDA ;
+            if (hi > 0 && !ok (g_nccl.Recv (h->N.Hii + h->h_Hip [c], hi, ncclInt32, e.src, comm, st), "ncclRecv")) return STMQR_ERR_CUDA ;
+            if (!ok (g_nccl.Recv (d_recv + 3 * ir, 3, ncclInt32, e.src, comm, st), "ncclRecv")) return STMQR_ERR_CUDA ;
+            ir++ ;
+        }
+    }
+    if (!ok (g_nccl.GroupEnd (), "ncclGroupEnd")) return STMQR_ERR_CUDA ;
+    if (!rl.empty ()) k_xunpack<<<(unsigned) ((rl.size () + 127) / 128), 128, 0, st>>> (d_rl, (I32) rl.size (), d_recv, h->N) ;
+    CK (cudaGetLastError ()) ;
+    h->launches += 2 ;
+    return STMQR_OK ;
+}
+
+int NcclTransport::allreduce (stmqr_handle h, void *p, I64 count, XType t, bool maxop)
+{
+    if (count <= 0) return STMQR_OK ;
+    const ncclDataType_t dt = (t == X_I8) ? ncclInt8 : ((t == X_I32) ? ncclInt32 : ((t == X_I64) ? ncclInt64 : ncclDouble)) ;
+    if (!ok (g_nccl.AllReduce (p, p, (size_t) count, dt, maxop ? ncclMax : ncclSum, comm, h->stream), "ncclAllReduce")) return STMQR_ERR_CUDA ;
+    return STMQR_OK ;
+}
+
+int PeerTransport::exchange (stmqr_handle h, const std::vector<XEdge> &edges, I32 glevel)
+{
+    (void) glevel ;
+    cudaStream_t st = h->stream ;
+    CK (cudaEventRecord (evReady, st)) ;
+    grp->barrier () ;                       // every handle has recorded where its level ends
+    for (const XEdge &e : edges)
+    {
+        if (e.dst != me) continue ;
+        stmqr_handle src = grp->hs [e.src] ;
+        PeerTransport *ts = (PeerTransport *) src->transport ;
+        const I32 c = e.c ;
+        const size_t cd = (size_t) h->h_Csize [c] * sizeof (double), hi = (size_t) (h->h_Hip [c+1] - h->h_Hip [c]) * sizeof (I32) ;
+        CK (cudaStreamWaitEvent (st, ts->evReady, 0)) ;
+        if (cd > 0) CK (cudaMemcpyPeerAsync (h->N.C + h->h_Coff [c], h->device, src->N.C + src->h_Coff [c], src->device, cd, st)) ;
+        if (hi > 0) CK (cudaMemcpyPeerAsync (h->N.Hii + h->h_Hip [c], h->device, src->N.Hii + src->h_Hip [c], src->device, hi, st)) ;
+        CK (cudaMemcpyPeerAsync (h->N.Cm + c, h->device, src->N.Cm + c, src->device, sizeof (I32), st)) ;
+        CK (cudaMemcpyPeerAsync (h->N.Hr + c, h->device, src->N.Hr + c, src->device, sizeof (I32), st)) ;
+        CK (cudaMemcpyPeerAsync (h->N.Hm + c, h->device, src->N.Hm + c, src->device, sizeof (I32), st)) ;
+    }
+    return STMQR_OK ;
+}
+
+int PeerTransport::allreduce (stmqr_handle h, void *p, I64 count, XType t, bool maxop)
+{
+    if (count <= 0) return STMQR_OK ;
+    cudaStream_t st = h->stream ;
+    const size_t bytes = (size_t) count * xsize (t) ;
+    const int n = nranks () ;
+    h->xptr = p ;
+    CK (cudaEventRecord (evReady, st)) ;
+    grp->barrier () ;
+    if (me == 0)
+    {
+        if (bytes > scratch_bytes)
+        {
+            if (scratch) cudaFree (scratch) ;
+            scratch = nullptr ; scratch_bytes = 0 ;
+            CK (cudaMalloc (&scratch, bytes)) ;
+            scratch_bytes = bytes ;
+        }
+        for (int r = 1 ; r < n ; r++)
+        {
+            stmqr_handle src = grp->hs [r] ;
+            CK (cudaStreamWaitEvent (st, ((PeerTransport *) src->transport)->evReady, 0)) ;
+            CK (cudaMemcpyPeerAsync (scratch, h->device, src->xptr, src->device, bytes, st)) ;
+            const int g = grid_for (count, 256) ;
+            if (t == X_I8) { if (maxop) k_merge<signed char, true><<<g, 256, 0, st>>> ((signed char *) p, (const signed char *) scratch, count) ; else k_merge<signed char, false><<<g, 256, 0, st>>> ((signed char *) p, (const signed char *) scratch, count) ; }
+            else if (t == X_I32) { if (maxop) k_merge<I32, true><<<g, 256, 0, st>>> ((I32 *) p, (const I32 *) scratch, count) ; else k_merge<I32, false><<<g, 256, 0, st>>> ((I32 *) p, (const I32 *) scratch, count) ; }
+            else if (t == X_I64) { if (maxop) k_merge<I64, true><<<g, 256, 0, st>>> ((I64 *) p, (const I64 *) scratch, count) ; else k_merge<I64, false><<<g, 256, 0, st>>> ((I64 *) p, (const I64 *) scratch, count) ; }
+            else { if (maxop) k_merge<double, true><<<g, 256, 0, st>>> ((double *) p, (const double *) scratch, count) ; else k_merge<double, false><<<g, 256, 0, st>>> ((double *) p, (const double *) scratch, count) ; }
+        }
+        CK (cudaEventRecord (evDone, st)) ;
+    }
+    grp->barrier () ;                       // handle 0 has enqueued the merge
+    if (me != 0)
+    {
+        stmqr_handle root = grp->hs [0] ;
+        CK (cudaStreamWaitEvent (st, ((PeerTransport *) root->transport)->evDone, 0)) ;
+        CK (cudaMemcpyPeerAsync (p, h->device, root->xptr, root->device, bytes, st)) ;
+    }
+    return STMQR_OK ;
+}
+
+// Owner of every front (host only, deterministic).  The subtrees below the cut are dealt to the GPUs as
+// partition_fronts does (largest first onto the lightest GPU); a front above the cut goes to the GPU of
+// its heaviest child, so the largest contribution block never moves and the fronts of one upper level
+// spread over the GPUs instead of queueing on GPU 0.
+int map_fronts (I64 nf, const int64_t *Childp, const int64_t *Child, const int64_t *Super, const int64_t *Rp,
+    const int64_t *Fm, int nparts, int32_t *owner)
+{
+    std::vector<int32_t> top ((size_t) std::max<I64> (nf, 1), 0) ;
+    int s = partition_fronts (nf, Childp, Child, Super, Rp, Fm, nparts, owner, top.data ()) ;
+    if (s != STMQR_OK || nparts == 1) return s ;
+    std::vector<double> sub ((size_t) nf, 0.0) ;
+    std::vector<I64> parent ((size_t) nf, -1) ;
+    for (I64 f = 0 ; f < nf ; f++) for (I64 q = Childp [f] ; q < Childp [f+1] ; q++) parent [Child [q]] = f ;
+    // children have smaller indices than parents in the reference's postordered front tree; fall back to
+    // repeated passes otherwise
+    bool monotone = true ;
+    for (I64 f = 0 ; f < nf ; f++) if (parent [f] >= 0 && parent [f] <= f) monotone = false ;
+    auto weight = [&] (I64 f) { const double fn = (double) (Rp [f+1] - Rp [f]), fm = (double) std::max<int64_t> (Fm [f], 1) ; return fm * fn * std::min (fm, fn) + 1.0 ; } ;
+    if (!monotone) return STMQR_OK ;        // keep the top of the tree on GPU 0 (still a valid ownership)
+    for (I64 f = 0 ; f < nf ; f++) { sub [f] += weight (f) ; if (parent [f] >= 0) sub [parent [f]] += sub [f] ; }
+    for (I64 f = 0 ; f < nf ; f++)
+    {
+        if (!top [f]) continue ;
+        I64 best = -1 ;
+        for (I64 q = Childp [f] ; q < Childp [f+1] ; q++) { const I64 c = Child [q] ; if (best < 0 || sub [c] > sub [best]) best = c ; }
+        owner [f] = (best >= 0) ? owner [best] : 0 ;     // (children come first: their owners are final)
+    }
     return STMQR_OK ;
 }
 
@@ -827,6 +983,7 @@ void stmqr_b200_destroy (stmqr_handle h)
     if (!h) return ;
     if (h->host_only) { delete h ; return ; }
     cudaSetDevice (h->device) ;
+    if (h->transport) { delete (Transport *) h->transport ; h->transport = nullptr ; }
     free_all (h) ;
     if (h->ev0) cudaEventDestroy (h->ev0) ;
     if (h->ev1) cudaEventDestroy (h->ev1) ;
@@ -993,6 +1150,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     for (I64 f = 0 ; f < nf ; f++) byLevel [level [f]].push_back ((I32) f) ;
     h->ls_all = LevelSet () ; h->ls_sub = LevelSet () ; h->ls_top = LevelSet () ;
     h->h_parent = parent ; h->nparts = 1 ; h->mypart = 0 ; h->h_owner.clear () ; h->h_istop.clear () ;
+    h->h_level = level ; h->ls_mine = LevelSet () ; h->xedges.clear () ; h->xall_c.clear () ; h->xall_src.clear () ; h->xall_dst.clear () ;
     h->Fcap = 0 ; h->maxLevelWidth = 0 ;
     // the fused shared-memory path of the small fronts (off under debug capture: the assembled F of
     // every front is tapped from the front arena)
@@ -1003,7 +1161,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     for (I32 l = 0 ; l < nlev ; l++)
     {
         auto &v = byLevel [l] ;
-        Level L ; L.first = (I32) h->ls_all.fronts.size () ;
+        Level L ; L.first = (I32) h->ls_all.fronts.size () ; L.glevel = l ;
         finish_level (L, v, Rp, FmB, h->small_cap_used, h->wide_rows) ;
         I64 off = 0 ;
         for (I32 f : v)
@@ -1115,7 +1273,8 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     ALLOC (N.Cmap, rjsize) ;
     ALLOC (N.rowpos, m) ;
     ALLOC (N.Hii, hisize) ;
-    ALLOC (N.Hm, nf) ; ALLOC (N.Hr, nf) ; ALLOC (N.Cm, nf) ; ALLOC (N.rank, nf) ;
+    ALLOC (N.Hm, 3 * std::max<I64> (nf, 1)) ; N.Hr = N.Hm + std::max<I64> (nf, 1) ; N.Cm = N.Hr + std::max<I64> (nf, 1) ;   // one block: merged over the GPUs by ONE all-reduce
+    ALLOC (N.rank, nf) ;
     ALLOC (N.colp, rjsize) ;
     ALLOC (N.rsize, nf) ; ALLOC (N.Roff, nf) ;
     ALLOC (N.Rdead, n) ;
@@ -1248,6 +1407,8 @@ int stmqr_b200_factorize_begin (stmqr_handle h, double tol, int64_t ntol)
     h->factorized = false ;
     h->htable_valid = false ;
     h->rcount_econ = h->rcount_nnz = -1 ;
+    for (cudaEvent_t e : h->evLevelT) cudaEventDestroy (e) ;
+    h->evLevelT.clear () ; h->lvlNote.clear () ;
     CK (cudaEventRecord (h->ev0, st)) ;
     CK (cudaMemsetAsync (N.Rdead, 0, std::max<I64> (h->n, 1), st)) ;
     CK (cudaMemsetAsync (N.rcursor, 0, sizeof (unsigned long long), st)) ;
@@ -1284,18 +1445,15 @@ int stmqr_b200_factorize_begin (stmqr_handle h, double tol, int64_t ntol)
 }
 
 // part: 0 = every front (one GPU), 1 = the etree subtrees this GPU owns, 2 = the top of the tree
-int stmqr_b200_factorize_levels (stmqr_handle h, int part)
+// one etree level of the level set LS on this handle's streams (everything asynchronous except the one small
+// read-back on levels with very large fronts)
+static int run_level (stmqr_handle h, const LevelSet &LS, const Level &Lv, long long levelno)
 {
-    if (!h || !h->analyzed || !h->have_matrix) return fail (h, STMQR_ERR_INVALID, "factorize_levels: not ready") ;
-    if (part != 0 && h->nparts <= 1) return fail (h, STMQR_ERR_INVALID, "factorize_levels: no partition set") ;
-    cudaSetDevice (h->device) ;
     cudaStream_t st = h->stream, st2 = h->stream2 ;
     DSym &S = h->S ; DNum &N = h->N ;
-    const LevelSet &LS = (part == 0) ? h->ls_all : ((part == 1) ? h->ls_sub : h->ls_top) ;
     const double tol = h->cur_tol ; const I64 ntol = h->cur_ntol ;
     const int nc_update = (h->opt.reserved >> 8) & 0xff ;   // 0 auto, 2 or 4: ring stages of the update kernel
     const int PB = (h->opt.panel > 0 && h->opt.panel <= PANEL_MAX) ? h->opt.panel : PANEL_MAX ;
-    long long levelno = -1 ;
     static const bool level_times = getenv ("STMQR_B200_LEVEL_TIMES") != nullptr ;
     auto mark_level = [&] (const std::string &note) {
         if (!level_times) return ;
@@ -1304,11 +1462,8 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
         cudaEventRecord (e, st) ;
         h->evLevelT.push_back (e) ; h->lvlNote.push_back (note) ;
     } ;
-    if (level_times && part != 2) { for (cudaEvent_t e : h->evLevelT) cudaEventDestroy (e) ; h->evLevelT.clear () ; h->lvlNote.clear () ; }
-    mark_level ("start") ;
-    for (const Level &Lv : LS.levels)
+    if (level_times && h->evLevelT.empty ()) mark_level ("start") ;
     {
-        levelno++ ;
         h->curtag = levelno << 32 ;
         const I32 *fr = LS.d_fronts + Lv.first ;
         const I32 nbig = Lv.nbig ;
@@ -1644,7 +1799,22 @@ int stmqr_b200_factorize_levels (stmqr_handle h, int part)
             h->scv.notify_one () ;
         }
     }
+    return STMQR_OK ;
+}
 
+int stmqr_b200_factorize_levels (stmqr_handle h, int part)
+{
+    if (!h || !h->analyzed || !h->have_matrix) return fail (h, STMQR_ERR_INVALID, "factorize_levels: not ready") ;
+    if (part != 0 && h->nparts <= 1) return fail (h, STMQR_ERR_INVALID, "factorize_levels: no partition set") ;
+    cudaSetDevice (h->device) ;
+    const LevelSet &LS = (part == 0) ? h->ls_all : ((part == 1) ? h->ls_sub : h->ls_top) ;
+    long long levelno = -1 ;
+    for (const Level &Lv : LS.levels)
+    {
+        levelno++ ;
+        const int s = run_level (h, LS, Lv, levelno) ;
+        if (s != STMQR_OK) return s ;
+    }
     return STMQR_OK ;
 }
 
@@ -2003,6 +2173,239 @@ int stmqr_b200_set_partition (stmqr_handle h, int nparts, int mypart, const int3
         if (!h->host_only) CK (cudaMemcpyAsync (h->d_Coff, h->h_Coff.data (), (size_t) nf * sizeof (I64), cudaMemcpyHostToDevice, h->stream)) ;
     }
     if (!h->host_only) CK (cudaStreamSynchronize (h->stream)) ;
+    return STMQR_OK ;
+}
+
+// ---- general ownership: every front on its owner GPU, blocks move after the child's level ---------------
+int stmqr_b200_map_fronts (const stmqr_symbolic_view *sym, int nparts, int32_t *owner)
+{
+    if (!sym || !sym->Childp || !sym->Child || !sym->Rp || !sym->Fm || !owner || nparts < 1) return STMQR_ERR_INVALID ;
+    return map_fronts (sym->nf, sym->Childp, sym->Child, sym->Super, sym->Rp, sym->Fm, nparts, owner) ;
+}
+
+int stmqr_b200_set_ownership (stmqr_handle h, int nparts, int mypart, const int32_t *owner)
+{
+    if (!h || !h->analyzed || nparts < 1 || mypart < 0 || mypart >= nparts || !owner)
+        return fail (h, STMQR_ERR_INVALID, "set_ownership: analyze first; 0 <= mypart < nparts") ;
+    if (!h->host_only) cudaSetDevice (h->device) ;
+    const I64 nf = h->nf ;
+    h->nparts = nparts ; h->mypart = mypart ;
+    h->h_owner.assign (owner, owner + nf) ;
+    h->h_istop.assign ((size_t) nf, 0) ;
+    std::vector<unsigned char> owned ((size_t) std::max<I64> (nf, 1), 0) ;
+    for (I64 f = 0 ; f < nf ; f++)
+    {
+        if (owner [f] < 0 || owner [f] >= nparts) return fail (h, STMQR_ERR_INVALID, "set_ownership: owner out of range") ;
+        owned [f] = (owner [f] == mypart) ;
+    }
+    filter_levels (h->ls_all, owned, h->h_Rp, h->h_FmB, h->small_cap_used, h->wide_rows, h->ls_mine) ;
+    h->ls_sub = LevelSet () ; h->ls_top = LevelSet () ;
+    // the blocks that move: child and parent on different GPUs, after the child's level, sorted by front
+    const I64 nlev = (I64) h->ls_all.levels.size () ;
+    h->xedges.assign ((size_t) nlev, std::vector<int> ()) ;
+    h->xall_c.clear () ; h->xall_src.clear () ; h->xall_dst.clear () ;
+    for (I64 c = 0 ; c < nf ; c++)
+    {
+        const I32 p = h->h_parent [c] ;
+        if (p < 0 || owner [p] == owner [c]) continue ;
+        h->xedges [h->h_level [c]].push_back ((int) h->xall_c.size ()) ;
+        h->xall_c.push_back ((I32) c) ; h->xall_src.push_back (owner [c]) ; h->xall_dst.push_back (owner [p]) ;
+    }
+    // contribution-block arena for this GPU's schedule: per etree level, the children of my fronts are
+    // consumed, my fronts' blocks are packed, then the blocks arriving from other GPUs are placed.  (A block
+    // whose parent lives elsewhere is kept: the copy that takes it away is asynchronous.)
+    if (!(h->opt.reserved & 64))
+    {
+        ArenaReplay A ;
+        std::vector<unsigned char> live ((size_t) std::max<I64> (nf, 1), 0) ;
+        std::fill (h->h_Coff.begin (), h->h_Coff.end (), (I64) 0) ;
+        size_t li = 0 ;
+        for (I64 gl = 0 ; gl < nlev ; gl++)
+        {
+            if (li < h->ls_mine.levels.size () && h->ls_mine.levels [li].glevel == gl)
+            {
+                const Level &Lv = h->ls_mine.levels [li++] ;
+                for (I32 i = 0 ; i < Lv.count ; i++)
+                {
+                    const I32 f = h->ls_mine.fronts [Lv.first + i] ;
+                    for (I32 q = h->h_Childp [f] ; q < h->h_Childp [f+1] ; q++)
+                    {
+                        const I32 c = h->h_Child [q] ;
+                        if (live [c]) { A.release (h->h_Coff [c], h->h_Csize [c]) ; live [c] = 0 ; }
+                    }
+                }
+                for (I32 i = 0 ; i < Lv.count ; i++)
+                {
+                    const I32 f = h->ls_mine.fronts [Lv.first + i] ;
+                    if (h->h_Csize [f] > 0) { h->h_Coff [f] = A.alloc (h->h_Csize [f]) ; live [f] = 1 ; }
+                }
+            }
+            for (int e : h->xedges [(size_t) gl])
+                if (h->xall_dst [e] == mypart)
+                {
+                    const I32 c = h->xall_c [e] ;
+                    if (h->h_Csize [c] > 0) { h->h_Coff [c] = A.alloc (h->h_Csize [c]) ; live [c] = 1 ; }
+                }
+            // (blocks sent away stay allocated: live[] is only cleared by a local parent)
+            for (int e : h->xedges [(size_t) gl]) if (h->xall_src [e] == mypart) live [h->xall_c [e]] = 0 ;
+        }
+        const I64 cap = A.high + 2 ;
+        h->Ccap = cap ;
+        if (h->host_only)
+        {
+            h->device_bytes += (size_t) std::max<I64> (0, cap - h->C_alloc) * sizeof (double) ;
+            h->C_alloc = std::max (h->C_alloc, cap) ;
+        }
+        else if (cap > h->C_alloc)
+        {
+            for (auto &pp : h->allocs) if (pp == (void *) h->N.C) { cudaFree (pp) ; pp = nullptr ; }
+            h->device_bytes -= (size_t) h->C_alloc * sizeof (double) ;
+            h->N.C = nullptr ;
+            double *nc = nullptr ;
+            if (cudaMalloc ((void **) &nc, (size_t) cap * sizeof (double)) != cudaSuccess)
+                return fail (h, STMQR_ERR_OUT_OF_MEMORY, "set_ownership: contribution-block arena") ;
+            for (auto &pp : h->allocs) if (pp == nullptr) { pp = (void *) nc ; break ; }
+            h->N.C = nc ; h->C_alloc = cap ;
+            h->device_bytes += (size_t) cap * sizeof (double) ;
+        }
+        if (!h->host_only) CK (cudaMemcpyAsync (h->d_Coff, h->h_Coff.data (), (size_t) nf * sizeof (I64), cudaMemcpyHostToDevice, h->stream)) ;
+    }
+    UPLOAD (h->ls_mine.d_fronts, h->ls_mine.fronts) ;
+    if (nparts > 1) { UPLOAD (h->d_owned, owned) ; h->N.owned = h->d_owned ; }
+    else { h->d_owned = nullptr ; h->N.owned = nullptr ; }
+    if (!h->host_only) CK (cudaStreamSynchronize (h->stream)) ;
+    return STMQR_OK ;
+}
+
+int stmqr_b200_nccl_unique_id (void *id128)
+{
+    if (!id128) return STMQR_ERR_INVALID ;
+    if (!g_nccl.load ()) return STMQR_ERR_INVALID ;
+    ncclUniqueId id ;
+    if (g_nccl.GetUniqueId (&id) != ncclSuccess) return STMQR_ERR_CUDA ;
+    static_assert (sizeof (ncclUniqueId) == 128, "ncclUniqueId") ;
+    memcpy (id128, &id, 128) ;
+    return STMQR_OK ;
+}
+
+int stmqr_b200_comm_init (stmqr_handle h, int nranks, int rank, const void *id128)
+{
+    if (!h || h->host_only || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return STMQR_ERR_INVALID ;
+    if (!g_nccl.load ()) return fail (h, STMQR_ERR_INVALID, "comm_init: libnccl.so.2 not found") ;
+    cudaSetDevice (h->device) ;
+    if (h->transport) { delete (Transport *) h->transport ; h->transport = nullptr ; }
+    NcclTransport *t = new NcclTransport ;
+    ncclUniqueId id ;
+    memcpy (&id, id128, 128) ;
+    t->nr = nranks ; t->me = rank ;
+    const ncclResult_t r = g_nccl.CommInitRank (&t->comm, nranks, id, rank) ;
+    if (r != ncclSuccess)
+    {
+        const std::string msg = std::string ("ncclCommInitRank: ") + g_nccl.GetErrorString (r) ;
+        t->comm = nullptr ; delete t ;
+        return fail (h, STMQR_ERR_CUDA, msg) ;
+    }
+    h->transport = t ;
+    return STMQR_OK ;
+}
+
+// N handles of this process as one group (peer copies; the handles may sit on different devices or, for
+// tests, on the same one).  The group owns nothing but the synchronisation state.
+int stmqr_b200_peer_group_create (stmqr_handle *hs, int n, void **group)
+{
+    if (!hs || n < 1 || !group) return STMQR_ERR_INVALID ;
+    PeerGroup *g = new PeerGroup ;
+    for (int i = 0 ; i < n ; i++)
+    {
+        stmqr_handle h = hs [i] ;
+        if (!h || h->host_only) { delete g ; return STMQR_ERR_INVALID ; }
+        g->hs.push_back (h) ;
+    }
+    for (int i = 0 ; i < n ; i++)
+    {
+        stmqr_handle h = hs [i] ;
+        cudaSetDevice (h->device) ;
+        for (int j = 0 ; j < n ; j++)
+            if (hs [j]->device != h->device)
+            {
+                int can = 0 ;
+                cudaDeviceCanAccessPeer (&can, h->device, hs [j]->device) ;
+                if (can) { cudaError_t e = cudaDeviceEnablePeerAccess (hs [j]->device, 0) ; if (e != cudaSuccess) cudaGetLastError () ; }
+            }
+        if (h->transport) delete (Transport *) h->transport ;
+        PeerTransport *t = new PeerTransport ;
+        t->grp = g ; t->me = i ;
+        if (cudaEventCreateWithFlags (&t->evReady, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags (&t->evDone, cudaEventDisableTiming) != cudaSuccess) { delete t ; delete g ; return STMQR_ERR_CUDA ; }
+        h->transport = t ;
+    }
+    *group = g ;
+    return STMQR_OK ;
+}
+
+void stmqr_b200_peer_group_destroy (void *group)
+{
+    PeerGroup *g = (PeerGroup *) group ;
+    if (!g) return ;
+    for (stmqr_handle h : g->hs) if (h->transport) { cudaSetDevice (h->device) ; delete (Transport *) h->transport ; h->transport = nullptr ; }
+    delete g ;
+}
+
+// The numeric phase of ONE GPU of a group (set_ownership + a transport first); every GPU of the group calls
+// it at the same time (one process per GPU with NCCL, or one host thread per handle with peer copies).
+int stmqr_b200_factorize_dist (stmqr_handle h, double tol, int64_t ntol, stmqr_numeric_info *info)
+{
+    if (!h || !h->analyzed || !h->have_matrix) return fail (h, STMQR_ERR_INVALID, "factorize_dist: analyze and upload_matrix first") ;
+    Transport *T = (Transport *) h->transport ;
+    if (!T || T->nranks () != h->nparts || T->rank () != h->mypart || h->xedges.size () != h->ls_all.levels.size ())
+        return fail (h, STMQR_ERR_INVALID, "factorize_dist: set_ownership and a transport of the same size first") ;
+    int s ;
+    auto tfail = [&] (int code) { return fail (h, code, "factorize_dist: " + T->error ()) ; } ;
+    if ((s = stmqr_b200_factorize_begin (h, tol, ntol)) != STMQR_OK) return s ;
+    cudaSetDevice (h->device) ;
+    DNum &N = h->N ;
+    const I64 nlev = (I64) h->ls_all.levels.size () ;
+    size_t li = 0 ;
+    std::vector<XEdge> edges ;
+    for (I64 gl = 0 ; gl < nlev ; gl++)
+    {
+        if (li < h->ls_mine.levels.size () && h->ls_mine.levels [li].glevel == gl)
+        {
+            if ((s = run_level (h, h->ls_mine, h->ls_mine.levels [li], gl)) != STMQR_OK) return s ;
+            li++ ;
+        }
+        if (h->xedges [(size_t) gl].empty ()) continue ;
+        edges.clear () ;
+        for (int e : h->xedges [(size_t) gl]) edges.push_back (XEdge {h->xall_c [e], h->xall_src [e], h->xall_dst [e]}) ;
+        if ((s = T->exchange (h, edges, (I32) gl)) != STMQR_OK) return tfail (s) ;
+    }
+    // merge the integer side outputs (every entry has one writer, the others hold the neutral element)
+    if ((s = T->allreduce (h, N.Hm, 3 * std::max<I64> (h->nf, 1), X_I32, true)) != STMQR_OK) return tfail (s) ;
+    if ((s = T->allreduce (h, N.Rdead, h->n, X_I8, true)) != STMQR_OK) return tfail (s) ;
+    if ((s = stmqr_b200_factorize_hpinv_a (h)) != STMQR_OK) return s ;
+    if ((s = T->allreduce (h, N.W, h->m, X_I32, true)) != STMQR_OK) return tfail (s) ;
+    if ((s = T->allreduce (h, N.sumrank, 1, X_I32, false)) != STMQR_OK) return tfail (s) ;
+    if ((s = T->allreduce (h, N.sumrank + 1, 2, X_I32, true)) != STMQR_OK) return tfail (s) ;
+    if ((s = T->allreduce (h, N.flops, 3, X_F64, false)) != STMQR_OK) return tfail (s) ;
+    return stmqr_b200_factorize_hpinv_b (h, info) ;
+}
+
+// All handles of a peer group, one host thread each.
+int stmqr_b200_factorize_multi (void *group, double tol, int64_t ntol, stmqr_numeric_info *infos)
+{
+    PeerGroup *g = (PeerGroup *) group ;
+    if (!g || g->hs.empty ()) return STMQR_ERR_INVALID ;
+    const int n = (int) g->hs.size () ;
+    { std::lock_guard<std::mutex> lk (g->mu) ; g->failed = 0 ; g->waiting = 0 ; }
+    std::vector<int> st ((size_t) n, STMQR_OK) ;
+    std::vector<std::thread> th ;
+    for (int i = 0 ; i < n ; i++)
+        th.emplace_back ([&, i] {
+            st [i] = stmqr_b200_factorize_dist (g->hs [i], tol, ntol, infos ? infos + i : nullptr) ;
+            if (st [i] != STMQR_OK) g->abort () ;       // the others must not wait for this handle at a barrier
+        }) ;
+    for (auto &t : th) t.join () ;
+    for (int i = 0 ; i < n ; i++) if (st [i] != STMQR_OK) return st [i] ;
     return STMQR_OK ;
 }
 

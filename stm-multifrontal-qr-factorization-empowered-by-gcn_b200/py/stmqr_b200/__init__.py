@@ -103,6 +103,9 @@ EXPORTS = (
     "stmqr_b200_create_planner", "stmqr_b200_plan_info",
     "stmqr_b200_upload_values", "stmqr_b200_refactorize_values",
     "stmqr_b200_qmult", "stmqr_b200_rsolve", "stmqr_b200_solve_ls", "stmqr_b200_rcount", "stmqr_b200_rconvert",
+    "stmqr_b200_map_fronts", "stmqr_b200_set_ownership", "stmqr_b200_nccl_unique_id", "stmqr_b200_comm_init",
+    "stmqr_b200_peer_group_create", "stmqr_b200_peer_group_destroy", "stmqr_b200_factorize_dist",
+    "stmqr_b200_factorize_multi",
 )
 
 _lib = None
@@ -161,6 +164,15 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.stmqr_b200_solve_ls.argtypes = [C.c_void_p, C.c_int64, _f64p, _f64p, _f64p]
     lib.stmqr_b200_rcount.argtypes = [C.c_void_p, C.c_int64, _i64p, _i64p]
     lib.stmqr_b200_rconvert.argtypes = [C.c_void_p, C.c_int64, _i64p, _i64p, _f64p]
+    lib.stmqr_b200_map_fronts.argtypes = [C.POINTER(SymbolicView), C.c_int, C.POINTER(C.c_int32)]
+    lib.stmqr_b200_set_ownership.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32)]
+    lib.stmqr_b200_nccl_unique_id.argtypes = [C.c_void_p]
+    lib.stmqr_b200_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.stmqr_b200_peer_group_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
+    lib.stmqr_b200_peer_group_destroy.argtypes = [C.c_void_p]
+    lib.stmqr_b200_peer_group_destroy.restype = None
+    lib.stmqr_b200_factorize_dist.argtypes = [C.c_void_p, C.c_double, C.c_int64, C.POINTER(NumericInfo)]
+    lib.stmqr_b200_factorize_multi.argtypes = [C.c_void_p, C.c_double, C.c_int64, C.POINTER(NumericInfo)]
     lib.stmqr_b200_create_planner.argtypes = [C.POINTER(C.c_void_p)]
     lib.stmqr_b200_plan_info.argtypes = [C.c_void_p, C.POINTER(PlanInfo), _i64p, _i64p, C.POINTER(C.c_int32)]
     _lib = lib
@@ -236,6 +248,53 @@ def partition_fronts(sym: "Symbolic", nparts: int):
     if st != STMQR_OK:
         raise RuntimeError(f"partition_fronts: {ERRORS.get(st, st)}")
     return owner[:sym.nf], top[:sym.nf]
+
+
+def map_fronts(sym: "Symbolic", nparts: int) -> np.ndarray:
+    """Host-only, deterministic owner of every front over nparts GPUs (subtrees below the cut dealt largest
+    first; a front above the cut on the GPU of its heaviest child)."""
+    lib = load_library()
+    owner = np.zeros(max(sym.nf, 1), np.int32)
+    st = lib.stmqr_b200_map_fronts(C.byref(sym.view), nparts, owner.ctypes.data_as(C.POINTER(C.c_int32)))
+    if st != STMQR_OK:
+        raise RuntimeError(f"map_fronts: {ERRORS.get(st, st)}")
+    return owner[:sym.nf]
+
+
+def nccl_unique_id() -> bytes:
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    st = lib.stmqr_b200_nccl_unique_id(buf)
+    if st != STMQR_OK:
+        raise RuntimeError(f"nccl_unique_id: {ERRORS.get(st, st)} (libnccl.so.2 not loadable?)")
+    return buf.raw
+
+
+class PeerGroup:
+    """N engines of this process as one multi-GPU group (peer copies, one host thread per engine inside
+    factorize()); the engines may sit on different devices or, for tests, on the same one."""
+
+    def __init__(self, engines):
+        self.lib = load_library()
+        self.engines = list(engines)
+        arr = (C.c_void_p * len(self.engines))(*[e.h for e in self.engines])
+        self.g = C.c_void_p()
+        st = self.lib.stmqr_b200_peer_group_create(arr, len(self.engines), C.byref(self.g))
+        if st != STMQR_OK:
+            raise EngineError(f"peer_group_create: {ERRORS.get(st, st)}")
+
+    def factorize(self, tol: float, ntol: int):
+        infos = (NumericInfo * len(self.engines))()
+        st = self.lib.stmqr_b200_factorize_multi(self.g, tol, ntol, infos)
+        if st != STMQR_OK:
+            msgs = [self.lib.stmqr_b200_last_error(e.h) for e in self.engines]
+            raise EngineError(f"factorize_multi: {ERRORS.get(st, st)}: {[m.decode() for m in msgs if m]}")
+        return list(infos)
+
+    def close(self):
+        if self.g:
+            self.lib.stmqr_b200_peer_group_destroy(self.g)
+            self.g = C.c_void_p()
 
 
 class Csc:
@@ -391,6 +450,19 @@ class Engine:
         self._check(self.lib.stmqr_b200_set_partition(self.h, nparts, mypart,
                                                       owner.ctypes.data_as(C.POINTER(C.c_int32)),
                                                       is_top.ctypes.data_as(C.POINTER(C.c_int32))), "set_partition")
+
+    def set_ownership(self, nparts: int, mypart: int, owner):
+        owner = np.ascontiguousarray(owner, np.int32)
+        self._check(self.lib.stmqr_b200_set_ownership(self.h, nparts, mypart,
+                                                      owner.ctypes.data_as(C.POINTER(C.c_int32))), "set_ownership")
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        self._check(self.lib.stmqr_b200_comm_init(self.h, nranks, rank, C.c_char_p(unique_id)), "comm_init")
+
+    def factorize_dist(self, tol: float, ntol: int) -> NumericInfo:
+        info = NumericInfo()
+        self._check(self.lib.stmqr_b200_factorize_dist(self.h, tol, ntol, C.byref(info)), "factorize_dist")
+        return info
 
     def device_array(self, which: int):
         """(device pointer, count, element bytes) of one of the arrays merged over the GPUs"""

@@ -220,6 +220,53 @@ class PartitionedFactorization:
         return infos
 
 
+class DistFactorization:
+    """One GPU's share of the multi-GPU numeric phase with the data plane in C (csrc/multigpu.cuh), one process
+    per GPU under torchrun: torch.distributed only carries the 128-byte NCCL unique id to the other ranks; the
+    contribution blocks, the row ids and the merges travel through ncclSend / ncclRecv / ncclAllReduce issued by
+    the C library on the engine's own stream, with no host synchronisation between the etree levels."""
+
+    def __init__(self, engine: Engine, sym: Symbolic, device=None):
+        import torch
+        import torch.distributed as dist
+        from . import map_fronts, nccl_unique_id
+        self.engine = engine
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.owner = map_fronts(sym, self.world)
+        engine.set_ownership(self.world, self.rank, self.owner)
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if self.rank == 0:
+            t.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, src=0)
+        engine.comm_init(self.world, self.rank, bytes(t.cpu().numpy().tobytes()))
+
+    def factorize(self, tol: float, ntol: int) -> NumericInfo:
+        return self.engine.factorize_dist(tol, ntol)
+
+
+def gather_numeric(sym: Symbolic, owner: np.ndarray, num, info):
+    """rank 0 <- every rank's download (torch.distributed.gather_object), merged into one qr_numeric-shaped
+    object; None on the other ranks.  For parity checks on small inputs."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    payload = (num, {k: getattr(info, k) for k in ("rank", "rank1", "maxfrank", "maxfm", "rh_size", "flops")})
+    out = [None] * world if rank == 0 else None
+    dist.gather_object(payload, out, dst=0)
+    if rank != 0:
+        return None
+
+    class _I:
+        pass
+    nums, infos = {}, {}
+    for p, (n, i) in enumerate(out):
+        nums[p] = n
+        o = _I()
+        o.__dict__.update(i)
+        infos[p] = o
+    return merge_numerics(sym, owner, nums, infos)
+
+
 def merge_numerics(sym: Symbolic, owner: np.ndarray, nums: dict, infos: dict):
     """Host-side gather of the per-GPU downloads into ONE qr_numeric-shaped object (every front's
     packed R+H, HStair, HTau and Hii come from the GPU that owns it; Hm, Hr, HPinv, Rdead are

@@ -92,3 +92,53 @@ def test_planner_has_no_compute_path():
     with pytest.raises(sq.EngineError):
         p.factorize_resident(tol, ntol)
     p.close()
+
+
+@pytest.mark.parametrize("case,nparts", [("lap2d_24_metis", 2), ("lap3d_8_metis", 4), ("lap3d_8_metis", 8),
+                                         ("dwt_992_metis", 3)])
+def test_ownership_map_and_arena(case, nparts):
+    """General ownership (stmqr_b200_map_fronts) + the per-GPU arena plan of stmqr_b200_set_ownership: whole
+    subtrees below the cut stay on one GPU, every GPU's blocks (its own and the ones it receives after the
+    child's level) never overlap while alive."""
+    sym, *_ = R.load_golden(case)
+    owner = sq.map_fronts(sym, nparts)
+    assert np.array_equal(owner, sq.map_fronts(sym, nparts))                  # deterministic
+    assert owner.min() >= 0 and owner.max() < nparts
+    _, is_top = sq.partition_fronts(sym, nparts)
+    par = parents(sym)
+    for c in range(sym.nf):
+        if par[c] >= 0 and not is_top[par[c]]:
+            assert owner[c] == owner[par[c]]                                   # subtrees below the cut are whole
+    if nparts > 1 and is_top.any():
+        assert len(set(owner[is_top.astype(bool)])) >= 1
+    for part in range(nparts):
+        p = sq.Planner()
+        p.analyze(sym)
+        p.set_ownership(nparts, part, owner)
+        info, coff, csize, level = p.plan_info()
+        mine = owner == part
+        # a received block is placed after the child's level and read by its parent's level on this GPU
+        recv = np.array([par[c] >= 0 and owner[par[c]] == part and owner[c] != part for c in range(sym.nf)])
+        alive = mine | recv
+        assert (coff[alive] + csize[alive] <= info.C_doubles).all()
+        # a block that was sent away is never recycled: give it an infinite life on the sender
+        sent = np.array([par[c] >= 0 and owner[par[c]] != part and owner[c] == part for c in range(sym.nf)])
+        birth = level.astype(np.int64)
+        check_no_overlap_general(sym, coff, csize, birth, alive, sent, par, level)
+        p.close()
+
+
+def check_no_overlap_general(sym, coff, csize, birth, alive, sent, par, level):
+    ev = []
+    for c in np.nonzero(alive)[0]:
+        if csize[c] <= 0:
+            continue
+        death = 10 ** 9 if (sent[c] or par[c] < 0) else int(level[par[c]])
+        ev.append((int(coff[c]), int(coff[c] + csize[c]), int(birth[c]), death, int(c)))
+    ev.sort()
+    for i, (a0, a1, b, d, c) in enumerate(ev):
+        j = i + 1
+        while j < len(ev) and ev[j][0] < a1:
+            _, _, b2, d2, c2 = ev[j]
+            assert d <= b2 or d2 <= b, f"blocks of fronts {c} and {c2} overlap while both are alive"
+            j += 1
