@@ -94,6 +94,7 @@ int rh_set_backend (int backend, const char *dropin_path)
     g_backend = backend ;
     return 0 ;
 }
+int rh_get_backend (void) { return g_backend ; }
 void rh_set_tap (int on) { g_tap = on ; }
 double rh_last_fac_seconds (void) { return g_last_fac_seconds ; }
 void rh_set_blas_threads (int n) { openblas_set_num_threads (n) ; }

@@ -857,6 +857,7 @@ int PeerTransport::allreduce (stmqr_handle h, void *p, I64 count, XType t, bool 
         CK (cudaStreamWaitEvent (st, ((PeerTransport *) root->transport)->evDone, 0)) ;
         CK (cudaMemcpyPeerAsync (p, h->device, root->xptr, root->device, bytes, st)) ;
     }
+    grp->barrier () ;                       // everybody has read handle 0's pointer and event: it may start the next one
     return STMQR_OK ;
 }
 
@@ -2360,24 +2361,37 @@ int stmqr_b200_factorize_dist (stmqr_handle h, double tol, int64_t ntol, stmqr_n
     if (!T || T->nranks () != h->nparts || T->rank () != h->mypart || h->xedges.size () != h->ls_all.levels.size ())
         return fail (h, STMQR_ERR_INVALID, "factorize_dist: set_ownership and a transport of the same size first") ;
     int s ;
-    auto tfail = [&] (int code) { return fail (h, code, "factorize_dist: " + T->error ()) ; } ;
+    auto tfail = [&] (int code) { return T->error ().empty () ? code : fail (h, code, "factorize_dist: " + T->error ()) ; } ;
     if ((s = stmqr_b200_factorize_begin (h, tol, ntol)) != STMQR_OK) return s ;
     cudaSetDevice (h->device) ;
     DNum &N = h->N ;
     const I64 nlev = (I64) h->ls_all.levels.size () ;
     size_t li = 0 ;
     std::vector<XEdge> edges ;
+    // STMQR_B200_DEBUG_SYNC=1: synchronise and check after every stage (names the stage of an asynchronous fault)
+    static const bool dbg_sync = getenv ("STMQR_B200_DEBUG_SYNC") != nullptr ;
+    auto stage = [&] (const char *what, I64 gl) -> int {
+        if (!dbg_sync) return STMQR_OK ;
+        cudaError_t e1 = cudaStreamSynchronize (h->stream), e2 = cudaStreamSynchronize (h->stream2), e3 = cudaGetLastError () ;
+        const cudaError_t e = (e1 != cudaSuccess) ? e1 : ((e2 != cudaSuccess) ? e2 : e3) ;
+        if (e == cudaSuccess) return STMQR_OK ;
+        return fail (h, STMQR_ERR_CUDA, std::string ("factorize_dist: part ") + std::to_string (h->mypart) + " after " + what +
+            " of level " + std::to_string (gl) + ": " + cudaGetErrorString (e)) ;
+    } ;
+    if ((s = stage ("begin", -1)) != STMQR_OK) return s ;
     for (I64 gl = 0 ; gl < nlev ; gl++)
     {
         if (li < h->ls_mine.levels.size () && h->ls_mine.levels [li].glevel == gl)
         {
             if ((s = run_level (h, h->ls_mine, h->ls_mine.levels [li], gl)) != STMQR_OK) return s ;
             li++ ;
+            if ((s = stage ("the kernels", gl)) != STMQR_OK) return s ;
         }
         if (h->xedges [(size_t) gl].empty ()) continue ;
         edges.clear () ;
         for (int e : h->xedges [(size_t) gl]) edges.push_back (XEdge {h->xall_c [e], h->xall_src [e], h->xall_dst [e]}) ;
         if ((s = T->exchange (h, edges, (I32) gl)) != STMQR_OK) return tfail (s) ;
+        if ((s = stage ("the exchange", gl)) != STMQR_OK) return s ;
     }
     // merge the integer side outputs (every entry has one writer, the others hold the neutral element)
     if ((s = T->allreduce (h, N.Hm, 3 * std::max<I64> (h->nf, 1), X_I32, true)) != STMQR_OK) return tfail (s) ;

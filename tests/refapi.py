@@ -255,6 +255,7 @@ class Reference:
 
         self.L.rh_set_probe.argtypes = [C.c_void_p]
         self.L.rh_set_probe(C.cast(probe, C.c_void_p))
+        before = int(self.L.rh_get_backend())               # (process-wide switch of the harness: put it back)
         assert self.L.rh_set_backend(2, None) == 0
         try:
             self.L.rh_set_blas_threads(1)
@@ -262,7 +263,9 @@ class Reference:
             QR = self.L.rh_sparseqr(self.cc, A, ordering_arg, tol, 1.0, 0)
             assert not QR
         finally:
-            self.L.rh_set_backend(0, None)
+            self.L.rh_set_backend(before if before in (0, 2) else 0, None)
+            if before == 1:
+                self.set_backend("b200")
             self.L.rh_set_probe(None)
             self.L.rh_clear_status(self.cc)
         if not got:

@@ -76,3 +76,34 @@ def test_header_is_plain_c(tmp_path):
     out = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only",
                           "-I", os.path.join(R.ROOT, "include"), str(src)], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
+
+
+def _static_link(tmp_path):
+    """qrtest of the reference linked STATICALLY (its stock build: archives + driver) with the drop-in object in
+    place of the one renamed symbol -- host/link_static.sh, INTEGRATION.md Option C."""
+    import subprocess
+    import refapi as R
+    obj = os.path.join(R.REF_DIR, "obj")
+    qrtest_c = "/root/reference/STMMQR/test/qrtest.c"
+    if not (os.path.isdir(obj) and os.path.exists(qrtest_c)):
+        pytest.skip("needs the reference sources and oracle/_ref/obj (this container)")
+    blas = open(os.path.join(R.REF_DIR, "blas_path.txt")).read().strip()
+    shim = os.path.join(R.ROOT, "oracle", "shim")
+    env = dict(os.environ, DRIVER_CFLAGS=f"-include {shim}/tpsm_platform.h -I{shim}")
+    out = subprocess.run(["bash", os.path.join(R.PKG, "host", "link_static.sh"), obj, qrtest_c, str(tmp_path), blas],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    return os.path.join(str(tmp_path), "qrtest_static")
+
+
+def test_static_link_of_the_dropin(tmp_path):
+    """the statically linked driver defines qr_factorize (drop-in) AND keeps the reference's own numeric phase as
+    qr_factorize_cpu, chunk_getSettings and qr_larftb (SparseQR.h:137,:263; qr_panel still needs the latter)"""
+    import subprocess
+    exe = _static_link(tmp_path)
+    syms = subprocess.run(["nm", exe], capture_output=True, text=True).stdout
+    defined = {ln.split()[-1] for ln in syms.splitlines() if len(ln.split()) == 3 and ln.split()[1] in "TtDdBbCc"}
+    for s in ("qr_factorize", "qr_factorize_cpu", "stmqr_b200_qr_factorize", "chunk_getSettings", "qr_larftb", "SparseQR"):
+        assert s in defined, s
+    undefined = {ln.split()[-1] for ln in syms.splitlines() if len(ln.split()) == 2 and ln.split()[0] == "U"}
+    assert "stmqr_b200_analyze" in undefined and "stmqr_b200_factorize_streamed" in undefined   # from libstmqr_b200.so

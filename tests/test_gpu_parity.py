@@ -223,6 +223,20 @@ def test_qrtest_driver_with_ld_preload(tmp_path):
     assert "res =  2.4e+01" in out.stdout, out.stdout[-2000:]     # STM-MQR.xlsx row 700 / SURVEY.md 4
 
 
+def test_qrtest_driver_statically_linked(tmp_path):
+    """The same driver from a STATIC link of the reference (its stock build) with the drop-in object in place of
+    the one renamed symbol (host/link_static.sh, INTEGRATION.md Option C): LD_PRELOAD is not involved."""
+    import test_abi
+    exe = test_abi._static_link(tmp_path)
+    (tmp_path / "Results").mkdir(exist_ok=True)
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+    env.pop("LD_PRELOAD", None)
+    out = subprocess.run([exe, os.path.join(R.DATA_DIR, "dwt_992.mtx"), "1", "1"], cwd=tmp_path, env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "res =  2.4e+01" in out.stdout, out.stdout[-2000:]
+
+
 @pytest.mark.parametrize("case", ["dwt_992_metis", "lap2d_24_metis", "tall_600x150_colamd"])
 def test_streamed_download_is_identical(engine, case):
     """stmqr_b200_factorize_streamed (R+H blocks copied level by level while later levels run)
