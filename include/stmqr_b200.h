@@ -262,6 +262,11 @@ void stmqr_b200_peer_group_destroy (void *group) ;
 int  stmqr_b200_factorize_dist (stmqr_handle h, double tol, int64_t ntol, stmqr_numeric_info *info) ;
 /* every handle of a peer group, one host thread each; infos [n] (may be NULL) */
 int  stmqr_b200_factorize_multi (void *group, double tol, int64_t ntol, stmqr_numeric_info *infos) ;
+/* collective, after factorize_dist: HStair, HTau, the permuted Hii and the offset of every packed block in its
+ * owner's stack become global on every GPU (the host then needs the integer side from ONE of them);
+ * factorize_multi_ex (..., gather = 1) calls it in every thread */
+int  stmqr_b200_gather_outputs (stmqr_handle h) ;
+int  stmqr_b200_factorize_multi_ex (void *group, double tol, int64_t ntol, stmqr_numeric_info *infos, int gather) ;
 
 #define STMQR_ARRAY_HM    0   /* int32 [nf] */
 #define STMQR_ARRAY_HR    1   /* int32 [nf] */

@@ -211,6 +211,8 @@ struct stmqr_handle_s
     std::vector<I64> h_Foff, h_Coff, h_Csize ;      // h_Csize: bound on the packed size of each contribution block
     I64 Fcap = 0, Ccap = 0, Rcap = 0 ;
     I64 Ccap_all = 0 ;                              // sum of all bounds (what an arena without recycling would need)
+    std::vector<I64> h_Rbound ;                     // bound on the packed R+H size of every front
+    I64 Rcap_owned = 0 ;                            // sum over the fronts this GPU owns (set_ownership), + slack
     I64 *d_Coff = nullptr ;                         // device copy of h_Coff (DSym.Coff)
     I64 C_alloc = 0 ;                               // doubles currently allocated for N.C
     I32 maxLevelWidth = 0 ;
@@ -1105,6 +1107,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
         }
     }
     h->h_Foff.assign ((size_t) nf, 0) ; h->h_Coff.assign ((size_t) nf, 0) ; h->h_Csize.assign ((size_t) nf, 0) ;
+    h->h_Rbound.assign ((size_t) nf, 0) ; h->Rcap_owned = 0 ;
     // ---- contribution-block arena (bound sizes) and R+H arena bound ------------------------------
     // csize bound: qr_analyze's Cm[f] rows by cn columns (SparseQR_analyze.c:536-550).
     // R+H bound per front: sum_j min (max (j+1, Stair_j), fm) with the bound staircase (:559-573).
@@ -1140,6 +1143,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
             }
             if (fm > FmB [f]) FmB [f] = (I32) fm ;     // never trust a smaller bound
             rcap += rh ;
+            h->h_Rbound [(size_t) f] = rh ;
         }
         h->Ccap_all = coff ;
         h->Rcap = rcap + 16 ;
@@ -1429,6 +1433,10 @@ int stmqr_b200_factorize_begin (stmqr_handle h, double tol, int64_t ntol)
         CK (cudaMemsetAsync (N.Hr, 0, std::max<I64> (h->nf, 1) * sizeof (I32), st)) ;
         CK (cudaMemsetAsync (N.Cm, 0, std::max<I64> (h->nf, 1) * sizeof (I32), st)) ;
         CK (cudaMemsetAsync (N.W, 0xff, std::max<I64> (h->m, 1) * sizeof (I32), st)) ;
+        // per-front outputs that stmqr_b200_gather_outputs merges: zero where this GPU does not write
+        CK (cudaMemsetAsync (N.stair, 0, std::max<I64> (h->rjsize, 1) * sizeof (I32), st)) ;
+        CK (cudaMemsetAsync (N.Roff, 0, std::max<I64> (h->nf, 1) * sizeof (I64), st)) ;
+        CK (cudaMemsetAsync (h->d_Hii64, 0, std::max<I64> (h->hisize, 1) * sizeof (I64), st)) ;
     }
     if (h->anz > 0)
     {
@@ -1985,7 +1993,8 @@ int stmqr_b200_refactorize_values (stmqr_handle h, const double *Ax, int64_t nnz
 int stmqr_b200_rh_bound (stmqr_handle h, int64_t *doubles)
 {
     if (!h || !h->analyzed || !doubles) return STMQR_ERR_INVALID ;
-    *doubles = h->Rcap ;
+    // (with an ownership set: only the blocks of this GPU's fronts land in its stack)
+    *doubles = (h->nparts > 1 && h->Rcap_owned > 0) ? h->Rcap_owned : h->Rcap ;
     return STMQR_OK ;
 }
 
@@ -2201,6 +2210,8 @@ int stmqr_b200_set_ownership (stmqr_handle h, int nparts, int mypart, const int3
     }
     filter_levels (h->ls_all, owned, h->h_Rp, h->h_FmB, h->small_cap_used, h->wide_rows, h->ls_mine) ;
     h->ls_sub = LevelSet () ; h->ls_top = LevelSet () ;
+    h->Rcap_owned = 16 ;
+    for (I64 f = 0 ; f < nf ; f++) if (owned [f]) h->Rcap_owned += h->h_Rbound [(size_t) f] ;
     // the blocks that move: child and parent on different GPUs, after the child's level, sorted by front
     const I64 nlev = (I64) h->ls_all.levels.size () ;
     h->xedges.assign ((size_t) nlev, std::vector<int> ()) ;
@@ -2404,8 +2415,31 @@ int stmqr_b200_factorize_dist (stmqr_handle h, double tol, int64_t ntol, stmqr_n
     return stmqr_b200_factorize_hpinv_b (h, info) ;
 }
 
+// After factorize_dist: make the per-front outputs (HStair, HTau, the permuted Hii, the offset of every packed
+// block in its owner's stack) global on every GPU of the group, so that ONE of them can hand the whole integer
+// side of the qr_numeric to the host.  Collective (every GPU of the group calls it).
+int stmqr_b200_gather_outputs (stmqr_handle h)
+{
+    if (!h || !h->factorized) return fail (h, STMQR_ERR_INVALID, "gather_outputs: factorize_dist first") ;
+    Transport *T = (Transport *) h->transport ;
+    if (!T) return fail (h, STMQR_ERR_INVALID, "gather_outputs: no transport") ;
+    cudaSetDevice (h->device) ;
+    int s ;
+    if ((s = T->allreduce (h, h->N.stair, h->rjsize, X_I32, true)) != STMQR_OK) return s ;
+    if ((s = T->allreduce (h, h->N.HTau, h->rjsize, X_F64, false)) != STMQR_OK) return s ;
+    if ((s = T->allreduce (h, h->N.Roff, h->nf, X_I64, true)) != STMQR_OK) return s ;
+    if ((s = T->allreduce (h, h->d_Hii64, h->hisize, X_I64, true)) != STMQR_OK) return s ;
+    CK (cudaStreamSynchronize (h->stream)) ;
+    return STMQR_OK ;
+}
+
 // All handles of a peer group, one host thread each.
 int stmqr_b200_factorize_multi (void *group, double tol, int64_t ntol, stmqr_numeric_info *infos)
+{
+    return stmqr_b200_factorize_multi_ex (group, tol, ntol, infos, 0) ;
+}
+
+int stmqr_b200_factorize_multi_ex (void *group, double tol, int64_t ntol, stmqr_numeric_info *infos, int gather)
 {
     PeerGroup *g = (PeerGroup *) group ;
     if (!g || g->hs.empty ()) return STMQR_ERR_INVALID ;
@@ -2416,6 +2450,7 @@ int stmqr_b200_factorize_multi (void *group, double tol, int64_t ntol, stmqr_num
     for (int i = 0 ; i < n ; i++)
         th.emplace_back ([&, i] {
             st [i] = stmqr_b200_factorize_dist (g->hs [i], tol, ntol, infos ? infos + i : nullptr) ;
+            if (st [i] == STMQR_OK && gather) st [i] = stmqr_b200_gather_outputs (g->hs [i]) ;
             if (st [i] != STMQR_OK) g->abort () ;       // the others must not wait for this handle at a barrier
         }) ;
     for (auto &t : th) t.join () ;

@@ -97,6 +97,201 @@ static void report (sparse_common *cc, int s, const char *where)
     if (cc->status >= SPARSE_OK) cc->status = st ;
 }
 
+/* ---- several GPUs behind the same entry point: STMQR_B200_DEVICES=0,1,2,3 ------------------------------------
+ * One engine handle per listed device (a device may be listed twice: the handles then share it, which is how the
+ * one-GPU test exercises this path).  Every front gets an owner GPU (stmqr_b200_map_fronts), the handles form a
+ * peer group (contribution blocks move by cudaMemcpyPeerAsync between the etree levels, one host thread per
+ * handle, csrc/multigpu.cuh), every GPU streams the packed R+H blocks of ITS fronts into ITS OWN host stack
+ * while it factorizes: the returned qr_numeric has ns = #GPUs stacks, Rblock [f] points into the stack of
+ * front f's owner -- any front-to-stack placement is legal for the consumers; the reference's
+ * own task scheduler also produces several stacks (SparseQR_factorize.c:405-410).  The integer side is merged
+ * on the devices and downloaded once. */
+#define MAXDEV 16
+static int g_ndev = -1 ;                    /* -1: STMQR_B200_DEVICES not parsed yet */
+static int g_devs [MAXDEV] ;
+static stmqr_handle g_hs [MAXDEV] ;
+static void *g_group = NULL ;
+static int32_t *g_owner = NULL ;
+static Long g_owner_nf = 0 ;
+static int g_multi_have_plan = 0 ;
+static uint64_t g_multi_key = 0 ;
+
+static void parse_devices (void)
+{
+    g_ndev = 0 ;
+    const char *e = getenv ("STMQR_B200_DEVICES") ;
+    if (!e) return ;
+    while (*e && g_ndev < MAXDEV)
+    {
+        char *end ;
+        long d = strtol (e, &end, 10) ;
+        if (end == e) break ;
+        g_devs [g_ndev++] = (int) d ;
+        e = (*end == ',') ? end + 1 : end ;
+    }
+    if (g_ndev < 2) g_ndev = 0 ;            /* one device: the ordinary path (STMQR_B200_DEVICE) */
+}
+
+static void multi_shutdown (void)
+{
+    if (g_group) stmqr_b200_peer_group_destroy (g_group) ;
+    g_group = NULL ;
+    for (int i = 0 ; i < MAXDEV ; i++) { if (g_hs [i]) stmqr_b200_destroy (g_hs [i]) ; g_hs [i] = NULL ; }
+    free (g_owner) ; g_owner = NULL ; g_owner_nf = 0 ;
+    g_multi_have_plan = 0 ;
+}
+
+static qr_numeric *multi_fail (sparse_csc **Ahandle, Long freeA, qr_numeric **QRnum, Long *Roff, Long nf,
+    sparse_common *cc, int s, const char *where, stmqr_handle h)
+{
+    if (s != STMQR_OK)
+    {
+        int st = map_status (s) ;
+        fprintf (stderr, "stmqr_b200 (multi-GPU) %s: %s\n", where, h ? stmqr_b200_last_error (h) : "") ;
+        SparseCore_error (st, __FILE__, __LINE__, "B200 numeric factorization failed", cc) ;
+        if (cc->status >= SPARSE_OK) cc->status = st ;
+    }
+    if (Roff) SparseCore_free (nf, sizeof (Long), Roff, cc) ;
+    if (QRnum && *QRnum) qr_freenum (QRnum, cc) ;
+    if (freeA) SparseCore_free_sparse (Ahandle, cc) ;
+    return (NULL) ;
+}
+
+static qr_numeric *qr_factorize_multi_gpu (sparse_csc **Ahandle, Long freeA, double tol, Long ntol,
+    qr_symbolic *QRsym, sparse_common *cc)
+{
+    sparse_csc *A = *Ahandle ;
+    const int verbose = getenv ("STMQR_B200_VERBOSE") != NULL ;
+    const double t_start = now_ms () ;
+    Long nf = QRsym->nf, m = QRsym->m, n = QRsym->n, rjsize = QRsym->rjsize, hisize = QRsym->hisize ;
+    const int nd = g_ndev ;
+    int s ;
+    for (int i = 0 ; i < nd ; i++)
+        if (g_hs [i] == NULL && (s = stmqr_b200_create (g_devs [i], &g_hs [i])) != STMQR_OK)
+        {
+            g_hs [i] = NULL ;
+            return multi_fail (Ahandle, freeA, NULL, NULL, nf, cc, s, "create", NULL) ;
+        }
+    /* plan: the same symbolic plan on every GPU, the ownership map, the peer group */
+    const uint64_t key = symbolic_key (QRsym) ;
+    if (!(g_multi_have_plan && key == g_multi_key))
+    {
+        stmqr_symbolic_view v ;
+        v.m = m ; v.n = n ; v.anz = QRsym->anz ; v.nf = nf ; v.maxfn = QRsym->maxfn ;
+        v.rjsize = rjsize ; v.hisize = hisize ;
+        v.do_rank_detection = QRsym->do_rank_detection ; v.keepH = QRsym->keepH ;
+        v.Sp = QRsym->Sp ; v.Sj = QRsym->Sj ; v.Qfill = QRsym->Qfill ; v.PLinv = QRsym->PLinv ;
+        v.Sleft = QRsym->Sleft ; v.Parent = QRsym->Parent ; v.Child = QRsym->Child ;
+        v.Childp = QRsym->Childp ; v.Super = QRsym->Super ; v.Rp = QRsym->Rp ; v.Rj = QRsym->Rj ;
+        v.Post = QRsym->Post ; v.Hip = QRsym->Hip ; v.Fm = QRsym->Fm ; v.Cm = QRsym->Cm ;
+        g_multi_have_plan = 0 ;
+        if (g_group) { stmqr_b200_peer_group_destroy (g_group) ; g_group = NULL ; }
+        free (g_owner) ;
+        g_owner = (int32_t *) malloc ((size_t) (nf > 0 ? nf : 1) * sizeof (int32_t)) ;
+        g_owner_nf = nf ;
+        if (!g_owner) return multi_fail (Ahandle, freeA, NULL, NULL, nf, cc, STMQR_ERR_OUT_OF_MEMORY, "owner map", NULL) ;
+        if ((s = stmqr_b200_map_fronts (&v, nd, g_owner)) != STMQR_OK)
+            return multi_fail (Ahandle, freeA, NULL, NULL, nf, cc, s, "map_fronts", NULL) ;
+        for (int i = 0 ; i < nd ; i++)
+        {
+            if ((s = stmqr_b200_analyze (g_hs [i], &v)) != STMQR_OK) return multi_fail (Ahandle, freeA, NULL, NULL, nf, cc, s, "analyze", g_hs [i]) ;
+            if ((s = stmqr_b200_set_ownership (g_hs [i], nd, i, g_owner)) != STMQR_OK) return multi_fail (Ahandle, freeA, NULL, NULL, nf, cc, s, "set_ownership", g_hs [i]) ;
+        }
+        if ((s = stmqr_b200_peer_group_create (g_hs, nd, &g_group)) != STMQR_OK)
+            return multi_fail (Ahandle, freeA, NULL, NULL, nf, cc, s, "peer_group_create", g_hs [0]) ;
+        g_multi_have_plan = 1 ;
+        g_multi_key = key ;
+    }
+    const double t_plan = now_ms () ;
+    SparseCore_allocate_work (0, (m > nf) ? m : nf, 0, cc) ;
+
+    stmqr_csc_view Av ;
+    Av.nrow = A->nrow ; Av.ncol = A->ncol ; Av.nzmax = A->nzmax ;
+    Av.p = (const int64_t *) A->p ; Av.i = (const int64_t *) A->i ; Av.x = (const double *) A->x ;
+
+    /* the numeric object: ns = #GPUs stacks, each allocated by the bound of its GPU's fronts and shrunk afterwards */
+    qr_numeric *QRnum = (qr_numeric *) SparseCore_malloc (1, sizeof (qr_numeric), cc) ;
+    if (cc->status < SPARSE_OK) return multi_fail (Ahandle, freeA, NULL, NULL, nf, cc, STMQR_OK, "", NULL) ;
+    Long ns = nd ;
+    QRnum->Rblock     = (double **) SparseCore_malloc (nf, sizeof (double *), cc) ;
+    QRnum->Rdead      = (char *)    SparseCore_calloc (n,  sizeof (char), cc) ;
+    QRnum->Stacks     = (double **) SparseCore_calloc (ns, sizeof (double *), cc) ;
+    QRnum->Stack_size = (Long *)    SparseCore_calloc (ns, sizeof (Long), cc) ;
+    QRnum->HStair = (Long *)   SparseCore_malloc (rjsize, sizeof (Long), cc) ;
+    QRnum->HTau   = (double *) SparseCore_malloc (rjsize, sizeof (double), cc) ;
+    QRnum->Hii    = (Long *)   SparseCore_malloc (hisize, sizeof (Long), cc) ;
+    QRnum->Hm     = (Long *)   SparseCore_malloc (nf, sizeof (Long), cc) ;
+    QRnum->Hr     = (Long *)   SparseCore_malloc (nf, sizeof (Long), cc) ;
+    QRnum->HPinv  = (Long *)   SparseCore_malloc (m, sizeof (Long), cc) ;
+    QRnum->n = n ; QRnum->m = m ; QRnum->nf = nf ;
+    QRnum->rjsize = rjsize ; QRnum->hisize = hisize ; QRnum->keepH = QRsym->keepH ;
+    QRnum->maxstack = QRsym->maxstack ;
+    QRnum->ns = ns ; QRnum->ntasks = nd ;
+    QRnum->maxfm = EMPTY ;
+    QRnum->norm_E_fro = 0 ;
+    Long *Roff = (Long *) SparseCore_malloc (nf, sizeof (Long), cc) ;
+    int64_t cap [MAXDEV] ;
+    for (int i = 0 ; i < nd && cc->status == SPARSE_OK ; i++)
+    {
+        cap [i] = 1 ;
+        stmqr_b200_rh_bound (g_hs [i], &cap [i]) ;
+        QRnum->Stack_size [i] = cap [i] ;
+        QRnum->Stacks [i] = (double *) SparseCore_malloc (cap [i], sizeof (double), cc) ;
+    }
+    if (cc->status < SPARSE_OK) return multi_fail (Ahandle, freeA, &QRnum, Roff, nf, cc, STMQR_OK, "", NULL) ;
+
+    /* upload A to every GPU (each builds the rows of S its fronts need from the whole matrix), start the
+     * downloaders, factorize with one host thread per GPU, merge the integer side on the devices */
+    for (int i = 0 ; i < nd ; i++)
+        if ((s = stmqr_b200_upload_matrix (g_hs [i], &Av)) != STMQR_OK) return multi_fail (Ahandle, freeA, &QRnum, Roff, nf, cc, s, "upload_matrix", g_hs [i]) ;
+    for (int i = 0 ; i < nd ; i++)
+        if ((s = stmqr_b200_stream_begin (g_hs [i], QRnum->Stacks [i], cap [i])) != STMQR_OK)
+        {
+            for (int j = 0 ; j < i ; j++) stmqr_b200_stream_end (g_hs [j]) ;
+            return multi_fail (Ahandle, freeA, &QRnum, Roff, nf, cc, s, "stream_begin", g_hs [i]) ;
+        }
+    stmqr_numeric_info infos [MAXDEV] ;
+    s = stmqr_b200_factorize_multi_ex (g_group, tol, ntol, infos, 1) ;
+    int s_end = STMQR_OK ;
+    for (int i = 0 ; i < nd ; i++) { int e2 = stmqr_b200_stream_end (g_hs [i]) ; if (e2 != STMQR_OK && s_end == STMQR_OK) s_end = e2 ; }
+    const double t_fact = now_ms () ;
+    if (s != STMQR_OK || s_end != STMQR_OK)
+    {
+        stmqr_handle bad = g_hs [0] ;
+        for (int i = 0 ; i < nd ; i++) if (stmqr_b200_last_error (g_hs [i]) [0]) { bad = g_hs [i] ; break ; }
+        return multi_fail (Ahandle, freeA, &QRnum, Roff, nf, cc, (s != STMQR_OK) ? s : s_end, "factorize", bad) ;
+    }
+    if (freeA) SparseCore_free_sparse (Ahandle, cc) ;
+    for (int i = 0 ; i < nd ; i++)
+    {
+        Long stacksize = (infos [i].rh_size > 0) ? infos [i].rh_size : 1 ;
+        size_t cur = (size_t) cap [i] ;
+        QRnum->Stacks [i] = (double *) SparseCore_realloc (stacksize, sizeof (double), QRnum->Stacks [i], &cur, cc) ;
+        QRnum->Stack_size [i] = (Long) cur ;
+    }
+    /* the integer side is global on every GPU after the gather: take it from the first one */
+    stmqr_numeric_view out ;
+    out.stack = NULL ;
+    out.Roff = (int64_t *) Roff ; out.Rdead = QRnum->Rdead ;
+    out.HStair = (int64_t *) QRnum->HStair ; out.HTau = QRnum->HTau ;
+    out.Hii = (int64_t *) QRnum->Hii ; out.Hm = (int64_t *) QRnum->Hm ;
+    out.Hr = (int64_t *) QRnum->Hr ; out.HPinv = (int64_t *) QRnum->HPinv ;
+    s = stmqr_b200_download (g_hs [0], &out) ;
+    if (s != STMQR_OK || cc->status < SPARSE_OK)
+        return multi_fail (Ahandle, 0, &QRnum, Roff, nf, cc, s, "download", g_hs [0]) ;
+    for (Long f = 0 ; f < nf ; f++) QRnum->Rblock [f] = QRnum->Stacks [g_owner [f]] + Roff [f] ;
+    SparseCore_free (nf, sizeof (Long), Roff, cc) ;
+    if (verbose)
+        fprintf (stderr, "stmqr_b200 qr_factorize on %d GPUs: plan %.1f ms, upload+numeric %.1f ms, download of the integer "
+            "side %.1f ms\n", nd, t_plan - t_start, t_fact - t_plan, now_ms () - t_fact) ;
+    QRnum->rank = infos [0].rank ;
+    QRnum->rank1 = infos [0].rank1 ;
+    QRnum->maxfrank = infos [0].maxfrank ;
+    QRnum->maxfm = infos [0].maxfm ;
+    cc->SPQR_flopcount = infos [0].flops ;
+    return (QRnum) ;
+}
+
 qr_numeric *stmqr_b200_qr_factorize (sparse_csc **Ahandle, Long freeA, double tol, Long ntol,
     qr_symbolic *QRsym, sparse_common *cc)
 {
@@ -105,6 +300,8 @@ qr_numeric *stmqr_b200_qr_factorize (sparse_csc **Ahandle, Long freeA, double to
         if (freeA) SparseCore_free_sparse (Ahandle, cc) ;
         return (NULL) ;
     }
+    if (g_ndev < 0) parse_devices () ;
+    if (g_ndev >= 2) return qr_factorize_multi_gpu (Ahandle, freeA, tol, ntol, QRsym, cc) ;
     sparse_csc *A = *Ahandle ;
     const int verbose = getenv ("STMQR_B200_VERBOSE") != NULL ;
     double t_start = now_ms (), t_plan, t_fact, t_alloc ;
@@ -311,6 +508,8 @@ void stmqr_b200_dropin_shutdown (void)
     if (g_handle) stmqr_b200_destroy (g_handle) ;
     g_handle = NULL ;
     g_have_plan = 0 ;
+    multi_shutdown () ;
+    g_ndev = -1 ;                           /* STMQR_B200_DEVICES is read again by the next call */
 }
 
 /* Forget the cached device plan: the next qr_factorize re-plans whatever its symbolic object is. */

@@ -209,6 +209,59 @@ def test_dropin_through_reference_api(name, order):
     ref.close()
 
 
+@pytest.mark.parametrize("name,order,devices", [("dwt_992", 2, "0,0"), ("t2d_q9", 2, "0,0,0"), ("epb1", 1, "0,0,0,0"),
+                                                ("cvxqp3", 1, "0,0")])
+def test_dropin_multi_gpu_through_reference_api(name, order, devices):
+    """STMQR_B200_DEVICES: the SAME drop-in entry point with one engine handle per listed device (here the handles
+    share device 0, which exercises every transfer and merge of csrc/multigpu.cuh's in-process transport): the
+    reference's SparseQR() gets a qr_numeric with one stack per GPU; same integer structure and R as the CPU
+    reference, same solve residual, Q'Q = I through the reference's untouched consumers, allocator balanced."""
+    if not R.have_reference():
+        pytest.skip("needs oracle/_ref")
+    ref = R.Reference()
+    A = ref.read_mtx(os.path.join(R.DATA_DIR, name + ".mtx"))
+    tol = ref.default_tol(A)
+    ref.set_backend("reference")
+    QRc = ref.sparseqr(A, order, tol, grain=1.0, tap=True)
+    symc = ref.symbolic(QRc); numc = ref.numeric(QRc, symc)
+    At, _, _ = ref.tapped()
+    res_c = ref.check_error(A, QRc)
+    i0 = ref.memory_inuse()
+    ref.free_qr(ref.sparseqr(A, order, tol, grain=1.0))
+    delta_cpu = ref.memory_inuse() - i0
+    ref.dropin_shutdown()
+    os.environ["STMQR_B200_DEVICES"] = devices
+    try:
+        ref.set_backend("b200")
+        inuse0 = ref.memory_inuse()
+        QRg = ref.sparseqr(A, order, tol, grain=1.0)
+        assert int(ref.qr_info(QRg)["ns"]) == len(devices.split(","))          # one stack per GPU
+        symg = ref.symbolic(QRg); numg = ref.numeric(QRg, symg)
+        assert not R.structural_equal(numg, numc, symg)
+        d = R.compare_R(symg, numg, numc, R.a_norm(At))
+        assert d <= R.r_tol_for(name), d
+        res_g = ref.check_error(A, QRg)
+        if numc.rank == symc.n:
+            assert res_g <= max(10 * res_c, 1e-9), (res_g, res_c)
+        if ref.qr_info(QRg)["n1cols"] == 0:
+            rng = np.random.default_rng(3)
+            X = rng.standard_normal((At.nrow, 2))
+            Y = ref.qmult(QRg, R.QR_QX, ref.qmult(QRg, R.QR_QTX, X))
+            assert np.max(np.abs(Y - X)) <= 1e-10 * max(1.0, np.max(np.abs(X)))
+        ref.refactorize(A, QRg)                                                 # cached multi-GPU plan, second call
+        numg2 = ref.numeric(QRg, symg)
+        assert not R.structural_equal(numg2, numc, symg)
+        ref.free_qr(QRg)
+        # (the stacks are counted differently from the one-stack layout only by the ns-sized pointer arrays)
+        assert abs((ref.memory_inuse() - inuse0) - delta_cpu) <= 0
+    finally:
+        os.environ.pop("STMQR_B200_DEVICES", None)
+        ref.dropin_shutdown()
+        ref.free_qr(QRc); ref.free_sparse(A)
+        ref.set_backend("reference")
+        ref.close()
+
+
 def test_qrtest_driver_with_ld_preload(tmp_path):
     """The reference's own acceptance driver (STMMQR/test/qrtest.c), unmodified binary, with the
     drop-in library preloaded: prints the published fingerprint residual for dwt_992."""
