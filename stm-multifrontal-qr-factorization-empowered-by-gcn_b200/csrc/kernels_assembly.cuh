@@ -197,47 +197,56 @@ __global__ void k_level_maxfm (const I32 *__restrict__ fronts, I32 count, DNum N
 }
 
 // ---------------------------------------------------------------------------------------------
-// Numeric assembly: F <- 0, scatter the rows of S, extend-add the children's packed C blocks
-// (qr_assemble, SparseQR_factorize.c:1176-1281).  grid = (fronts of the level, column slices);
-// each CTA owns a contiguous block of columns of F, so zero-fill and scatter need no inter-CTA
-// ordering and the zero-fill is a fully coalesced stream.
+// Numeric assembly (qr_assemble, SparseQR_factorize.c:1176-1281) in two launches per level:
+//   k_zero_fronts   F <- 0 for every front of the level: one contiguous 16-byte store stream per front
+//                   (front offsets are 16-byte aligned), grid = (fronts, chunks)
+//   k_assemble      scatter the rows of S and stack the children's packed C blocks.  In multifrontal QR
+//                   every row of F has exactly one source (an original row of S or one row of one child's
+//                   C block), so the writes are disjoint and need no order among themselves.  grid =
+//                   (fronts, slices); the slices deal out the SOURCES (rows of S, columns of each child C
+//                   block) round-robin, so nothing is read twice and nothing is read to be discarded.
 // ---------------------------------------------------------------------------------------------
+__global__ void k_zero_fronts (const I32 *__restrict__ fronts, DSym S, DNum N)
+{
+    const I32 f = fronts [blockIdx.x] ;
+    const I64 fn = S.Rp [f+1] - S.Rp [f] ;
+    const I64 cnt = (I64) N.Hm [f] * fn ;
+    if (cnt == 0) return ;
+    double *F = N.F + S.Foff [f] ;
+    double2 *F2 = reinterpret_cast<double2 *> (F) ;
+    const I64 n2 = cnt >> 1 ;
+    const I64 stride = (I64) gridDim.y * blockDim.x ;
+    const double2 z = make_double2 (0.0, 0.0) ;
+    I64 i = (I64) blockIdx.y * blockDim.x + threadIdx.x ;
+    for ( ; i + 3 * stride < n2 ; i += 4 * stride)
+    {
+        F2 [i] = z ; F2 [i + stride] = z ; F2 [i + 2 * stride] = z ; F2 [i + 3 * stride] = z ;
+    }
+    for ( ; i < n2 ; i += stride) F2 [i] = z ;
+    if ((cnt & 1) && blockIdx.y == 0 && threadIdx.x == 0) F [cnt - 1] = 0.0 ;
+}
+
 __global__ void k_assemble (const I32 *__restrict__ fronts, DSym S, DNum N)
 {
     const I32 f = fronts [blockIdx.x] ;
     const I32 col1 = S.Super [f], fp = S.Super [f+1] - col1 ;
-    const I32 p1 = S.Rp [f], fn = S.Rp [f+1] - p1 ;
     const I32 fm = N.Hm [f] ;
     if (fm == 0) return ;
-    const I32 nsl = gridDim.y ;
-    const I32 cb = (fn + nsl - 1) / nsl ;
-    const I32 j1 = blockIdx.y * cb, j2 = min (fn, j1 + cb) ;
-    if (j1 >= j2) return ;
     double *F = N.F + S.Foff [f] ;
-    const int tid = threadIdx.x, nt = blockDim.x ;
-    const int lane = tid & 31, w = tid >> 5, nw = nt >> 5 ;
-
-    {   // zero my columns (contiguous)
-        double *z = F + (I64) j1 * fm ;
-        const I64 cnt = (I64) (j2 - j1) * fm ;
-        for (I64 i = tid ; i < cnt ; i += nt) z [i] = 0.0 ;
-    }
-    __syncthreads () ;
+    const int lane = threadIdx.x & 31 ;
+    const I32 gw = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5) ;        // my warp among the front's warps
+    const I32 ngw = gridDim.y * (blockDim.x >> 5) ;
 
     // rows of S: one warp per row, lanes over its entries
     const I32 r1 = S.Sleft [col1], r2 = S.Sleft [col1+fp] ;
-    for (I32 r = r1 + w ; r < r2 ; r += nw)
+    for (I32 r = r1 + gw ; r < r2 ; r += ngw)
     {
         const I32 i = N.rowpos [r] ;
         const I32 e2 = S.Sp [r+1] ;
-        for (I32 p = S.Sp [r] + lane ; p < e2 ; p += 32)
-        {
-            const I32 j = S.Sjf [p] ;
-            if (j >= j1 && j < j2) F [i + (I64) j * fm] = N.Sx [p] ;
-        }
+        for (I32 p = S.Sp [r] + lane ; p < e2 ; p += 32) F [i + (I64) S.Sjf [p] * fm] = N.Sx [p] ;
     }
 
-    // children: one warp per column of the child's C block
+    // children: one warp per column of the child's C block (contiguous source, one column of F)
     for (I32 q = S.Childp [f] ; q < S.Childp [f+1] ; q++)
     {
         const I32 c = S.Child [q] ;
@@ -248,14 +257,20 @@ __global__ void k_assemble (const I32 *__restrict__ fronts, DSym S, DNum N)
         if (cm <= 0) continue ;
         const double *C = N.C + S.Coff [c] ;
         const I32 *Cmap = N.Cmap + pc ;
-        for (I32 cj = w ; cj < cn ; cj += nw)
+        // (start at a different warp for every child: short children do not all land on the first slices)
+        for (I32 cj = (gw + ngw - (q % ngw)) % ngw ; cj < cn ; cj += ngw)
         {
-            const I32 j = S.Cj [pc+cj] ;
-            if (j < j1 || j >= j2) continue ;
             const I32 len = min (cj+1, cm) ;
             const double *src = C + cblock_col_offset (cj, cm) ;
-            double *Fj = F + (I64) j * fm ;
-            for (I32 ci = lane ; ci < len ; ci += 32) Fj [Cmap [ci]] = src [ci] ;
+            double *Fj = F + (I64) S.Cj [pc+cj] * fm ;
+            I32 ci = lane ;
+            for ( ; ci + 96 < len ; ci += 128)
+            {
+                const double v0 = src [ci], v1 = src [ci+32], v2 = src [ci+64], v3 = src [ci+96] ;
+                const I32 i0 = Cmap [ci], i1 = Cmap [ci+32], i2 = Cmap [ci+64], i3 = Cmap [ci+96] ;
+                Fj [i0] = v0 ; Fj [i1] = v1 ; Fj [i2] = v2 ; Fj [i3] = v3 ;
+            }
+            for ( ; ci < len ; ci += 32) Fj [Cmap [ci]] = src [ci] ;
         }
     }
 }

@@ -950,11 +950,19 @@ int stmqr_b200_create (int device, stmqr_handle *out)
             (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (8) + PANEL_XR_DOUBLES) * (int) sizeof (double)) == cudaSuccess &&
         cudaFuncSetAttribute (k_panel_cluster<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (16)) * (int) sizeof (double)) == cudaSuccess &&
+        cudaFuncSetAttribute (k_panel_cluster<256, 1, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (8) + PANEL_XR_DOUBLES) * (int) sizeof (double)) == cudaSuccess &&
+        cudaFuncSetAttribute (k_panel_cluster<256, 2, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (8) + PANEL_XR_DOUBLES) * (int) sizeof (double)) == cudaSuccess &&
+        cudaFuncSetAttribute (k_panel_cluster<128, 4, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (4) + PANEL_XR_DOUBLES) * (int) sizeof (double)) == cudaSuccess &&
         cudaFuncSetAttribute (k_panel_cluster<128, 6>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
         cudaFuncSetAttribute (k_panel_cluster<256, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
         cudaFuncSetAttribute (k_panel_cluster<512, 1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-        cudaFuncSetAttribute (k_panel_grid, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute (k_panel_grid<512, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (16)) * (int) sizeof (double)) == cudaSuccess &&
+        cudaFuncSetAttribute (k_panel_grid<256, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (8)) * (int) sizeof (double)) == cudaSuccess &&
         cudaFuncSetAttribute (k_update_dmma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (int) update_smem_bytes<2> ()) == cudaSuccess &&
         cudaFuncSetAttribute (k_update_dmma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1489,7 +1497,12 @@ static int run_level (stmqr_handle h, const LevelSet &LS, const Level &Lv, long 
             CK (cudaStreamSynchronize (st)) ;
             actFm = std::min (Lv.maxFm, std::max (1, h->pin_lvl [0])) ;
         }
-        LAUNCH (2, k_assemble<<<dim3 (nbig, nsl), 256, 0, st>>> (fr, S, N)) ;
+        {
+            // zero-fill at ~4 CTAs of 16-byte stores per SM over the whole level, then the scatter
+            const int nz = (int) std::min<I64> (148, std::max<I64> (1, std::min<I64> (Lv.maxFelems / 4096, (4 * (I64) h->nsm + nbig - 1) / nbig))) ;
+            LAUNCH (2, k_zero_fronts<<<dim3 (nbig, nz), 256, 0, st>>> (fr, S, N)) ;
+            LAUNCH (2, k_assemble<<<dim3 (nbig, nsl), 256, 0, st>>> (fr, S, N)) ;
+        }
         if (h->debug_capture)
         {
             CK (cudaStreamSynchronize (st)) ;
@@ -1529,6 +1542,19 @@ static int run_level (stmqr_handle h, const LevelSet &LS, const Level &Lv, long 
         // few fronts in the level: idle SMs are better spent on shorter slabs (a column step sweeps the
         // slab three times through shared memory); up to the non-portable cluster size 16
         while (CS < h->cluster_max && (I64) nbig * CS * 2 <= h->nsm && (actFm + CS - 1) / CS > h->cluster_rows) CS *= 2 ;
+        // fronts too tall for a cluster of 8 shared-memory slabs: G CTAs per front with a global-memory
+        // exchange (k_panel_grid), as many fronts per launch as fit one CTA per SM
+        const bool gridpanel = (actFm >= h->grid_rows) && PB == PANEL_MAX && !(h->opt.reserved & 4) ;
+        // register-resident slabs (kernels_panel.cuh): 8 warps x 48 rows (one CTA per SM), 8 x 24 (two per SM) or
+        // 4 x 24 (four per SM); a level whose slabs need more than 384 rows keeps the shared-memory column loop
+        int regrpt = 0 ;
+        if ((h->opt.reserved & 128) && PB == PANEL_MAX && !gridpanel)       // bit 7: register-resident slabs (A/B: measured slower)
+        {
+            auto rl = [&] (int c) { return (I64) ((((actFm + c - 1) / c) + 3) & ~3) ; } ;
+            int cs = CS ;
+            while (cs < PANEL_CLUSTER_MAX && rl (cs) > 8 * 48) cs *= 2 ;
+            if (rl (cs) <= 8 * 48) { CS = cs ; regrpt = (rl (cs) <= 8 * 24) ? 24 : 48 ; }
+        }
         const I64 rowsPerCta = ((I64) (actFm + CS - 1) / CS + 7) & ~(I64) 3 ;
         // (at least 2 x 32 x 33 doubles: the leader builds T in the slab after writing it back)
         const I32 slabCap = (I32) std::max<I64> (2 * PANEL_MAX * (PANEL_MAX + 1),
@@ -1540,6 +1566,7 @@ static int run_level (stmqr_handle h, const LevelSet &LS, const Level &Lv, long 
         if (rowsPerCta <= h->panel128_rows && (I64) nbig >= 2 * (I64) h->nsm) pthreads = 128 ;
         if (((h->opt.reserved >> 16) & 0xff) >= 16 && rowsPerCta >= 256 && CS == 1) pthreads = 512 ;
         if ((h->opt.reserved >> 16) & 0xff) pthreads = std::min (pthreads, 32 * ((h->opt.reserved >> 16) & 0xff)) ;   // tuning
+        if (regrpt) pthreads = (regrpt == 24 && pthreads == 128 && rowsPerCta <= 4 * 24) ? 128 : 256 ;
         // number of fronts of the level with more than k columns (sorted by # columns descending)
         auto active_at = [&] (I32 k, I32 hi) -> I32 {
             I32 lo = 0 ;
@@ -1551,15 +1578,15 @@ static int run_level (stmqr_handle h, const LevelSet &LS, const Level &Lv, long 
             }
             return lo ;
         } ;
-        // fronts too tall for a cluster of 8 shared-memory slabs: G CTAs per front with a global-memory
-        // exchange (k_panel_grid), as many fronts per launch as fit one CTA per SM
-        const bool gridpanel = (actFm >= h->grid_rows) && PB == PANEL_MAX && !(h->opt.reserved & 4) ;
-        const I32 gneed = (I32) (((I64) actFm + 8 + 759) / 760) ;
+        // (register slabs: 8 warps x 48 rows per CTA; shared-memory slabs: 760 rows)
+        const bool gridreg = gridpanel && (h->opt.reserved & 128) && ((I64) actFm + 383) / 384 <= h->nsm ;
+        const I32 gneed = gridreg ? (I32) (((I64) actFm + 383) / 384) : (I32) (((I64) actFm + 8 + 759) / 760) ;
         auto launch_panel = [&] (I32 active, I32 k1, I32 parity) -> cudaError_t {
             if (gridpanel && gneed <= h->nsm)
             {
                 const I32 per = std::max<I32> (1, h->nsm / gneed) ;
-                const size_t smem = (size_t) (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (16)) * sizeof (double) ;
+                const I32 gslab = gridreg ? (I32) (8 * 48 + 4) * PANEL_MAX : (I32) PANEL_SLAB_MAX_DOUBLES ;
+                const size_t smem = (size_t) (gslab + panel_scratch_doubles (gridreg ? 8 : 16)) * sizeof (double) ;
                 for (I32 s0 = 0 ; s0 < active ; s0 += per)
                 {
                     const I32 nb = std::min<I32> (per, active - s0) ;
@@ -1567,8 +1594,8 @@ static int run_level (stmqr_handle h, const LevelSet &LS, const Level &Lv, long 
                     // become resident before the panel starts)
                     const I32 G = std::min<I32> (std::min<I32> (h->nsm / nb, std::max<I32> (gneed, h->grid_maxg)),
                         std::max<I32> (gneed, (I32) std::sqrt (0.84 * (double) actFm) + 1)) ;
-                    k_panel_grid<<<(unsigned) (G * nb), 512, smem, st>>> (L, S, N, k1, (I32) PB, parity,
-                        (I32) PANEL_SLAB_MAX_DOUBLES, G, s0, ++h->grid_seq) ;
+                    if (gridreg) k_panel_grid<256, 48><<<(unsigned) (G * nb), 256, smem, st>>> (L, S, N, k1, (I32) PB, parity, gslab, G, s0, ++h->grid_seq) ;
+                    else k_panel_grid<512, 0><<<(unsigned) (G * nb), 512, smem, st>>> (L, S, N, k1, (I32) PB, parity, gslab, G, s0, ++h->grid_seq) ;
                     if (s0 + per < active) h->launches++ ;
                 }
                 return cudaGetLastError () ;
@@ -1582,6 +1609,9 @@ static int run_level (stmqr_handle h, const LevelSet &LS, const Level &Lv, long 
             at [0].id = cudaLaunchAttributeClusterDimension ;
             at [0].val.clusterDim.x = CS ; at [0].val.clusterDim.y = 1 ; at [0].val.clusterDim.z = 1 ;
             cfg.attrs = at ; cfg.numAttrs = 1 ;
+            if (regrpt == 48) return cudaLaunchKernelEx (&cfg, k_panel_cluster<256, 1, 48>, L, S, N, k1, (I32) PB, parity, slabCap) ;
+            if (regrpt == 24 && pthreads == 256) return cudaLaunchKernelEx (&cfg, k_panel_cluster<256, 2, 24>, L, S, N, k1, (I32) PB, parity, slabCap) ;
+            if (regrpt == 24) return cudaLaunchKernelEx (&cfg, k_panel_cluster<128, 4, 24>, L, S, N, k1, (I32) PB, parity, slabCap) ;
             if (pthreads == 128) return cudaLaunchKernelEx (&cfg, k_panel_cluster<128, 6>, L, S, N, k1, (I32) PB, parity, slabCap) ;
             if (pthreads == 256) return cudaLaunchKernelEx (&cfg, k_panel_cluster<256, 2>, L, S, N, k1, (I32) PB, parity, slabCap) ;
             return cudaLaunchKernelEx (&cfg, k_panel_cluster<512, 1>, L, S, N, k1, (I32) PB, parity, slabCap) ;

@@ -105,7 +105,7 @@ EXPORTS = (
     "stmqr_b200_qmult", "stmqr_b200_rsolve", "stmqr_b200_solve_ls", "stmqr_b200_rcount", "stmqr_b200_rconvert",
     "stmqr_b200_map_fronts", "stmqr_b200_set_ownership", "stmqr_b200_nccl_unique_id", "stmqr_b200_comm_init",
     "stmqr_b200_peer_group_create", "stmqr_b200_peer_group_destroy", "stmqr_b200_factorize_dist",
-    "stmqr_b200_factorize_multi",
+    "stmqr_b200_factorize_multi", "stmqr_b200_factorize_multi_ex", "stmqr_b200_gather_outputs",
 )
 
 _lib = None
