@@ -142,8 +142,7 @@ typedef struct
                                         k_panel_grid, bit 3 no small-front kernel (read by analyze),
                                         bit 4 non-persistent K = 128 apply, bit 5 one column per panel
                                         exchange, bit 6 no recycling of the contribution-block arena (read
-                                        by analyze), bit 7 panel slabs in registers instead of
-                                        shared memory (experimental); bits 8-15 ring stages of k_update_dmma (2/4),
+                                        by analyze); bits 8-15 ring stages of k_update_dmma (2/4),
                                         bits 16-23 max warps per panel CTA                            */
 } stmqr_options ;
 

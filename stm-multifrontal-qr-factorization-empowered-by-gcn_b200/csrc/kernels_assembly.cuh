@@ -410,7 +410,6 @@ __global__ void k_pack (const I32 *__restrict__ fronts, DSym S, DNum N)
     const I32 j1 = blockIdx.y * cb, j2 = min (fn, j1 + cb) ;
     if (j1 >= j2) return ;
     const double *F = N.F + S.Foff [f] ;
-    const I32 *st = N.stair + p1 ;
     const I64 *colp = N.colp + p1 ;
     double *R = N.R + N.Roff [f] ;
     double *C = N.C + S.Coff [f] ;
@@ -418,27 +417,49 @@ __global__ void k_pack (const I32 *__restrict__ fronts, DSym S, DNum N)
     const I64 rsize = N.rsize [f] ;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5 ;
 
+    // every column is a contiguous read and a contiguous write; four independent loads are in flight per lane
+    // before the first store (source and destination never overlap)
     for (I32 k = j1 + w ; k < j2 ; k += nw)
     {
-        const double *Fk = F + (I64) k * fm ;
-        double *Rk = R + colp [k] ;
+        const double *__restrict__ Fk = F + (I64) k * fm ;
+        double *__restrict__ Rk = R + colp [k] ;
         const I64 len = ((k+1 < fn) ? colp [k+1] : rsize) - colp [k] ;
         if (k < fp)
         {
-            for (I64 i = lane ; i < len ; i += 32) Rk [i] = Fk [i] ;
+            I64 i = lane ;
+            for ( ; i + 96 < len ; i += 128)
+            {
+                const double v0 = Fk [i], v1 = Fk [i+32], v2 = Fk [i+64], v3 = Fk [i+96] ;
+                Rk [i] = v0 ; Rk [i+32] = v1 ; Rk [i+64] = v2 ; Rk [i+96] = v3 ;
+            }
+            for ( ; i < len ; i += 32) Rk [i] = Fk [i] ;
         }
         else
         {
             // rows 0..rm-1, then rows h..t-1 with h = min (rm + (k-fp+1), fm)
             const I32 h = min (rm + (k - fp + 1), fm) ;
-            for (I64 i = lane ; i < len ; i += 32) Rk [i] = (i < rm) ? Fk [i] : Fk [h + (i - rm)] ;
+            const I64 sh = (I64) h - rm ;
+            I64 i = lane ;
+            for ( ; i + 96 < len ; i += 128)
+            {
+                const double v0 = Fk [i + ((i < rm) ? 0 : sh)], v1 = Fk [i + 32 + ((i + 32 < rm) ? 0 : sh)],
+                    v2 = Fk [i + 64 + ((i + 64 < rm) ? 0 : sh)], v3 = Fk [i + 96 + ((i + 96 < rm) ? 0 : sh)] ;
+                Rk [i] = v0 ; Rk [i+32] = v1 ; Rk [i+64] = v2 ; Rk [i+96] = v3 ;
+            }
+            for ( ; i < len ; i += 32) Rk [i] = Fk [i + ((i < rm) ? 0 : sh)] ;
             // contribution block column cj = k - fp: rows rank .. rank+min(cj+1,cm)-1
             const I32 cj = k - fp ;
             const I32 clen = min (cj+1, cm) ;
-            double *Ck = C + cblock_col_offset (cj, cm) ;
-            for (I32 i = lane ; i < clen ; i += 32) Ck [i] = Fk [rank + i] ;
+            double *__restrict__ Ck = C + cblock_col_offset (cj, cm) ;
+            const double *__restrict__ Fr = Fk + rank ;
+            I32 ci = lane ;
+            for ( ; ci + 96 < clen ; ci += 128)
+            {
+                const double v0 = Fr [ci], v1 = Fr [ci+32], v2 = Fr [ci+64], v3 = Fr [ci+96] ;
+                Ck [ci] = v0 ; Ck [ci+32] = v1 ; Ck [ci+64] = v2 ; Ck [ci+96] = v3 ;
+            }
+            for ( ; ci < clen ; ci += 32) Ck [ci] = Fr [ci] ;
         }
-        (void) st ;
     }
 }
 

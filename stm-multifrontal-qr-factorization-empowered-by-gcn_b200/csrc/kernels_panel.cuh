@@ -430,75 +430,7 @@ __device__ __forceinline__ double panel_allreduce (cg::cluster_group &cluster, G
 // the one-column algorithm.  Both reflectors are applied in one sweep: y <- ya y - fa x_k - fb x_{k+1}.
 constexpr double LA_THETA = 1.0 / 32.0 ;
 
-// ---- register-resident slab (RPT > 0) ------------------------------------------------------------
-// The column loop below sweeps the slab three times per step (dots, update read, update write); from
-// shared memory that is ~10 LSU wavefronts per warp and slab row, i.e. the loop is bound by the 128 B/clk
-// of the shared-memory pipe, not by latency.  With RPT > 0 thread (w, lane) keeps column `lane` of the
-// slab rows  i = 2 (NW q + w) + b,  j = 2 q + b < RPT  in REGISTERS (row pairs dealt round-robin to the
-// warps, so the shrinking row window stays balanced).  Per step only the two pivot columns k, k+1 go
-// through shared memory: their owner lanes stage them in a per-warp buffer (rows are warp-local, so a
-// __syncwarp is enough) and every lane reads them back as broadcast 16-byte loads.
-template <int NW>
-__device__ __forceinline__ int reg_rows_below (const I32 b, const int w)
-{
-    // how many of warp w's rows have a local index < b
-    const I32 bb = max (b, 0) ;
-    const int r = (int) (bb & (2 * NW - 1)) - 2 * w ;
-    return 2 * (int) (bb / (2 * NW)) + min (max (r, 0), 2) ;
-}
-
-// partial dots of the staged columns with my column over my rows j in [ja,jbA) (column k) / [ja,jbB) (k+1)
-template <int RPT, bool PRED, bool TWO>
-__device__ __forceinline__ void reg_dots_chunk (const double (&y) [RPT], const double *xsw, const int ch,
-    const int ja, const int jbA, const int jbB, double (&a) [4], double (&b) [4])
-{
-#pragma unroll
-    for (int p = 0 ; p < 4 ; p++)
-    {
-        const int j = 8 * ch + 2 * p ;
-        const double2 u = *reinterpret_cast<const double2 *> (xsw + j) ;
-        if (TWO)
-        {
-            const double2 v = *reinterpret_cast<const double2 *> (xsw + RPT + j) ;
-            if (!PRED || (j >= ja && j < jbA)) a [p] = fma (u.x, y [j], a [p]) ;
-            if (!PRED || (j >= ja && j < jbB)) b [p] = fma (v.x, y [j], b [p]) ;
-            if (!PRED || (j + 1 >= ja && j + 1 < jbA)) a [p] = fma (u.y, y [j+1], a [p]) ;
-            if (!PRED || (j + 1 >= ja && j + 1 < jbB)) b [p] = fma (v.y, y [j+1], b [p]) ;
-        }
-        else
-        {
-            // one column: a | b are eight accumulators of the same sum
-            if (!PRED || (j >= ja && j < jbA)) a [p] = fma (u.x, y [j], a [p]) ;
-            if (!PRED || (j + 1 >= ja && j + 1 < jbA)) b [p] = fma (u.y, y [j+1], b [p]) ;
-        }
-    }
-}
-
-// y <- ya y - fa x_k - fb x_{k+1} on my rows j in [ja,jb)
-template <int RPT, bool PRED, bool TWO>
-__device__ __forceinline__ void reg_update_chunk (double (&y) [RPT], const double *xsw, const int ch,
-    const int ja, const int jb, const double ya, const double fa, const double fb)
-{
-#pragma unroll
-    for (int p = 0 ; p < 4 ; p++)
-    {
-        const int j = 8 * ch + 2 * p ;
-        const double2 u = *reinterpret_cast<const double2 *> (xsw + j) ;
-        if (TWO)
-        {
-            const double2 v = *reinterpret_cast<const double2 *> (xsw + RPT + j) ;
-            if (!PRED || (j >= ja && j < jb)) y [j] = fma (-v.x, fb, fma (-u.x, fa, y [j] * ya)) ;
-            if (!PRED || (j + 1 >= ja && j + 1 < jb)) y [j+1] = fma (-v.y, fb, fma (-u.y, fa, y [j+1] * ya)) ;
-        }
-        else
-        {
-            if (!PRED || (j >= ja && j < jb)) y [j] = fma (-u.x, fa, y [j] * ya) ;
-            if (!PRED || (j + 1 >= ja && j + 1 < jb)) y [j+1] = fma (-u.y, fa, y [j+1] * ya) ;
-        }
-    }
-}
-
-template <int NW, bool GRID, int RPT = 0>
+template <int NW, bool GRID>
 __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, GridComm &gc, const unsigned ECS,
     const I32 slab_cap, const I32 ldp, const LevelArgs &L, const DSym &S, const DNum &N,
     const I32 slot, const I32 f, const I32 k1, const I32 k2, const I32 parity, const I32 lrow0,
@@ -542,23 +474,7 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
         stl [tid] = (tid < np) ? st [k1 + tid] : 0 ;
         sto [tid] = -1 ;
     }
-    constexpr bool REG = (RPT > 0) ;
-    constexpr int RPTA = REG ? RPT : 8 ;
-    static_assert (RPTA % 8 == 0, "register slabs are swept in chunks of 8 rows") ;
-    // pivot rows g, g+1 have a local index <= 32 in their owner CTA: they sit in the first JP registers
-    constexpr int JP = (2 * (16 / NW) + 2 < RPTA) ? 2 * (16 / NW) + 2 : RPTA ;
-    double y [RPTA] ;
-    double *const xsw = P + w * (2 * RPTA) ;                // per-warp staging: column k | column k+1 over my rows
-    if constexpr (REG)
-    {
-#pragma unroll
-        for (int j = 0 ; j < RPTA ; j++)
-        {
-            const I32 i = 2 * (NW * (j >> 1) + w) + (j & 1) ;
-            y [j] = (mycol && i < nloc) ? P [(I64) lane * ldp + i] : 0.0 ;
-        }
-    }
-    __syncthreads () ;              // (REG: the slab in shared memory is free from here on)
+    __syncthreads () ;
 
     I32 g = rbeg ;
     const I32 g1 = g ;
@@ -587,11 +503,8 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
         const unsigned owner0 = (ECS > 1) ? (unsigned) ((g - rbeg) / RL) : 0u ;
         const unsigned owner1 = (ECS > 1 && have1) ? (unsigned) ((g + 1 - rbeg) / RL) : 0u ;
         const I32 gi0 = g - lrow0, gi1 = g + 1 - lrow0 ;
-        const bool own_g0 = (cr == owner0) && (((REG ? (gi0 >> 1) : gi0) & (NW - 1)) == w) ;            // my warp owns the pivot row
-        const bool own_g1 = have1 && (cr == owner1) && (((REG ? (gi1 >> 1) : gi1) & (NW - 1)) == w) ;   // ... the row below it
-        // REG: register index of the pivot rows in their owner warp, my rows of [j0,e0) are j in [ja,jbA), of [j0,e1): [ja,jbB)
-        const int jg0 = 2 * ((gi0 >> 1) / NW) + (gi0 & 1), jg1 = 2 * ((gi1 >> 1) / NW) + (gi1 & 1) ;
-        int ja = 0, jbA = 0, jbB = 0 ;
+        const bool own_g0 = (cr == owner0) && ((gi0 & (NW - 1)) == w) ;             // my warp owns the pivot row
+        const bool own_g1 = have1 && (cr == owner1) && ((gi1 & (NW - 1)) == w) ;    // ... the row below it
         const int par = step & 1 ;
         step++ ;
         const double *x0 = P + (I64) c * ldp ;
@@ -601,44 +514,7 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
 
         // ---- partial dots of columns k and k+1 with my column over my warp's rows -----------------
         double sA, sB = 0 ;
-        if constexpr (REG)
-        {
-            ja = reg_rows_below<NW> (j0, w) ;
-            jbA = max (ja, reg_rows_below<NW> (e0, w)) ;
-            jbB = la ? max (jbA, reg_rows_below<NW> (e1, w)) : jbA ;
-            // stage x_k | x_{k+1} (my warp's rows from g+1 on: the rare rescale path starts one row earlier)
-            const int js = reg_rows_below<NW> (max (g + 1, lrow0) - lrow0, w) ;
-            __syncwarp () ;
-            if (lane == c || (la && lane == c1))
-            {
-                double *d = xsw + ((lane == c) ? 0 : RPTA) ;
-#pragma unroll
-                for (int jp = 0 ; jp < RPTA / 2 ; jp++)
-                    if (2 * jp + 2 > js && 2 * jp < jbB)
-                        *reinterpret_cast<double2 *> (d + 2 * jp) = make_double2 (y [2*jp], y [2*jp+1]) ;
-            }
-            __syncwarp () ;
-            double a [4] = {0, 0, 0, 0}, b [4] = {0, 0, 0, 0} ;
-#pragma unroll
-            for (int ch = 0 ; ch < RPTA / 8 ; ch++)
-            {
-                if (8 * ch + 8 <= ja || 8 * ch >= jbB) continue ;
-                const bool full = (8 * ch >= ja) && (8 * ch + 8 <= jbA) ;      // (jbA <= jbB)
-                if (la)
-                {
-                    if (full) reg_dots_chunk<RPTA, false, true> (y, xsw, ch, ja, jbA, jbB, a, b) ;
-                    else reg_dots_chunk<RPTA, true, true> (y, xsw, ch, ja, jbA, jbB, a, b) ;
-                }
-                else
-                {
-                    if (full) reg_dots_chunk<RPTA, false, false> (y, xsw, ch, ja, jbA, jbB, a, b) ;
-                    else reg_dots_chunk<RPTA, true, false> (y, xsw, ch, ja, jbA, jbB, a, b) ;
-                }
-            }
-            if (la) { sA = (a [0] + a [1]) + (a [2] + a [3]) ; sB = (b [0] + b [1]) + (b [2] + b [3]) ; }
-            else sA = ((a [0] + a [1]) + (a [2] + a [3])) + ((b [0] + b [1]) + (b [2] + b [3])) ;
-        }
-        else if (la)
+        if (la)
         {
             double a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0 ;
             I32 i = ifirst ;
@@ -693,42 +569,14 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
             // second case with a positive value below every regular sum of squares, so that the total
             // is 0 if and only if the sub-column is exactly zero (no extra exchange needed later)
             bool nz = false ;
-            if constexpr (REG)
-            {
-#pragma unroll
-                for (int j = 0 ; j < RPTA ; j++) nz |= (j >= ja && j < jbA && y [j] != 0.0) ;
-            }
-            else
-            {
-                for (I32 i = ifirst ; i < e0 ; i += NW) nz |= (x0 [i] != 0.0) ;
-            }
+            for (I32 i = ifirst ; i < e0 ; i += NW) nz |= (x0 [i] != 0.0) ;
             if (nz) sA = 1e-300 ;
         }
         PT_MARK (0) ;
         part [(par * NW + w) * PM2 + lane] = mycol ? sA : 0.0 ;
         if (la) part [(par * NW + w) * PM2 + PANEL_MAX + lane] = mycol ? sB : 0.0 ;
-        if constexpr (REG)
-        {
-            if (own_g0)
-            {
-                double v = 0.0 ;
-#pragma unroll
-                for (int j = 0 ; j < JP ; j++) if (j == jg0) v = y [j] ;
-                prow [par * PM2 + lane] = v ;               // (columns >= np hold zeros)
-            }
-            if (own_g1)
-            {
-                double v = 0.0 ;
-#pragma unroll
-                for (int j = 0 ; j < JP ; j++) if (j == jg1) v = y [j] ;
-                prow [par * PM2 + PANEL_MAX + lane] = v ;
-            }
-        }
-        else
-        {
-            if (own_g0) prow [par * PM2 + lane] = mycol ? yc [gi0] : 0.0 ;
-            if (own_g1) prow [par * PM2 + PANEL_MAX + lane] = mycol ? yc [gi1] : 0.0 ;
-        }
+        if (own_g0) prow [par * PM2 + lane] = mycol ? yc [gi0] : 0.0 ;
+        if (own_g1) prow [par * PM2 + PANEL_MAX + lane] = mycol ? yc [gi1] : 0.0 ;
         __syncthreads () ;
         PT_MARK (1) ;
         {
@@ -774,14 +622,14 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
             {
                 // warp w gathers the records w, w+NW, ...: all loads in flight at once, polled until the
                 // tag of this step shows up; summed in a fixed order, the same in every CTA
-                constexpr int NREC = (148 + NW - 1) / NW ;          // records per warp (at most one CTA per SM)
-                double v [NREC], vb [NREC] ;
+                static_assert (!GRID || NW * 10 >= 148, "records per warp") ;
+                double v [10], vb [10] ;
                 bool ok ;
                 do
                 {
                     ok = true ;
 #pragma unroll
-                    for (int j = 0 ; j < NREC ; j++)
+                    for (int j = 0 ; j < 10 ; j++)
                     {
                         const unsigned r = (unsigned) (w + NW * j) ;
                         v [j] = 0.0 ; vb [j] = 0.0 ;
@@ -804,14 +652,10 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
                     if (have1) while (!__all_sync (STMQR_FULL_MASK, ll_load (rec + owner1 * 128 + 96 + lane, tag, rv))) { }
                     prow [par * PM2 + PANEL_MAX + lane] = rv ;
                 }
-                // fixed-shape tree (same in every CTA): FP64 adds have a long dependent latency
-#pragma unroll
-                for (int h2 = 16 ; h2 > 0 ; h2 >>= 1)
-#pragma unroll
-                    for (int j = 0 ; j < h2 ; j++)
-                        if (j + h2 < NREC) { v [j] += v [j + h2] ; vb [j] += vb [j + h2] ; }
-                part [(par * NW + w) * PM2 + lane] = v [0] ;
-                part [(par * NW + w) * PM2 + PANEL_MAX + lane] = vb [0] ;
+                part [(par * NW + w) * PM2 + lane] = (((v [0] + v [1]) + (v [2] + v [3])) + ((v [4] + v [5]) + (v [6] + v [7])))
+                    + (v [8] + v [9]) ;
+                part [(par * NW + w) * PM2 + PANEL_MAX + lane] = (((vb [0] + vb [1]) + (vb [2] + vb [3])) + ((vb [4] + vb [5]) + (vb [6] + vb [7])))
+                    + (vb [8] + vb [9]) ;
             }
             __syncthreads () ;
             {
@@ -921,16 +765,13 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
                 const I32 i0 = max (g + 1, lrow0) - lrow0 ;
                 const I32 if1 = i0 + ((w - i0) & (NW - 1)) ;
                 double mx = 0 ;
-                const int jr0 = REG ? reg_rows_below<NW> (i0, w) : 0 ;      // (REG: my rows of (g,t) are j in [jr0,jbA), staged in xsw)
-                if constexpr (REG) { for (int j = jr0 ; j < jbA ; j++) mx = fmax (mx, fabs (xsw [j])) ; }
-                else { for (I32 i = if1 ; i < e0 ; i += NW) mx = fmax (mx, fabs (x0 [i])) ; }
+                for (I32 i = if1 ; i < e0 ; i += NW) mx = fmax (mx, fabs (x0 [i])) ;
                 mx = panel_allreduce<NW, true, GRID> (cluster, gc, ECS, mx, red, xch [par], par) ;
                 if (mx > 0)
                 {
                     const double inv = 1.0 / mx ;
                     double s2 = 0 ;
-                    if constexpr (REG) { for (int j = jr0 ; j < jbA ; j++) { const double v = xsw [j] * inv ; s2 += v * v ; } }
-                    else { for (I32 i = if1 ; i < e0 ; i += NW) { const double v = x0 [i] * inv ; s2 += v * v ; } }
+                    for (I32 i = if1 ; i < e0 ; i += NW) { const double v = x0 [i] * inv ; s2 += v * v ; }
                     s2 = panel_allreduce<NW, false, GRID> (cluster, gc, ECS, s2, red + NW, xch [par], par) ;
                     nrm = hypot (alpha, mx * sqrt (s2)) ;
                     ss = 1.0 ;
@@ -1014,16 +855,7 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
             if (lane == c)
             {
                 const I32 z0 = max (g, lrow0) - lrow0 ;
-                if constexpr (REG)
-                {
-                    const int jz = reg_rows_below<NW> (z0, w) ;
-#pragma unroll
-                    for (int j = 0 ; j < RPTA ; j++) if (j >= jz) y [j] = 0.0 ;
-                }
-                else
-                {
-                    for (I32 i = z0 + ((w - z0) & (NW - 1)) ; i < nloc ; i += NW) yc [i] = 0.0 ;
-                }
+                for (I32 i = z0 + ((w - z0) & (NW - 1)) ; i < nloc ; i += NW) yc [i] = 0.0 ;
             }
             if (leader)
             {
@@ -1053,46 +885,7 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
             if (lane == c) { if (tau != 0) ya = scale ; }
             else if (two && lane == c1) { if (tau1 != 0) ya = scale1 ; fa = ya * so ; }
             else if (lane > c) { fb = scale1 * w1 ; fa = fma (-fb, so, scale * wv) ; }
-            if constexpr (REG)
-            {
-                if ((tau != 0 || two) && lane >= c && mycol)
-                {
-                    const int jb = two ? jbB : jbA ;
-#pragma unroll
-                    for (int ch = 0 ; ch < RPTA / 8 ; ch++)
-                    {
-                        if (8 * ch + 8 <= ja || 8 * ch >= jb) continue ;
-                        const bool full = (8 * ch >= ja) && (8 * ch + 8 <= jb) ;
-                        if (two)
-                        {
-                            if (full) reg_update_chunk<RPTA, false, true> (y, xsw, ch, ja, jb, ya, fa, fb) ;
-                            else reg_update_chunk<RPTA, true, true> (y, xsw, ch, ja, jb, ya, fa, fb) ;
-                        }
-                        else
-                        {
-                            if (full) reg_update_chunk<RPTA, false, false> (y, xsw, ch, ja, jb, ya, fa, fb) ;
-                            else reg_update_chunk<RPTA, true, false> (y, xsw, ch, ja, jb, ya, fa, fb) ;
-                        }
-                    }
-                }
-                // the two pivot rows, by their owner warps
-                if (own_g0 && mycol && (lane == c || (lane > c && tau != 0)))
-                {
-#pragma unroll
-                    for (int j = 0 ; j < JP ; j++) if (j == jg0) y [j] = (lane == c) ? beta : y [j] - wv ;
-                }
-                if (own_g1 && mycol && lane >= c)
-                {
-                    // (lane c: v_k (g+1); lanes > c: row g+1 after H_k, and after H_{k+1} when it rode along)
-                    bool wr = (tau != 0 && g + 1 < t) ;
-                    double nv1 = r1p ;
-                    if (two && lane == c1) { nv1 = beta1 ; wr = true ; }
-                    else if (two && lane > c1) { nv1 = r1p - w1 ; wr = true ; }
-#pragma unroll
-                    for (int j = 0 ; j < JP ; j++) if (wr && j == jg1) y [j] = nv1 ;
-                }
-            }
-            else if ((tau != 0 || two) && lane >= c && mycol)
+            if ((tau != 0 || two) && lane >= c && mycol)
             {
                 const I32 ee = two ? e1 : e0 ;
                 I32 i = ifirst ;
@@ -1135,12 +928,12 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
                 }
             }
             // the two pivot rows, by their owner warps
-            if (!REG && own_g0 && mycol)
+            if (own_g0 && mycol)
             {
                 if (lane == c) yc [gi0] = beta ;
                 else if (lane > c && tau != 0) yc [gi0] -= wv ;
             }
-            if (!REG && own_g1 && mycol && lane >= c)
+            if (own_g1 && mycol && lane >= c)
             {
                 if (two && lane == c1) yc [gi1] = beta1 ;
                 else if (two && lane > c1) yc [gi1] = r1p - w1 ;
@@ -1180,17 +973,6 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
         // the next step's dots read, on this warp's rows, columns that other lanes of the warp just wrote
         __syncwarp () ;
         PT_MARK (4) ;
-    }
-    if constexpr (REG)
-    {
-        // the slab goes back to shared memory (the per-warp staging area lies inside it), then to the front
-        __syncthreads () ;
-#pragma unroll
-        for (int j = 0 ; j < RPTA ; j++)
-        {
-            const I32 i = 2 * (NW * (j >> 1) + w) + (j & 1) ;
-            if (mycol && i < nloc) P [(I64) lane * ldp + i] = y [j] ;
-        }
     }
     __syncthreads () ;
     PT_MARK (5) ;
@@ -1301,9 +1083,7 @@ __device__ __forceinline__ void panel_columns_smem (cg::cluster_group &cluster, 
 // memory = slab_cap doubles (the row slab of one CTA: RL rows x np columns, column-major, odd ld)
 // followed by panel_scratch_doubles (NT/32) doubles of scratch.  NT = threads per CTA: small
 // fronts use small CTAs so that many of them are resident per SM.
-// RPT > 0: the slab lives in registers during the column loop (NT/32 warps x RPT rows per CTA; the host picks the
-// variant from the level's row count), shared memory only stages it on the way in and out.
-template <int NT, int MINB, int RPT = 0>
+template <int NT, int MINB>
 __global__ void __launch_bounds__ (NT, MINB) k_panel_cluster (LevelArgs L, DSym S, DNum N, I32 k1, I32 PB,
     I32 parity, I32 slab_cap)
 {
@@ -1350,15 +1130,13 @@ __global__ void __launch_bounds__ (NT, MINB) k_panel_cluster (LevelArgs L, DSym 
     const I32 nrows = max (rend - g1, 0) ;
     // effective cluster size: a window that fits one CTA's slab is done by the leader alone (no
     // cluster barriers at all); the other CTAs of the cluster leave
-    const unsigned ECS = ((I64) ((nrows + 3) | 1) * np <= (I64) slab_cap &&
-        (RPT == 0 || ((nrows + 3) & ~3) <= NW * RPT)) ? 1u : CS ;
+    const unsigned ECS = ((I64) ((nrows + 3) | 1) * np <= (I64) slab_cap) ? 1u : CS ;
     if (cr >= ECS) return ;
     const I32 RL = max (4, (((nrows + (I32) ECS - 1) / (I32) ECS) + 3) & ~3) ;
     const I32 lrow0 = g1 + (I32) cr * RL ;
     const I32 nloc = max (0, min (rend - lrow0, RL)) ;
     const I32 ldp = RL | 1 ;
-    // (a register variant launched on a level whose slabs do not fit its registers runs in place on the front)
-    const bool insmem = ((I64) ldp * np <= (I64) slab_cap) && (RPT == 0 || RL <= NW * RPT) ;
+    const bool insmem = ((I64) ldp * np <= (I64) slab_cap) ;
     double *F = N.F + S.Foff [f] ;
     const I64 ld = fm ;
 
@@ -1378,7 +1156,7 @@ __global__ void __launch_bounds__ (NT, MINB) k_panel_cluster (LevelArgs L, DSym 
         }
         __syncthreads () ;
         GridComm nogrid {} ;
-        panel_columns_smem<NW, false, RPT> (cluster, nogrid, ECS, slab_cap, ldp, L, S, N, slot, f, k1, k2, parity, lrow0, nloc, g1,
+        panel_columns_smem<NW, false> (cluster, nogrid, ECS, slab_cap, ldp, L, S, N, slot, f, k1, k2, parity, lrow0, nloc, g1,
             RL, rend, xch, xrec, xrows, cols, tq) ;
     }
     else
@@ -1398,14 +1176,13 @@ __global__ void __launch_bounds__ (NT, MINB) k_panel_cluster (LevelArgs L, DSym 
 // grid = G x nfronts, slot = slot0 + blockIdx.x / G.  ctr: 2 counters per slot, zero on entry (the
 // last CTA to leave resets them).
 // ---------------------------------------------------------------------------------------------
-template <int NT, int RPT>
-__global__ void __launch_bounds__ (NT, 1) k_panel_grid (LevelArgs L, DSym S, DNum N, I32 k1, I32 PB, I32 parity,
+__global__ void __launch_bounds__ (512, 1) k_panel_grid (LevelArgs L, DSym S, DNum N, I32 k1, I32 PB, I32 parity,
     I32 slab_cap, I32 G, I32 slot0, unsigned seq)
 {
     extern __shared__ double slab [] ;
     __shared__ PanelXch xch [2] ;
     __shared__ I32 cols [PANEL_MAX], tq [PANEL_MAX] ;
-    constexpr int NW = NT / 32 ;
+    constexpr int NW = 16 ;
     cg::cluster_group cluster = cg::this_cluster () ;
     const I32 slot = slot0 + blockIdx.x / G ;
     const unsigned cr = blockIdx.x % G ;
@@ -1428,16 +1205,14 @@ __global__ void __launch_bounds__ (NT, 1) k_panel_grid (LevelArgs L, DSym S, DNu
     const I32 nrows = max (rend - g1, 0) ;
     // CTAs that take part: a step costs ~5.7 cycles per slab row (shared-memory sweeps) plus
     // ~27/4 cycles per arriving CTA (L2 atomics): ECS ~ sqrt (0.84 nrows), at least what fits
-    // (RPT > 0: the slab lives in registers, NW x RPT rows at most, and a step costs about half as much per row)
-    const I32 rlcap0 = max (4, (slab_cap / max (np, 1) - 4) & ~3) ;
-    const I32 rlcap = (RPT > 0) ? min (rlcap0, NW * RPT) : rlcap0 ;
+    const I32 rlcap = max (4, (slab_cap / max (np, 1) - 4) & ~3) ;
     const I32 ecs_fit = (nrows + rlcap - 1) / rlcap ;
-    const I32 ecs_opt = (I32) sqrtf ((RPT > 0 ? 0.4f : 0.84f) * (float) nrows) ;
+    const I32 ecs_opt = (I32) sqrtf (0.84f * (float) nrows) ;
     unsigned ECS = (unsigned) max (1, min ((I32) G, max (ecs_fit, ecs_opt))) ;
     const bool idle = (k1 >= fn || done0) ;
     const I32 RL = max (4, (((nrows + (I32) ECS - 1) / (I32) ECS) + 3) & ~3) ;
     const I32 ldp = RL | 1 ;
-    const bool fits = ((I64) ldp * np <= (I64) slab_cap) && (RPT == 0 || RL <= NW * RPT) ;
+    const bool fits = ((I64) ldp * np <= (I64) slab_cap) ;
     // the staircase of the panel's columns is read inside panel_columns_smem: stage it before the barrier
     grid_barrier (g0) ;
     if (!idle && fits && cr < ECS)
@@ -1462,7 +1237,7 @@ __global__ void __launch_bounds__ (NT, 1) k_panel_grid (LevelArgs L, DSym S, DNu
         gc.red = N.gridred + (I64) slot * (2 * 148) ;
         gc.ctr = ctr + 128 ; gc.G = ECS ; gc.cr = cr ; gc.epoch = 0 ;
         gc.ll = N.gridll + (I64) slot * (2 * 148 * 128) ; gc.tagbase = seq * 64u ;
-        panel_columns_smem<NW, true, RPT> (cluster, gc, ECS, slab_cap, ldp, L, S, N, slot, f, k1, k2, parity, lrow0, nloc, g1,
+        panel_columns_smem<NW, true> (cluster, gc, ECS, slab_cap, ldp, L, S, N, slot, f, k1, k2, parity, lrow0, nloc, g1,
             RL, rend, xch, nullptr, nullptr, cols, tq) ;
     }
     else if (cr == 0 && tid == 0)

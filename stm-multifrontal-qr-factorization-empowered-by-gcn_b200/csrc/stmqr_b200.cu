@@ -17,6 +17,7 @@
 #include <deque>
 #include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <set>
 #include <string>
@@ -341,16 +342,53 @@ void free_all (stmqr_handle h)
     h->solveZ_cap = h->solveX_cap = h->solveIO_cap = 0 ;
 }
 
+// host threads of the planner (the plan is pure host work on the symbolic object: STMQR_B200_PLAN_THREADS, default
+// min (16, cores))
+inline int plan_threads ()
+{
+    static const int nt = [] {
+        int t = (int) std::min<unsigned> (16u, std::max<unsigned> (1u, std::thread::hardware_concurrency ())) ;
+        if (const char *e = getenv ("STMQR_B200_PLAN_THREADS")) t = std::max (1, std::min (64, atoi (e))) ;
+        return t ;
+    } () ;
+    return nt ;
+}
+
+// run task (i), i = 0 .. ntasks-1, on the planner's threads (tasks are handed out by an atomic counter)
+// task (i, worker) with worker < plan_threads (): per-worker scratch can be allocated once by the caller
+template <typename F> void parallel_tasks (I64 ntasks, F &&task)
+{
+    const int nt = (int) std::min<I64> (plan_threads (), ntasks) ;
+    if (nt <= 1) { for (I64 i = 0 ; i < ntasks ; i++) task (i, 0) ; return ; }
+    std::atomic<I64> next {0} ;
+    auto worker = [&] (int me) { for (I64 i ; (i = next.fetch_add (1)) < ntasks ; ) task (i, me) ; } ;
+    std::vector<std::thread> th ;
+    for (int t = 1 ; t < nt ; t++) th.emplace_back (worker, t) ;
+    worker (0) ;
+    for (auto &t : th) t.join () ;
+}
+
+// int64 -> int32 with an overflow check (branch-free: the loop vectorises); large arrays in parallel slices
 bool narrow (const int64_t *src, I64 count, std::vector<I32> &dst)
 {
-    dst.resize ((size_t) count) ;
-    for (I64 i = 0 ; i < count ; i++)
-    {
-        int64_t v = src [i] ;
-        if (v < INT32_MIN || v > INT32_MAX) return false ;
-        dst [(size_t) i] = (I32) v ;
-    }
-    return true ;
+    dst.resize ((size_t) std::max<I64> (count, 0)) ;
+    if (count <= 0) return true ;
+    const I64 slice = 1 << 18 ;
+    const I64 ns = (count + slice - 1) / slice ;
+    std::atomic<int> bad {0} ;
+    I32 *d = dst.data () ;
+    parallel_tasks (ns, [&] (I64 t, int) {
+        const I64 a = t * slice, b = std::min (count, a + slice) ;
+        uint64_t acc = 0 ;
+        for (I64 i = a ; i < b ; i++)
+        {
+            const int64_t v = src [i] ;
+            acc |= (uint64_t) (v + 0x80000000LL) >> 32 ;
+            d [i] = (I32) v ;
+        }
+        if (acc) bad.store (1) ;
+    }) ;
+    return bad.load () == 0 ;
 }
 
 inline void prof_begin (stmqr_handle h, int cls)
@@ -547,62 +585,78 @@ int partition_fronts (I64 nf, const int64_t *Childp, const int64_t *Child, const
 class ArenaReplay
 {
 public:
-    I64 high = 0 ;
-    I64 alloc (I64 size)
-    {
-        size = (size + 1) & ~(I64) 1 ;                      // 16-byte granules
-        if (size <= 0) return 0 ;
-        auto it = by_size.lower_bound (std::make_pair (size, (I64) -1)) ;      // best fit, lowest offset among equals
-        if (it == by_size.end ())
-        {
-            // grow at the top (merging with a free block that touches the top)
-            I64 off = high ;
-            if (!by_off.empty ())
-            {
-                auto last = std::prev (by_off.end ()) ;
-                if (last->first + last->second == high)
-                {
-                    off = last->first ;
-                    by_size.erase (std::make_pair (last->second, last->first)) ;
-                    by_off.erase (last) ;
-                }
-            }
-            high = off + size ;
-            return off ;
-        }
-        const I64 bsz = it->first, off = it->second ;
-        by_size.erase (it) ;
-        by_off.erase (off) ;
-        if (bsz > size) insert (off + size, bsz - size) ;
-        return off ;
-    }
+    I64 high = 0, peak = 0 ;            // current top of the arena, and its high-water mark (= the capacity needed)
+    // holes of the arena, sorted by offset, never adjacent (merged on release)
+    std::vector<std::pair<I64, I64>> holes ;        // (offset, size)
+    // blocks released since the last merge (the assembly of one level releases all its children at once)
+    std::vector<std::pair<I64, I64>> freed ;
     void release (I64 off, I64 size)
     {
         size = (size + 1) & ~(I64) 1 ;
-        if (size <= 0) return ;
-        auto nx = by_off.lower_bound (off) ;
-        if (nx != by_off.end () && off + size == nx->first)
+        if (size > 0) freed.emplace_back (off, size) ;
+    }
+    // fold the released blocks into the hole list: one sort of the level's releases, one linear merge
+    void merge_freed ()
+    {
+        if (freed.empty ()) return ;
+        std::sort (freed.begin (), freed.end ()) ;
+        std::vector<std::pair<I64, I64>> out ;
+        out.reserve (holes.size () + freed.size ()) ;
+        size_t a = 0, b = 0 ;
+        auto push = [&] (const std::pair<I64, I64> &x) {
+            if (!out.empty () && out.back ().first + out.back ().second == x.first) out.back ().second += x.second ;
+            else out.push_back (x) ;
+        } ;
+        while (a < holes.size () || b < freed.size ())
         {
-            size += nx->second ;
-            by_size.erase (std::make_pair (nx->second, nx->first)) ;
-            nx = by_off.erase (nx) ;
+            if (b >= freed.size () || (a < holes.size () && holes [a].first < freed [b].first)) push (holes [a++]) ;
+            else push (freed [b++]) ;
         }
-        if (nx != by_off.begin ())
+        // a hole that touches the top gives the space back
+        if (!out.empty () && out.back ().first + out.back ().second == high) { high = out.back ().first ; out.pop_back () ; }
+        holes.swap (out) ;
+        freed.clear () ;
+    }
+    // the blocks of one level: first fit decreasing.  Largest block first, every block goes into the LOWEST hole
+    // that can hold it (a max-tree over the offset-sorted holes answers that in O(log holes), and the hole shrinks
+    // in place), what fits nowhere grows the arena at the top.  Deterministic; O((holes + blocks) log holes) per
+    // level on flat arrays (a best-fit search tree of std::map / std::set nodes cost 130 ms on 110 000 fronts).
+    void alloc_level (std::vector<std::pair<I64, I32>> &want, std::vector<I64> &Coff)
+    {
+        merge_freed () ;
+        if (want.empty ()) return ;
+        std::sort (want.begin (), want.end (), [] (const std::pair<I64, I32> &x, const std::pair<I64, I32> &y) {
+            return (x.first != y.first) ? x.first > y.first : x.second < y.second ; }) ;
+        const size_t H = holes.size () ;
+        size_t base = 1 ;
+        while (base < std::max<size_t> (H, 1)) base <<= 1 ;
+        tree.assign (2 * base, 0) ;
+        for (size_t k = 0 ; k < H ; k++) tree [base + k] = holes [k].second ;
+        for (size_t k = base - 1 ; k >= 1 ; k--) tree [k] = std::max (tree [2*k], tree [2*k+1]) ;
+        for (const auto &wb : want)
         {
-            auto pv = std::prev (nx) ;
-            if (pv->first + pv->second == off)
+            const I64 size = (wb.first + 1) & ~(I64) 1 ;
+            const I32 f = wb.second ;
+            if (H > 0 && tree [1] >= size)
             {
-                off = pv->first ; size += pv->second ;
-                by_size.erase (std::make_pair (pv->second, pv->first)) ;
-                by_off.erase (pv) ;
+                size_t k = 1 ;
+                while (k < base) k = (tree [2*k] >= size) ? 2*k : 2*k + 1 ;
+                auto &hole = holes [k - base] ;
+                Coff [f] = hole.first ;
+                hole.first += size ; hole.second -= size ;
+                tree [k] = hole.second ;
+                for (k >>= 1 ; k >= 1 ; k >>= 1) tree [k] = std::max (tree [2*k], tree [2*k+1]) ;
             }
+            else { Coff [f] = high ; high += size ; }
         }
-        insert (off, size) ;
+        peak = std::max (peak, high) ;
+        // drop the holes that were used up
+        size_t o = 0 ;
+        for (size_t k = 0 ; k < H ; k++) if (holes [k].second > 0) holes [o++] = holes [k] ;
+        holes.resize (o) ;
     }
 private:
-    void insert (I64 off, I64 size) { by_off [off] = size ; by_size.insert (std::make_pair (size, off)) ; }
-    std::map<I64, I64> by_off ;
-    std::set<std::pair<I64, I64>> by_size ;
+    std::vector<I64> tree ;
 } ;
 
 // Replays `phases` (level sets in processing order) and assigns Coff.  `received`: fronts whose block
@@ -614,10 +668,15 @@ void plan_contribution_arena (const std::vector<const LevelSet *> &phases, size_
     ArenaReplay A ;
     std::vector<unsigned char> live (Coff.size (), 0) ;
     std::fill (Coff.begin (), Coff.end (), (I64) 0) ;
+    std::vector<std::pair<I64, I32>> want ;
     for (size_t ph = 0 ; ph < phases.size () ; ph++)
     {
         if (ph == recv_before)
-            for (I32 c : received) if (Csize [c] > 0 && !live [c]) { Coff [c] = A.alloc (Csize [c]) ; live [c] = 1 ; }
+        {
+            want.clear () ;
+            for (I32 c : received) if (Csize [c] > 0 && !live [c]) { want.emplace_back (Csize [c], c) ; live [c] = 1 ; }
+            A.alloc_level (want, Coff) ;
+        }
         const LevelSet &LS = *phases [ph] ;
         for (const Level &Lv : LS.levels)
         {
@@ -632,14 +691,16 @@ void plan_contribution_arena (const std::vector<const LevelSet *> &phases, size_
                 }
             }
             // ... then the level's own blocks are packed
+            want.clear () ;
             for (I32 i = 0 ; i < Lv.count ; i++)
             {
                 const I32 f = LS.fronts [Lv.first + i] ;
-                if (Csize [f] > 0 && !live [f]) { Coff [f] = A.alloc (Csize [f]) ; live [f] = 1 ; }
+                if (Csize [f] > 0 && !live [f]) { want.emplace_back (Csize [f], f) ; live [f] = 1 ; }
             }
+            A.alloc_level (want, Coff) ;
         }
     }
-    cap = A.high + 2 ;
+    cap = A.peak + 2 ;
 }
 
 constexpr I32 SMALL_CLASS_ELEMS [2] = {2048, 1024} ;     // boundaries between the shared-memory classes
@@ -950,19 +1011,11 @@ int stmqr_b200_create (int device, stmqr_handle *out)
             (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (8) + PANEL_XR_DOUBLES) * (int) sizeof (double)) == cudaSuccess &&
         cudaFuncSetAttribute (k_panel_cluster<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (16)) * (int) sizeof (double)) == cudaSuccess &&
-        cudaFuncSetAttribute (k_panel_cluster<256, 1, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (8) + PANEL_XR_DOUBLES) * (int) sizeof (double)) == cudaSuccess &&
-        cudaFuncSetAttribute (k_panel_cluster<256, 2, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (8) + PANEL_XR_DOUBLES) * (int) sizeof (double)) == cudaSuccess &&
-        cudaFuncSetAttribute (k_panel_cluster<128, 4, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (4) + PANEL_XR_DOUBLES) * (int) sizeof (double)) == cudaSuccess &&
         cudaFuncSetAttribute (k_panel_cluster<128, 6>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
         cudaFuncSetAttribute (k_panel_cluster<256, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
         cudaFuncSetAttribute (k_panel_cluster<512, 1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-        cudaFuncSetAttribute (k_panel_grid<512, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute (k_panel_grid, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (16)) * (int) sizeof (double)) == cudaSuccess &&
-        cudaFuncSetAttribute (k_panel_grid<256, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (8)) * (int) sizeof (double)) == cudaSuccess &&
         cudaFuncSetAttribute (k_update_dmma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (int) update_smem_bytes<2> ()) == cudaSuccess &&
         cudaFuncSetAttribute (k_update_dmma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1048,8 +1101,17 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
 {
     if (!h || !sym) return STMQR_ERR_INVALID ;
     auto t0 = std::chrono::steady_clock::now () ;
+    static const bool plan_times = getenv ("STMQR_B200_PLAN_TIMES") != nullptr ;
+    auto tmark = t0 ;
+    auto PLAN_MARK = [&] (const char *what) {
+        if (!plan_times) return ;
+        auto t = std::chrono::steady_clock::now () ;
+        fprintf (stderr, "STMQR_B200_PLAN_TIMES %8.2f ms  %s\n", std::chrono::duration<double, std::milli> (t - tmark).count (), what) ;
+        tmark = t ;
+    } ;
     if (!h->host_only) cudaSetDevice (h->device) ;
     free_all (h) ;
+    PLAN_MARK ("free_all") ;
     h->err.clear () ;
     const I64 m = sym->m, n = sym->n, nf = sym->nf, anz = sym->anz, rjsize = sym->rjsize,
         hisize = sym->hisize ;
@@ -1085,6 +1147,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
         Qfill32 [(size_t) k] = (I32) j ;
     }
 
+    PLAN_MARK ("narrow + Qinv") ;
     // ---- parent of each front, etree levels (all fronts of a level are independent) --------------
     std::vector<I32> parent ((size_t) nf, -1), level ((size_t) nf, 0) ;
     for (I64 f = 0 ; f < nf ; f++)
@@ -1114,49 +1177,83 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
             }
         }
     }
+    PLAN_MARK ("parent + levels") ;
     h->h_Foff.assign ((size_t) nf, 0) ; h->h_Coff.assign ((size_t) nf, 0) ; h->h_Csize.assign ((size_t) nf, 0) ;
     h->h_Rbound.assign ((size_t) nf, 0) ; h->Rcap_owned = 0 ;
-    // ---- contribution-block arena (bound sizes) and R+H arena bound ------------------------------
-    // csize bound: qr_analyze's Cm[f] rows by cn columns (SparseQR_analyze.c:536-550).
-    // R+H bound per front: sum_j min (max (j+1, Stair_j), fm) with the bound staircase (:559-573).
+    // ---- one pass over the fronts (in parallel slices, every slice with its own column map):
+    //   * contribution-block bound: qr_analyze's Cm[f] rows by cn columns (SparseQR_analyze.c:536-550)
+    //   * R+H bound per front: sum_j min (max (j+1, Stair_j), fm) with the bound staircase (:559-573)
+    //   * the symbolic maps Cj (child column -> column of the parent front) and Sjf (S entry -> front column)
+    std::vector<I32> Cj ((size_t) std::max<I64> (rjsize, 1), 0), Sjf ((size_t) std::max<I64> (anz, 1), 0) ;
     {
-        I64 coff = 0, rcap = 0 ;
-        std::vector<I32> stairB ((size_t) std::max<I64> (sym->maxfn, 1)) ;
-        std::vector<I32> Fmap ((size_t) std::max<I64> (n, 1)) ;
-        for (I64 f = 0 ; f < nf ; f++)
+        const I64 nslice = std::max<I64> (1, std::min<I64> (nf, 8 * (I64) plan_threads ())) ;
+        std::vector<I64> cut ((size_t) nslice + 1, nf) ;
+        cut [0] = 0 ;
         {
-            const I64 fp = Super [f+1] - Super [f], fn = Rp [f+1] - Rp [f] ;
-            const I64 cn = fn - fp, cm = std::min<I64> (CmB [f], cn) ;
-            const I64 csize = (cm * (cm + 1)) / 2 + cm * (cn - cm) ;
-            h->h_Csize [f] = csize ;
-            coff += (csize + 1) & ~(I64) 1 ;
-            // staircase bound
-            for (I64 j = 0 ; j < fn ; j++) Fmap [Rj [Rp [f] + j]] = (I32) j ;
-            for (I64 j = 0 ; j < fn ; j++)
-                stairB [j] = (j < fp) ? (Sleft [Super [f]+j+1] - Sleft [Super [f]+j]) : 0 ;
-            for (I32 q = Childp [f] ; q < Childp [f+1] ; q++)
+            // slices of about equal work: by position in Rj (columns of the fronts) plus the front count
+            const double total = (double) rjsize + (double) nf ;
+            I64 f = 0 ;
+            for (I64 t = 1 ; t < nslice ; t++)
             {
-                const I32 c = Child [q] ;
-                const I64 fpc = Super [c+1] - Super [c] ;
-                const I64 cnc = (Rp [c+1] - Rp [c]) - fpc ;
-                const I64 cmc = std::min<I64> (CmB [c], cnc) ;
-                for (I64 ci = 0 ; ci < cmc ; ci++) stairB [Fmap [Rj [Rp [c] + fpc + ci]]]++ ;
+                const double goal = total * (double) t / (double) nslice ;
+                while (f < nf && (double) Rp [f] + (double) f < goal) f++ ;
+                cut [(size_t) t] = f ;
             }
-            I64 fm = 0, rh = 0, run = 0 ;
-            for (I64 j = 0 ; j < fn ; j++) fm += stairB [j] ;
-            for (I64 j = 0 ; j < fn ; j++)
-            {
-                run += stairB [j] ;
-                rh += std::min<I64> (std::max<I64> (j + 1, run), fm) ;
-            }
-            if (fm > FmB [f]) FmB [f] = (I32) fm ;     // never trust a smaller bound
-            rcap += rh ;
-            h->h_Rbound [(size_t) f] = rh ;
         }
+        const I64 maxfn1 = std::max<I64> (sym->maxfn, 1) ;
+        // per-worker scratch, allocated without initialisation (every entry is written before it is read)
+        const int nwk = plan_threads () ;
+        std::vector<std::unique_ptr<I32 []>> FmapW ((size_t) nwk), stairW ((size_t) nwk) ;
+        parallel_tasks (nslice, [&] (I64 t, int me) {
+            if (!FmapW [(size_t) me])
+            {
+                FmapW [(size_t) me].reset (new I32 [(size_t) std::max<I64> (n, 1)]) ;
+                stairW [(size_t) me].reset (new I32 [(size_t) maxfn1]) ;
+            }
+            I32 *const Fmap = FmapW [(size_t) me].get (), *const stairB = stairW [(size_t) me].get () ;
+            for (I64 f = cut [(size_t) t] ; f < cut [(size_t) t + 1] ; f++)
+            {
+                const I64 p1 = Rp [f], col1 = Super [f] ;
+                const I64 fp = Super [f+1] - col1, fn = Rp [f+1] - p1 ;
+                const I64 cn = fn - fp, cm = std::min<I64> (CmB [f], cn) ;
+                h->h_Csize [f] = (cm * (cm + 1)) / 2 + cm * (cn - cm) ;
+                for (I64 j = 0 ; j < fn ; j++) Fmap [Rj [p1 + j]] = (I32) j ;
+                for (I64 j = 0 ; j < fn ; j++)
+                    stairB [j] = (j < fp) ? (Sleft [col1+j+1] - Sleft [col1+j]) : 0 ;
+                for (I32 r = Sleft [col1] ; r < Sleft [col1+fp] ; r++)
+                    for (I32 pz = Sp [r] ; pz < Sp [r+1] ; pz++) Sjf [pz] = Fmap [Sj [pz]] ;
+                for (I32 q = Childp [f] ; q < Childp [f+1] ; q++)
+                {
+                    const I32 c = Child [q] ;
+                    const I64 fpc = Super [c+1] - Super [c] ;
+                    const I64 cnc = (Rp [c+1] - Rp [c]) - fpc ;
+                    const I64 cmc = std::min<I64> (CmB [c], cnc) ;
+                    const I64 pc = Rp [c] + fpc ;
+                    for (I64 ci = 0 ; ci < cnc ; ci++)
+                    {
+                        const I32 j = Fmap [Rj [pc + ci]] ;
+                        Cj [pc + ci] = j ;
+                        if (ci < cmc) stairB [j]++ ;
+                    }
+                }
+                I64 fm = 0, rh = 0, run = 0 ;
+                for (I64 j = 0 ; j < fn ; j++) fm += stairB [j] ;
+                for (I64 j = 0 ; j < fn ; j++)
+                {
+                    run += stairB [j] ;
+                    rh += std::min<I64> (std::max<I64> (j + 1, run), fm) ;
+                }
+                if (fm > FmB [f]) FmB [f] = (I32) fm ;     // never trust a smaller bound
+                h->h_Rbound [(size_t) f] = rh ;
+            }
+        }) ;
+        I64 coff = 0, rcap = 0 ;
+        for (I64 f = 0 ; f < nf ; f++) { coff += (h->h_Csize [f] + 1) & ~(I64) 1 ; rcap += h->h_Rbound [(size_t) f] ; }
         h->Ccap_all = coff ;
         h->Rcap = rcap + 16 ;
     }
 
+    PLAN_MARK ("bounds + Cj + Sjf maps") ;
     I32 nlev = 0 ;
     for (I64 f = 0 ; f < nf ; f++) nlev = std::max (nlev, level [f] + 1) ;
     std::vector<std::vector<I32>> byLevel ((size_t) nlev) ;
@@ -1191,25 +1288,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
         h->ls_all.levels.push_back (L) ;
     }
 
-    // ---- symbolic maps: Cj (child column -> parent column), Sjf (S entry -> front column) -------
-    std::vector<I32> Cj ((size_t) std::max<I64> (rjsize, 1), 0), Sjf ((size_t) std::max<I64> (anz, 1), 0) ;
-    {
-        std::vector<I32> Fmap ((size_t) std::max<I64> (n, 1), -1) ;
-        for (I64 f = 0 ; f < nf ; f++)
-        {
-            const I64 p1 = Rp [f], fn = Rp [f+1] - p1, col1 = Super [f], fp = Super [f+1] - col1 ;
-            for (I64 j = 0 ; j < fn ; j++) Fmap [Rj [p1+j]] = (I32) j ;
-            for (I32 r = Sleft [col1] ; r < Sleft [col1+fp] ; r++)
-                for (I32 p = Sp [r] ; p < Sp [r+1] ; p++) Sjf [p] = Fmap [Sj [p]] ;
-            for (I32 q = Childp [f] ; q < Childp [f+1] ; q++)
-            {
-                const I32 c = Child [q] ;
-                const I64 fpc = Super [c+1] - Super [c] ;
-                for (I64 p = Rp [c] + fpc ; p < Rp [c+1] ; p++) Cj [p] = Fmap [Rj [p]] ;
-            }
-        }
-    }
-
+    PLAN_MARK ("level sets") ;
     // ---- device memory -----------------------------------------------------------------------------
     h->h_Super = Super ; h->h_Rp = Rp ; h->h_Hip = Hip ; h->h_FmB = FmB ;
     DSym &S = h->S ;
@@ -1235,6 +1314,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
             h->Ccap = coff + 2 ;
         }
     }
+    PLAN_MARK ("uploads + contribution arena plan") ;
     UPLOAD (p64, h->h_Coff) ; S.Coff = p64 ; h->d_Coff = p64 ;
     UPLOAD (h->ls_all.d_fronts, h->ls_all.fronts) ;
     h->d_owned = nullptr ; h->N.owned = nullptr ;
@@ -1282,6 +1362,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
             CK (cudaMemsetAsync (N.griderr, 0, sizeof (I32), h->stream)) ;
         }
     }
+    PLAN_MARK ("arena allocations") ;
     ALLOC (N.stair, rjsize) ;
     ALLOC (N.Cmap, rjsize) ;
     ALLOC (N.rowpos, m) ;
@@ -1306,23 +1387,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
     ALLOC (N.base1, nf) ; ALLOC (N.base2, nf) ;
     ALLOC (h->d_err, 1) ;
     ALLOC (h->d_hcol, rjsize) ; ALLOC (h->d_nh, nf) ;
-    {
-        // transpose of Rj (column of R -> its positions in Rj, ascending = in front order) and the front of
-        // every position: symbolic inputs of the device R extraction (k_rcol_scan, k_rcount, k_rfill)
-        std::vector<I32> RjTp ((size_t) n + 1, 0), RjTi ((size_t) std::max<I64> (rjsize, 1)), posfront ((size_t) std::max<I64> (rjsize, 1)) ;
-        for (I64 pz = 0 ; pz < rjsize ; pz++) RjTp [(size_t) Rj [pz] + 1]++ ;
-        for (I64 j = 0 ; j < n ; j++) RjTp [(size_t) j + 1] += RjTp [(size_t) j] ;
-        std::vector<I32> cur (RjTp.begin (), RjTp.end () - 1) ;
-        for (I64 f = 0 ; f < nf ; f++)
-            for (I32 pz = Rp [f] ; pz < Rp [f+1] ; pz++)
-            {
-                posfront [pz] = (I32) f ;
-                RjTi [cur [Rj [pz]]++] = pz ;
-            }
-        UPLOAD (h->d_RjTp, RjTp) ; UPLOAD (h->d_RjTi, RjTi) ; UPLOAD (h->d_posfront, posfront) ;
-        ALLOC (h->d_rlen, rjsize) ; ALLOC (h->d_rcnt, rjsize) ; ALLOC (h->d_roff, rjsize) ;
-        ALLOC (h->d_Rcolp, n + 2) ;
-    }
+    ALLOC (h->d_rlen, rjsize) ;         // R part length of every front column (k_htable; the R extraction tables are lazy)
     ALLOC (h->d_HPinv64, m) ;
     ALLOC (h->d_Hii64, hisize) ;
     ALLOC (h->d_wide, rjsize + 2 * nf + 2) ;
@@ -1334,7 +1399,9 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
         ALLOC (h->d_capA, h->h_capOff [nf]) ;
         ALLOC (h->d_capF, h->h_capOff [nf]) ;
     }
+    PLAN_MARK ("remaining allocations") ;
     if (!h->host_only) CK (cudaStreamSynchronize (h->stream)) ;
+    PLAN_MARK ("stream sync") ;
     h->analyzed = true ;
     memset (&h->stats, 0, sizeof (h->stats)) ;
     h->stats.ms_plan = std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now () - t0).count () ;
@@ -1486,7 +1553,9 @@ static int run_level (stmqr_handle h, const LevelSet &LS, const Level &Lv, long 
         const I32 nbig = Lv.nbig ;
         const int nsl = (int) std::min<I64> (148, std::max<I64> (1, Lv.maxFelems / 8192)) ;
         auto big_path = [&] () -> int {
-        LAUNCH (1, k_front_setup<<<nbig, 128, 0, st>>> (fr, S, N)) ;
+        // one CTA per front: as many threads as the widest front of the level can use (scans and per-column loops)
+        const int fthreads = (Lv.maxfn >= 2048) ? 1024 : ((Lv.maxfn >= 512) ? 512 : ((Lv.maxfn >= 192) ? 256 : 128)) ;
+        LAUNCH (1, k_front_setup<<<nbig, fthreads, 0, st>>> (fr, S, N)) ;
         // levels with large fronts: the ACTUAL # rows of the tallest front decides which kernels run
         // (the symbolic bound is ~2x too big under rank detection).  One tiny read-back per such level.
         I32 actFm = Lv.maxFm ;
@@ -1545,16 +1614,6 @@ static int run_level (stmqr_handle h, const LevelSet &LS, const Level &Lv, long 
         // fronts too tall for a cluster of 8 shared-memory slabs: G CTAs per front with a global-memory
         // exchange (k_panel_grid), as many fronts per launch as fit one CTA per SM
         const bool gridpanel = (actFm >= h->grid_rows) && PB == PANEL_MAX && !(h->opt.reserved & 4) ;
-        // register-resident slabs (kernels_panel.cuh): 8 warps x 48 rows (one CTA per SM), 8 x 24 (two per SM) or
-        // 4 x 24 (four per SM); a level whose slabs need more than 384 rows keeps the shared-memory column loop
-        int regrpt = 0 ;
-        if ((h->opt.reserved & 128) && PB == PANEL_MAX && !gridpanel)       // bit 7: register-resident slabs (A/B: measured slower)
-        {
-            auto rl = [&] (int c) { return (I64) ((((actFm + c - 1) / c) + 3) & ~3) ; } ;
-            int cs = CS ;
-            while (cs < PANEL_CLUSTER_MAX && rl (cs) > 8 * 48) cs *= 2 ;
-            if (rl (cs) <= 8 * 48) { CS = cs ; regrpt = (rl (cs) <= 8 * 24) ? 24 : 48 ; }
-        }
         const I64 rowsPerCta = ((I64) (actFm + CS - 1) / CS + 7) & ~(I64) 3 ;
         // (at least 2 x 32 x 33 doubles: the leader builds T in the slab after writing it back)
         const I32 slabCap = (I32) std::max<I64> (2 * PANEL_MAX * (PANEL_MAX + 1),
@@ -1566,7 +1625,6 @@ static int run_level (stmqr_handle h, const LevelSet &LS, const Level &Lv, long 
         if (rowsPerCta <= h->panel128_rows && (I64) nbig >= 2 * (I64) h->nsm) pthreads = 128 ;
         if (((h->opt.reserved >> 16) & 0xff) >= 16 && rowsPerCta >= 256 && CS == 1) pthreads = 512 ;
         if ((h->opt.reserved >> 16) & 0xff) pthreads = std::min (pthreads, 32 * ((h->opt.reserved >> 16) & 0xff)) ;   // tuning
-        if (regrpt) pthreads = (regrpt == 24 && pthreads == 128 && rowsPerCta <= 4 * 24) ? 128 : 256 ;
         // number of fronts of the level with more than k columns (sorted by # columns descending)
         auto active_at = [&] (I32 k, I32 hi) -> I32 {
             I32 lo = 0 ;
@@ -1578,15 +1636,12 @@ static int run_level (stmqr_handle h, const LevelSet &LS, const Level &Lv, long 
             }
             return lo ;
         } ;
-        // (register slabs: 8 warps x 48 rows per CTA; shared-memory slabs: 760 rows)
-        const bool gridreg = gridpanel && (h->opt.reserved & 128) && ((I64) actFm + 383) / 384 <= h->nsm ;
-        const I32 gneed = gridreg ? (I32) (((I64) actFm + 383) / 384) : (I32) (((I64) actFm + 8 + 759) / 760) ;
+        const I32 gneed = (I32) (((I64) actFm + 8 + 759) / 760) ;
         auto launch_panel = [&] (I32 active, I32 k1, I32 parity) -> cudaError_t {
             if (gridpanel && gneed <= h->nsm)
             {
                 const I32 per = std::max<I32> (1, h->nsm / gneed) ;
-                const I32 gslab = gridreg ? (I32) (8 * 48 + 4) * PANEL_MAX : (I32) PANEL_SLAB_MAX_DOUBLES ;
-                const size_t smem = (size_t) (gslab + panel_scratch_doubles (gridreg ? 8 : 16)) * sizeof (double) ;
+                const size_t smem = (size_t) (PANEL_SLAB_MAX_DOUBLES + panel_scratch_doubles (16)) * sizeof (double) ;
                 for (I32 s0 = 0 ; s0 < active ; s0 += per)
                 {
                     const I32 nb = std::min<I32> (per, active - s0) ;
@@ -1594,8 +1649,8 @@ static int run_level (stmqr_handle h, const LevelSet &LS, const Level &Lv, long 
                     // become resident before the panel starts)
                     const I32 G = std::min<I32> (std::min<I32> (h->nsm / nb, std::max<I32> (gneed, h->grid_maxg)),
                         std::max<I32> (gneed, (I32) std::sqrt (0.84 * (double) actFm) + 1)) ;
-                    if (gridreg) k_panel_grid<256, 48><<<(unsigned) (G * nb), 256, smem, st>>> (L, S, N, k1, (I32) PB, parity, gslab, G, s0, ++h->grid_seq) ;
-                    else k_panel_grid<512, 0><<<(unsigned) (G * nb), 512, smem, st>>> (L, S, N, k1, (I32) PB, parity, gslab, G, s0, ++h->grid_seq) ;
+                    k_panel_grid<<<(unsigned) (G * nb), 512, smem, st>>> (L, S, N, k1, (I32) PB, parity,
+                        (I32) PANEL_SLAB_MAX_DOUBLES, G, s0, ++h->grid_seq) ;
                     if (s0 + per < active) h->launches++ ;
                 }
                 return cudaGetLastError () ;
@@ -1609,9 +1664,6 @@ static int run_level (stmqr_handle h, const LevelSet &LS, const Level &Lv, long 
             at [0].id = cudaLaunchAttributeClusterDimension ;
             at [0].val.clusterDim.x = CS ; at [0].val.clusterDim.y = 1 ; at [0].val.clusterDim.z = 1 ;
             cfg.attrs = at ; cfg.numAttrs = 1 ;
-            if (regrpt == 48) return cudaLaunchKernelEx (&cfg, k_panel_cluster<256, 1, 48>, L, S, N, k1, (I32) PB, parity, slabCap) ;
-            if (regrpt == 24 && pthreads == 256) return cudaLaunchKernelEx (&cfg, k_panel_cluster<256, 2, 24>, L, S, N, k1, (I32) PB, parity, slabCap) ;
-            if (regrpt == 24) return cudaLaunchKernelEx (&cfg, k_panel_cluster<128, 4, 24>, L, S, N, k1, (I32) PB, parity, slabCap) ;
             if (pthreads == 128) return cudaLaunchKernelEx (&cfg, k_panel_cluster<128, 6>, L, S, N, k1, (I32) PB, parity, slabCap) ;
             if (pthreads == 256) return cudaLaunchKernelEx (&cfg, k_panel_cluster<256, 2>, L, S, N, k1, (I32) PB, parity, slabCap) ;
             return cudaLaunchKernelEx (&cfg, k_panel_cluster<512, 1>, L, S, N, k1, (I32) PB, parity, slabCap) ;
@@ -1807,7 +1859,7 @@ static int run_level (stmqr_handle h, const LevelSet &LS, const Level &Lv, long 
             }
         }
         check ("front QR", 0, 0) ;
-        LAUNCH (5, k_front_finish<<<nbig, 128, 0, st>>> (fr, S, N)) ;
+        LAUNCH (5, k_front_finish<<<nbig, fthreads, 0, st>>> (fr, S, N)) ;
         return STMQR_OK ;
         } ;
         if (nbig > 0) { const int sb = big_path () ; if (sb != STMQR_OK) return sb ; }
@@ -2260,6 +2312,7 @@ int stmqr_b200_set_ownership (stmqr_handle h, int nparts, int mypart, const int3
     {
         ArenaReplay A ;
         std::vector<unsigned char> live ((size_t) std::max<I64> (nf, 1), 0) ;
+        std::vector<std::pair<I64, I32>> want ;
         std::fill (h->h_Coff.begin (), h->h_Coff.end (), (I64) 0) ;
         size_t li = 0 ;
         for (I64 gl = 0 ; gl < nlev ; gl++)
@@ -2276,22 +2329,26 @@ int stmqr_b200_set_ownership (stmqr_handle h, int nparts, int mypart, const int3
                         if (live [c]) { A.release (h->h_Coff [c], h->h_Csize [c]) ; live [c] = 0 ; }
                     }
                 }
+                want.clear () ;
                 for (I32 i = 0 ; i < Lv.count ; i++)
                 {
                     const I32 f = h->ls_mine.fronts [Lv.first + i] ;
-                    if (h->h_Csize [f] > 0) { h->h_Coff [f] = A.alloc (h->h_Csize [f]) ; live [f] = 1 ; }
+                    if (h->h_Csize [f] > 0) { want.emplace_back (h->h_Csize [f], f) ; live [f] = 1 ; }
                 }
+                A.alloc_level (want, h->h_Coff) ;
             }
+            want.clear () ;
             for (int e : h->xedges [(size_t) gl])
                 if (h->xall_dst [e] == mypart)
                 {
                     const I32 c = h->xall_c [e] ;
-                    if (h->h_Csize [c] > 0) { h->h_Coff [c] = A.alloc (h->h_Csize [c]) ; live [c] = 1 ; }
+                    if (h->h_Csize [c] > 0) { want.emplace_back (h->h_Csize [c], c) ; live [c] = 1 ; }
                 }
+            A.alloc_level (want, h->h_Coff) ;
             // (blocks sent away stay allocated: live[] is only cleared by a local parent)
             for (int e : h->xedges [(size_t) gl]) if (h->xall_src [e] == mypart) live [h->xall_c [e]] = 0 ;
         }
-        const I64 cap = A.high + 2 ;
+        const I64 cap = A.peak + 2 ;
         h->Ccap = cap ;
         if (h->host_only)
         {
@@ -2738,6 +2795,33 @@ int stmqr_b200_solve_ls (stmqr_handle h, int64_t nrhs, const double *B, double *
     return STMQR_OK ;
 }
 
+// Symbolic inputs of the device R extraction, built on first use (the drop-in's numeric phase never needs them):
+// the transpose of Rj (column of R -> its positions in Rj, ascending = in front order) and the front of every
+// position (k_rcol_scan, k_rcount, k_rfill).
+static int ensure_rconvert_tables (stmqr_handle h)
+{
+    if (h->d_RjTp) return STMQR_OK ;
+    const I64 n = h->n, nf = h->nf, rjsize = h->rjsize ;
+    std::vector<I32> Rj ((size_t) std::max<I64> (rjsize, 1)) ;
+    if (rjsize > 0) CK (cudaMemcpy (Rj.data (), h->S.Rj, (size_t) rjsize * sizeof (I32), cudaMemcpyDeviceToHost)) ;
+    const std::vector<I32> &Rp = h->h_Rp ;
+    std::vector<I32> RjTp ((size_t) n + 1, 0), RjTi ((size_t) std::max<I64> (rjsize, 1)), posfront ((size_t) std::max<I64> (rjsize, 1)) ;
+    for (I64 pz = 0 ; pz < rjsize ; pz++) RjTp [(size_t) Rj [pz] + 1]++ ;
+    for (I64 j = 0 ; j < n ; j++) RjTp [(size_t) j + 1] += RjTp [(size_t) j] ;
+    std::vector<I32> cur (RjTp.begin (), RjTp.end () - 1) ;
+    for (I64 f = 0 ; f < nf ; f++)
+        for (I32 pz = Rp [f] ; pz < Rp [f+1] ; pz++)
+        {
+            posfront [pz] = (I32) f ;
+            RjTi [cur [Rj [pz]]++] = pz ;
+        }
+    UPLOAD (h->d_RjTp, RjTp) ; UPLOAD (h->d_RjTi, RjTi) ; UPLOAD (h->d_posfront, posfront) ;
+    ALLOC (h->d_rcnt, rjsize) ; ALLOC (h->d_roff, rjsize) ;
+    ALLOC (h->d_Rcolp, n + 2) ;
+    CK (cudaStreamSynchronize (h->stream)) ;        // (the host vectors go out of scope)
+    return STMQR_OK ;
+}
+
 // -------------------------------------------------------------------------------------------------
 // R as a compressed-column matrix (qr_rcount / qr_rconvert on the device, kernels_solve.cuh)
 // -------------------------------------------------------------------------------------------------
@@ -2746,6 +2830,7 @@ int stmqr_b200_rcount (stmqr_handle h, int64_t econ, int64_t *Rp_out, int64_t *n
     int s = solve_ready (h, "rcount") ;
     if (s != STMQR_OK) return s ;
     if (econ < 0) return fail (h, STMQR_ERR_INVALID, "rcount: econ < 0") ;
+    if ((s = ensure_rconvert_tables (h)) != STMQR_OK) return s ;
     cudaStream_t st = h->stream ;
     const I64 rj = h->rjsize, n = h->n ;
     if (h->rcount_econ != econ)
