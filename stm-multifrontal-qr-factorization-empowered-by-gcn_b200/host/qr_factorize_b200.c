@@ -50,6 +50,21 @@ static uint64_t hash_words (uint64_t h, const Long *a, Long count, Long max_samp
 {
     if (a == NULL || count <= 0) return mix64 (h, (uint64_t) count) ;
     Long stride = (max_samples > 0 && count > max_samples) ? (count + max_samples - 1) / max_samples : 1 ;
+    if (stride == 1)
+    {
+        /* four independent chains (the multiply-xor chain of one accumulator is latency bound), folded in a
+         * fixed order */
+        uint64_t h0 = h, h1 = h ^ 0x9e3779b97f4a7c15ULL, h2 = h + 0x632be59bd9b4e019ULL, h3 = ~h ;
+        Long i = 0 ;
+        for ( ; i + 3 < count ; i += 4)
+        {
+            h0 = mix64 (h0, (uint64_t) a [i]) ;   h1 = mix64 (h1, (uint64_t) a [i+1]) ;
+            h2 = mix64 (h2, (uint64_t) a [i+2]) ; h3 = mix64 (h3, (uint64_t) a [i+3]) ;
+        }
+        for ( ; i < count ; i++) h0 = mix64 (h0, (uint64_t) a [i]) ;
+        h = mix64 (mix64 (mix64 (h0, h1), h2), h3) ;
+        return mix64 (h, (uint64_t) count) ;
+    }
     for (Long i = 0 ; i < count ; i += stride) h = mix64 (h, (uint64_t) a [i]) ;
     if (stride > 1) for (Long i = (count > 512) ? count - 512 : 0 ; i < count ; i++) h = mix64 (h, (uint64_t) a [i]) ;
     return mix64 (h, (uint64_t) count) ;
