@@ -1567,8 +1567,8 @@ static int run_level (stmqr_handle h, const LevelSet &LS, const Level &Lv, long 
             actFm = std::min (Lv.maxFm, std::max (1, h->pin_lvl [0])) ;
         }
         {
-            // zero-fill at ~4 CTAs of 16-byte stores per SM over the whole level, then the scatter
-            const int nz = (int) std::min<I64> (148, std::max<I64> (1, std::min<I64> (Lv.maxFelems / 4096, (4 * (I64) h->nsm + nbig - 1) / nbig))) ;
+            // zero-fill at ~8 CTAs of 16-byte stores per SM over the whole level, then the scatter
+            const int nz = (int) std::min<I64> (148, std::max<I64> (1, std::min<I64> (Lv.maxFelems / 4096, (8 * (I64) h->nsm + nbig - 1) / nbig))) ;
             LAUNCH (2, k_zero_fronts<<<dim3 (nbig, nz), 256, 0, st>>> (fr, S, N)) ;
             LAUNCH (2, k_assemble<<<dim3 (nbig, nsl), 256, 0, st>>> (fr, S, N)) ;
         }
