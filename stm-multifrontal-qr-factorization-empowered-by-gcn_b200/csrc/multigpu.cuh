@@ -56,6 +56,14 @@ struct Transport
     // point-to-point traffic of one etree level: edges sorted by front id, the same list on both ends
     virtual int exchange (stmqr_handle h, const std::vector<XEdge> &edges, I32 glevel) = 0 ;
     virtual int allreduce (stmqr_handle h, void *p, I64 count, XType t, bool maxop) = 0 ;
+    // cooperative fronts (the trailing update of ONE large front spread over the GPUs, see run_level): plain
+    // byte transfers ordered on the engine's stream.  A transport without them never takes the cooperative path.
+    virtual bool cooperative () const { return false ; }
+    virtual int group_begin () { return STMQR_OK ; }
+    virtual int group_end () { return STMQR_OK ; }
+    virtual int bcast (stmqr_handle, void *, size_t, int) { return STMQR_ERR_INVALID ; }
+    virtual int send (stmqr_handle, const void *, size_t, int) { return STMQR_ERR_INVALID ; }
+    virtual int recv (stmqr_handle, void *, size_t, int) { return STMQR_ERR_INVALID ; }
     virtual std::string error () const { return err ; }
     std::string err ;
 } ;
@@ -72,6 +80,7 @@ struct NcclApi
     ncclResult_t (*Send) (const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr ;
     ncclResult_t (*Recv) (void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr ;
     ncclResult_t (*AllReduce) (const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr ;
+    ncclResult_t (*Broadcast) (const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr ;
     ncclResult_t (*GroupStart) () = nullptr ;
     ncclResult_t (*GroupEnd) () = nullptr ;
     const char *(*GetErrorString) (ncclResult_t) = nullptr ;
@@ -83,7 +92,7 @@ struct NcclApi
         if (!lib) return false ;
 #define NCCL_SYM(f) *(void **) (&f) = dlsym (lib, "nccl" #f) ; if (!f) { lib = nullptr ; return false ; }
         NCCL_SYM (GetUniqueId) NCCL_SYM (CommInitRank) NCCL_SYM (CommDestroy) NCCL_SYM (Send) NCCL_SYM (Recv)
-        NCCL_SYM (AllReduce) NCCL_SYM (GroupStart) NCCL_SYM (GroupEnd) NCCL_SYM (GetErrorString)
+        NCCL_SYM (AllReduce) NCCL_SYM (Broadcast) NCCL_SYM (GroupStart) NCCL_SYM (GroupEnd) NCCL_SYM (GetErrorString)
 #undef NCCL_SYM
         return true ;
     }
@@ -121,6 +130,12 @@ struct NcclTransport : Transport
     }
     int exchange (stmqr_handle h, const std::vector<XEdge> &edges, I32 glevel) override ;
     int allreduce (stmqr_handle h, void *p, I64 count, XType t, bool maxop) override ;
+    bool cooperative () const override { return nr > 1 ; }
+    int group_begin () override { return ok (g_nccl.GroupStart (), "ncclGroupStart") ? STMQR_OK : STMQR_ERR_CUDA ; }
+    int group_end () override { return ok (g_nccl.GroupEnd (), "ncclGroupEnd") ? STMQR_OK : STMQR_ERR_CUDA ; }
+    int bcast (stmqr_handle h, void *p, size_t bytes, int root) override ;
+    int send (stmqr_handle h, const void *p, size_t bytes, int dst) override ;
+    int recv (stmqr_handle h, void *p, size_t bytes, int src) override ;
 } ;
 
 // ---------------------------------------------------------------------------------------------

@@ -269,6 +269,19 @@ struct stmqr_handle_s
     std::vector<std::vector<int>> xedges ;          // per etree level: indices into xall of the edges leaving that level
     std::vector<I32> xall_c, xall_src, xall_dst ;   // all transfer edges (child front, owner of child, owner of parent)
     void *xptr = nullptr ;                          // PeerTransport: the array this handle contributes to the running all-reduce
+    // cooperative front (multi-GPU, one front per level): set by factorize_dist around run_level / coop_peer_level
+    struct Coop
+    {
+        bool armed = false ;                        // the level about to run may go cooperative (every GPU agrees: static test)
+        bool on = false ;                           // ... and it does (decided by the home GPU from the actual # rows)
+        int home = 0 ;                              // owner of the front
+        I32 f = -1, fn = 0 ;
+        std::vector<int> chunk_owner ;              // owner GPU of every chunk of COOP_CHUNK columns
+        double *stage = nullptr ; I64 stage_cap = 0 ;   // home: the block reflector in the compact layout that travels
+        int enabled = 1 ;                           // STMQR_B200_COOP=0 switches the path off, =2 forces it on 2 GPUs too
+        int min_parts = 3 ;                         // (measured: on 2 GPUs the home GPU's own share leaves nothing to gain)
+        I64 levels_run = 0 ;                        // statistics: cooperative levels of the last factorization
+    } coop ;
 
     stmqr_numeric_info info {} ;
     stmqr_stats stats {} ;
@@ -859,6 +872,22 @@ int NcclTransport::allreduce (stmqr_handle h, void *p, I64 count, XType t, bool 
     return STMQR_OK ;
 }
 
+int NcclTransport::bcast (stmqr_handle h, void *p, size_t bytes, int root)
+{
+    if (bytes == 0) return STMQR_OK ;
+    return ok (g_nccl.Broadcast (p, p, bytes, ncclChar, root, comm, h->stream), "ncclBroadcast") ? STMQR_OK : STMQR_ERR_CUDA ;
+}
+int NcclTransport::send (stmqr_handle h, const void *p, size_t bytes, int dst)
+{
+    if (bytes == 0) return STMQR_OK ;
+    return ok (g_nccl.Send (p, bytes, ncclChar, dst, comm, h->stream), "ncclSend") ? STMQR_OK : STMQR_ERR_CUDA ;
+}
+int NcclTransport::recv (stmqr_handle h, void *p, size_t bytes, int src)
+{
+    if (bytes == 0) return STMQR_OK ;
+    return ok (g_nccl.Recv (p, bytes, ncclChar, src, comm, h->stream), "ncclRecv") ? STMQR_OK : STMQR_ERR_CUDA ;
+}
+
 int PeerTransport::exchange (stmqr_handle h, const std::vector<XEdge> &edges, I32 glevel)
 {
     (void) glevel ;
@@ -991,6 +1020,7 @@ int stmqr_b200_create (int device, stmqr_handle *out)
     if (const char *e = getenv ("STMQR_B200_CLUSTER_ROWS")) h->cluster_rows = std::max (32, atoi (e)) ;
     if (const char *e = getenv ("STMQR_B200_FLAGS")) h->opt.reserved = (int32_t) strtol (e, nullptr, 0) ;
     if (const char *e = getenv ("STMQR_B200_SPECULATIVE")) h->speculative = atoi (e) ;
+    if (const char *e = getenv ("STMQR_B200_COOP")) h->coop.enabled = atoi (e) ;
     int prio_lo = 0, prio_hi = 0 ;
     bool ok = cudaSetDevice (device) == cudaSuccess &&
         cudaDeviceGetStreamPriorityRange (&prio_lo, &prio_hi) == cudaSuccess &&
@@ -1049,6 +1079,7 @@ void stmqr_b200_destroy (stmqr_handle h)
     cudaSetDevice (h->device) ;
     if (h->transport) { delete (Transport *) h->transport ; h->transport = nullptr ; }
     free_all (h) ;
+    if (h->coop.stage) { cudaFree (h->coop.stage) ; h->coop.stage = nullptr ; h->coop.stage_cap = 0 ; }
     if (h->ev0) cudaEventDestroy (h->ev0) ;
     if (h->ev1) cudaEventDestroy (h->ev1) ;
     if (h->ev2) cudaEventDestroy (h->ev2) ;
@@ -1528,6 +1559,157 @@ int stmqr_b200_factorize_begin (stmqr_handle h, double tol, int64_t ntol)
     return STMQR_OK ;
 }
 
+// The K = 128 trailing update of columns [cb,ce) of the first nfronts fronts of a wide level with the block
+// reflector of the outer block WA.buf (kernels_wide.cuh): W = Vb'C over row splits, W2 = -T' sum W, C += Vb W2.
+// Every column tile is independent of the others, so any partition of the columns into ranges (look-ahead, or
+// column blocks of one front spread over several GPUs) performs bit for bit the same arithmetic per column.
+static void wide_outer_update (stmqr_handle h, const WideArgs &WA, I32 actFm, I32 nsplit_max, cudaStream_t su,
+    I32 nfronts, I32 cb, I32 ce)
+{
+    if (nfronts <= 0 || cb >= ce) return ;
+    DSym &S = h->S ; DNum &N = h->N ;
+    const I32 nrt = std::min<I32> (WA.ldv / W_RT, (actFm + W_RT - 1) / W_RT) ;
+    const I32 nsplA = std::min<I32> (nsplit_max, (actFm + WIDE_RS - 1) / WIDE_RS) ;
+    const I32 nct = (ce - cb + W_NC - 1) / W_NC ;
+    LAUNCH (14, k_wide_vtc<4><<<dim3 (nct * nsplA, nfronts), 256, wide_vtc_smem_bytes<4> (), su>>> (WA, S, N, WIDE_OUTER, 0, cb, ce, nct)) ;
+    LAUNCH (15, k_wide_wt<4><<<dim3 ((ce - cb + 15) / 16, nfronts), 256, 0, su>>> (WA, S, N, WIDE_OUTER, 0, cb, ce)) ;
+    if (h->opt.reserved & 16)
+    {
+        LAUNCH (16, k_wide_apply<4><<<dim3 (nct * nrt, nfronts), 256, wide_apply_smem_bytes<4> (), su>>> (WA, S, N, WIDE_OUTER, 0, cb, ce, nct)) ;
+    }
+    else
+    {
+        // row groups: about 3 CTAs per SM in total, every CTA walks down its share of the row tiles
+        // (the count that fills whole waves of one CTA per SM best, every CTA at least 4 row tiles)
+        I32 nrg = 1 ;
+        {
+            const I64 base = (I64) nct * nfronts ;
+            double best = -1 ;
+            const I32 hi = std::max<I32> (1, std::min<I32> (nrt / 4, (I32) ((8 * (I64) h->nsm + base - 1) / base))) ;
+            for (I32 c = 1 ; c <= hi ; c++)
+            {
+                const I64 tot = base * c, waves = (tot + h->nsm - 1) / h->nsm ;
+                const double eff = (double) tot / (double) (waves * h->nsm) ;
+                if (eff >= best - 1e-9) { best = eff ; nrg = c ; }
+            }
+        }
+        LAUNCH (16, k_wide_apply_rows<<<dim3 (nct * nrg, nfronts), 256, wide_apply_rows_smem_bytes (), su>>> (WA, S, N, cb, ce, nct, nrg)) ;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cooperative front (several GPUs): the top of the etree of a 3-D problem is a chain of single
+// fronts that holds most of the flops; subtree ownership leaves it on one GPU.  Here the front's HOME GPU keeps
+// the whole critical path (assembly, every panel, the block reflectors, the pack), and the K = 128 trailing
+// update -- the bulk of the flops -- is spread over all GPUs by column chunks:
+//   * home assembles F and sends every other GPU the column chunks it owns (chunks of 512 columns, dealt so that
+//     home, which also runs the panels, gets a smaller share);
+//   * after the four panels of outer block J, home broadcasts the block reflector (V in the compact layout,
+//     T, the row window) and everybody applies it to the columns it still holds;
+//   * the owner of block J+2 applies it to that block FIRST and sends the block home, where it arrives while
+//     the panels of block J+1 run: home applies the last reflector (V_{J+1}) itself and factorizes it.
+// Every column sees the same reflectors in the same order through the same kernels as on one GPU, so the
+// factorization is bit for bit the single-GPU one.  All transfers are ordered on the engine streams (NCCL
+// send/recv/broadcast); the only host synchronisation is one 16-byte header per cooperative level.
+// ---------------------------------------------------------------------------------------------
+constexpr I32 COOP_CHUNK = 4 * WB ;
+
+static void coop_plan (stmqr_handle_s::Coop &C, int np, int home, I32 f, I32 fn)
+{
+    C.home = home ; C.f = f ; C.fn = fn ;
+    const int nch = (int) ((fn + COOP_CHUNK - 1) / COOP_CHUNK) ;
+    // share of the home GPU: the panels of a block cost about rho of its trailing update on one GPU
+    const double rho = 0.14 ;
+    const double hs = std::max (0.0, (1.0 - rho * (np - 1)) / np) ;
+    std::vector<double> target ((size_t) np, (np > 1) ? (1.0 - hs) / (np - 1) : 1.0), have ((size_t) np, 0.0) ;
+    target [(size_t) home] = hs ;
+    C.chunk_owner.assign ((size_t) std::max (nch, 1), home) ;      // chunk 0 (blocks 0 .. 3) never leaves home
+    for (int c = 1 ; c < nch ; c++)
+    {
+        int best = -1 ; double bd = -1e300 ;
+        for (int q = 0 ; q < np ; q++)
+        {
+            const int p = (home + 1 + q) % np ;                    // ties: the GPUs after home first
+            const double d = target [(size_t) p] * c - have [(size_t) p] ;
+            if (target [(size_t) p] > 0 && d > bd + 1e-12) { bd = d ; best = p ; }
+        }
+        if (best < 0) best = home ;
+        C.chunk_owner [(size_t) c] = best ; have [(size_t) best] += 1.0 ;
+    }
+}
+static inline int coop_owner (const stmqr_handle_s::Coop &C, I32 col) { return C.chunk_owner [(size_t) (col / COOP_CHUNK)] ; }
+// the column ranges [a,b) that GPU `me` holds at or after column `from`
+static void coop_ranges (const stmqr_handle_s::Coop &C, int me, I32 from, std::vector<std::pair<I32, I32>> &out)
+{
+    out.clear () ;
+    for (I32 c = from / COOP_CHUNK ; (I64) c * COOP_CHUNK < C.fn ; c++)
+    {
+        if (C.chunk_owner [(size_t) c] != me) continue ;
+        const I32 a = std::max<I32> (from, c * COOP_CHUNK), b = std::min<I32> (C.fn, (c + 1) * COOP_CHUNK) ;
+        if (a >= b) continue ;
+        if (!out.empty () && out.back ().second == a) out.back ().second = b ; else out.emplace_back (a, b) ;
+    }
+}
+// rows of the block reflector that travel: every row of the front, padded like k_wide_vextract pads them
+static inline I32 coop_ldv (I32 fm, I32 ldv) { return std::min<I32> (ldv, ((fm + W_RT - 1) / W_RT) * W_RT + W_RT) ; }
+
+// a GPU that does not own the front of a cooperative level: holds column chunks of F and applies the broadcast
+// block reflectors to them
+static int coop_peer_level (stmqr_handle h, I64 gl)
+{
+    Transport *T = (Transport *) h->transport ;
+    stmqr_handle_s::Coop &C = h->coop ;
+    cudaStream_t st = h->stream ;
+    DNum &N = h->N ;
+    const Level &Lv = h->ls_all.levels [(size_t) gl] ;
+    const int me = T->rank () ;
+    int s ;
+    // header from home: does the level go cooperative (actual # rows), and the # rows
+    if ((s = T->bcast (h, N.lvlstat, 4 * sizeof (I32), C.home)) != STMQR_OK) return s ;
+    I32 hdr [4] = {0, 0, 0, 0} ;
+    CK (cudaMemcpyAsync (hdr, N.lvlstat, sizeof (hdr), cudaMemcpyDeviceToHost, st)) ;
+    CK (cudaStreamSynchronize (st)) ;
+    if (!hdr [1]) return STMQR_OK ;
+    C.on = true ; C.levels_run++ ;
+    const I32 fm = hdr [2], fn = C.fn, f = C.f ;
+    CK (cudaMemcpyAsync (N.Hm + f, hdr + 2, sizeof (I32), cudaMemcpyHostToDevice, st)) ;   // (ld of F in the kernels; max-merged later: same value as home's)
+    double *F = N.F + h->h_Foff [f] ;
+    std::vector<std::pair<I32, I32>> mine ;
+    coop_ranges (C, me, 0, mine) ;
+    if ((s = T->group_begin ()) != STMQR_OK) return s ;
+    for (auto &r : mine)
+        if ((s = T->recv (h, F + (I64) r.first * fm, (size_t) fm * (size_t) (r.second - r.first) * sizeof (double), C.home)) != STMQR_OK) return s ;
+    if ((s = T->group_end ()) != STMQR_OK) return s ;
+    const I32 ldvC = coop_ldv (fm, Lv.ldv) ;
+    WideArgs WA ; WA.fronts = h->ls_all.d_fronts + Lv.first ; WA.count = 1 ; WA.buf = 0 ; WA.ldv = ldvC ;
+    WA.rs = WIDE_RS ; WA.nsplit = Lv.nsplit ; WA.ncmax = Lv.maxfn ;
+    const I32 nblk = (fn + WB - 1) / WB ;
+    for (I32 J = 0 ; J < nblk ; J++)
+    {
+        const I32 cb = (J + 1) * WB ;
+        if (cb >= fn) break ;
+        const int buf = J & 1 ;
+        WA.buf = buf ;
+        h->curtag = ((long long) gl << 32) | (long long) (J * WB) ;
+        if ((s = T->group_begin ()) != STMQR_OK) return s ;
+        if ((s = T->bcast (h, N.wVb + (I64) buf * ((I64) ldvC * WB), (size_t) ldvC * WB * sizeof (double), C.home)) != STMQR_OK) return s ;
+        if ((s = T->bcast (h, N.wTbt + (I64) buf * (WB * WB), (size_t) WB * WB * sizeof (double), C.home)) != STMQR_OK) return s ;
+        if ((s = T->bcast (h, N.wblk + (I64) buf * 4, 4 * sizeof (I32), C.home)) != STMQR_OK) return s ;
+        if ((s = T->group_end ()) != STMQR_OK) return s ;
+        // block J+1 is at home already; block J+2 goes there after this update
+        const I32 c2 = cb + WB ;
+        if (c2 >= fn) continue ;
+        const I32 e2 = std::min<I32> (c2 + WB, fn) ;
+        const bool send2 = (coop_owner (C, c2) == me) ;
+        if (send2) wide_outer_update (h, WA, fm, Lv.nsplit, st, 1, c2, e2) ;
+        coop_ranges (C, me, send2 ? e2 : c2, mine) ;
+        for (auto &r : mine) wide_outer_update (h, WA, fm, Lv.nsplit, st, 1, r.first, r.second) ;
+        if (send2 && (s = T->send (h, F + (I64) c2 * fm, (size_t) fm * (size_t) (e2 - c2) * sizeof (double), C.home)) != STMQR_OK) return s ;
+    }
+    CK (cudaGetLastError ()) ;
+    return STMQR_OK ;
+}
+
 // part: 0 = every front (one GPU), 1 = the etree subtrees this GPU owns, 2 = the top of the tree
 // one etree level of the level set LS on this handle's streams (everything asynchronous except the one small
 // read-back on levels with very large fronts)
@@ -1698,6 +1880,35 @@ static int run_level (stmqr_handle h, const LevelSet &LS, const Level &Lv, long 
         // look-ahead pays only when the trailing update is much bigger than its first 32 columns
         const bool lookahead = !h->opt.profile_phases && !(h->opt.reserved & 1) && Lv.maxFelems >= h->lookahead_elems ;
         const bool wide = Lv.wide && actFm >= h->wide_rows && !(h->opt.reserved & 2) && PB == PANEL_MAX ;
+        // cooperative front: this GPU is the home of the level's only front (factorize_dist armed the level on
+        // every GPU); tell the others whether it goes ahead, and hand out their column chunks of the assembled F
+        Transport *const coopT = h->coop.armed ? (Transport *) h->transport : nullptr ;
+        const int coop_me = coopT ? coopT->rank () : 0 ;
+        bool coop_on = false ;
+        if (coopT)
+        {
+            coop_on = wide && nbig == 1 && Lv.count == 1 ;
+            int cs ;
+            I32 hdr [4] = {0, coop_on ? 1 : 0, actFm, 0} ;
+            CK (cudaMemcpyAsync (N.lvlstat, hdr, sizeof (hdr), cudaMemcpyHostToDevice, st)) ;     // (pageable source: staged before the call returns)
+            if ((cs = coopT->bcast (h, N.lvlstat, sizeof (hdr), coop_me)) != STMQR_OK) return cs ;
+            if (coop_on)
+            {
+                h->coop.on = true ; h->coop.levels_run++ ;
+                const I32 f0 = LS.fronts [Lv.first] ;
+                double *F0 = N.F + h->h_Foff [f0] ;
+                if ((cs = coopT->group_begin ()) != STMQR_OK) return cs ;
+                for (int p = 0 ; p < coopT->nranks () ; p++)
+                {
+                    if (p == coop_me) continue ;
+                    std::vector<std::pair<I32, I32>> theirs ;
+                    coop_ranges (h->coop, p, 0, theirs) ;
+                    for (auto &r : theirs)
+                        if ((cs = coopT->send (h, F0 + (I64) r.first * actFm, (size_t) actFm * (size_t) (r.second - r.first) * sizeof (double), p)) != STMQR_OK) return cs ;
+                }
+                if ((cs = coopT->group_end ()) != STMQR_OK) return cs ;
+            }
+        }
         if (wide)
         {
             // ---- two-level blocking (kernels_wide.cuh): outer blocks of 128 columns = 4 panels -------
@@ -1721,31 +1932,7 @@ static int run_level (stmqr_handle h, const LevelSet &LS, const Level &Lv, long 
             } ;
             // (events of LAUNCH are recorded on the main stream: only meaningful when su == st)
             auto outer_update = [&] (cudaStream_t su, I32 nfronts, I32 cb, I32 ce) {
-                const I32 nct = (ce - cb + W_NC - 1) / W_NC ;
-                LAUNCH (14, k_wide_vtc<4><<<dim3 (nct * nsplA, nfronts), 256, wide_vtc_smem_bytes<4> (), su>>> (WA, S, N, WIDE_OUTER, 0, cb, ce, nct)) ;
-                LAUNCH (15, k_wide_wt<4><<<dim3 ((ce - cb + 15) / 16, nfronts), 256, 0, su>>> (WA, S, N, WIDE_OUTER, 0, cb, ce)) ;
-                if (h->opt.reserved & 16)
-                {
-                    LAUNCH (16, k_wide_apply<4><<<dim3 (nct * nrt, nfronts), 256, wide_apply_smem_bytes<4> (), su>>> (WA, S, N, WIDE_OUTER, 0, cb, ce, nct)) ;
-                }
-                else
-                {
-                    // row groups: about 3 CTAs per SM in total, every CTA walks down its share of the row tiles
-                    // (the count that fills whole waves of one CTA per SM best, every CTA at least 4 row tiles)
-                    I32 nrg = 1 ;
-                    {
-                        const I64 base = (I64) nct * nfronts ;
-                        double best = -1 ;
-                        const I32 hi = std::max<I32> (1, std::min<I32> (nrt / 4, (I32) ((8 * (I64) h->nsm + base - 1) / base))) ;
-                        for (I32 c = 1 ; c <= hi ; c++)
-                        {
-                            const I64 tot = base * c, waves = (tot + h->nsm - 1) / h->nsm ;
-                            const double eff = (double) tot / (double) (waves * h->nsm) ;
-                            if (eff >= best - 1e-9) { best = eff ; nrg = c ; }
-                        }
-                    }
-                    LAUNCH (16, k_wide_apply_rows<<<dim3 (nct * nrg, nfronts), 256, wide_apply_rows_smem_bytes (), su>>> (WA, S, N, cb, ce, nct, nrg)) ;
-                }
+                wide_outer_update (h, WA, actFm, Lv.nsplit, su, nfronts, cb, ce) ;
             } ;
             const I32 nblk = (Lv.maxfn + WB - 1) / WB ;
             bool pending [2] = {false, false} ;     // a "rest of the trailing matrix" update in flight on stream2
@@ -1772,7 +1959,50 @@ static int run_level (stmqr_handle h, const LevelSet &LS, const Level &Lv, long 
                 const I32 act2 = active_at (cb, nbig) ;
                 if (act2 == 0) break ;
                 LAUNCH (13, k_wide_tmerge<<<act2, 1024, wide_tmerge_smem_bytes (), st>>> (WI, S, N)) ;
-                if (lookahead)
+                if (coop_on)
+                {
+                    int cs ;
+                    const I32 f0 = LS.fronts [Lv.first] ;
+                    double *F0 = N.F + h->h_Foff [f0] ;
+                    const I32 cm = std::min<I32> (cb + WB, Lv.maxfn) ;
+                    const int buf = J & 1 ;
+                    // block J+1 comes home with the reflectors of blocks 0 .. J-1 applied (its owner posted the send
+                    // before it enters the broadcast below: same order on both sides)
+                    const int own1 = coop_owner (h->coop, cb) ;
+                    if (own1 != coop_me &&
+                        (cs = coopT->recv (h, F0 + (I64) cb * actFm, (size_t) actFm * (size_t) (cm - cb) * sizeof (double), own1)) != STMQR_OK) return cs ;
+                    // the block reflector of block J to everybody: V in the compact layout (actual rows), T, the row window
+                    const I32 ldvC = coop_ldv (actFm, Lv.ldv) ;
+                    const I64 need = (I64) ldvC * WB ;
+                    if (need > h->coop.stage_cap)
+                    {
+                        if (h->coop.stage) { CK (cudaStreamSynchronize (st)) ; cudaFree (h->coop.stage) ; h->coop.stage = nullptr ; h->coop.stage_cap = 0 ; }
+                        CK (cudaMalloc ((void **) &h->coop.stage, (size_t) need * sizeof (double))) ;
+                        h->coop.stage_cap = need ;
+                    }
+                    CK (cudaMemcpy2DAsync (h->coop.stage, (size_t) ldvC * sizeof (double),
+                        N.wVb + (I64) buf * nbig * ((I64) Lv.ldv * WB), (size_t) Lv.ldv * sizeof (double),
+                        (size_t) ldvC * sizeof (double), WB, cudaMemcpyDeviceToDevice, st)) ;
+                    if ((cs = coopT->group_begin ()) != STMQR_OK) return cs ;
+                    if ((cs = coopT->bcast (h, h->coop.stage, (size_t) need * sizeof (double), coop_me)) != STMQR_OK) return cs ;
+                    if ((cs = coopT->bcast (h, N.wTbt + (I64) buf * nbig * (WB * WB), (size_t) WB * WB * sizeof (double), coop_me)) != STMQR_OK) return cs ;
+                    if ((cs = coopT->bcast (h, N.wblk + (I64) buf * nbig * 4, 4 * sizeof (I32), coop_me)) != STMQR_OK) return cs ;
+                    if ((cs = coopT->group_end ()) != STMQR_OK) return cs ;
+                    // V_J -> block J+1 here, then my own chunks beyond it on the second stream beside the next panels
+                    if (pending [(J + 1) & 1]) { CK (cudaStreamWaitEvent (st, h->evN [(J + 1) & 1], 0)) ; pending [(J + 1) & 1] = false ; }
+                    outer_update (st, act2, cb, cm) ;
+                    std::vector<std::pair<I32, I32>> mine ;
+                    coop_ranges (h->coop, coop_me, cm, mine) ;
+                    if (!mine.empty ())
+                    {
+                        CK (cudaEventRecord (h->evP [J & 1], st)) ;
+                        CK (cudaStreamWaitEvent (st2, h->evP [J & 1], 0)) ;
+                        for (auto &r : mine) outer_update (st2, act2, r.first, r.second) ;
+                        CK (cudaEventRecord (h->evN [J & 1], st2)) ;
+                        pending [J & 1] = true ;
+                    }
+                }
+                else if (lookahead)
                 {
                     // the next block's columns first (main stream), the rest of the trailing matrix on the
                     // second stream while the next block's panels run
@@ -2477,14 +2707,33 @@ int stmqr_b200_factorize_dist (stmqr_handle h, double tol, int64_t ntol, stmqr_n
             " of level " + std::to_string (gl) + ": " + cudaGetErrorString (e)) ;
     } ;
     if ((s = stage ("begin", -1)) != STMQR_OK) return s ;
+    h->coop.levels_run = 0 ;
     for (I64 gl = 0 ; gl < nlev ; gl++)
     {
+        // a level that consists of ONE large front may be factorized cooperatively (static test: the same on
+        // every GPU; the home GPU confirms with the actual # rows, see run_level / coop_peer_level)
+        const Level &Lg = h->ls_all.levels [(size_t) gl] ;
+        const bool coop_lvl = h->coop.enabled && T->cooperative () && h->nparts >= ((h->coop.enabled >= 2) ? 2 : h->coop.min_parts) &&
+            Lg.count == 1 && Lg.nbig == 1 && Lg.wide ;
+        h->coop.armed = false ; h->coop.on = false ;
+        if (coop_lvl)
+        {
+            const I32 cf = h->ls_all.fronts [Lg.first] ;
+            coop_plan (h->coop, h->nparts, h->h_owner [cf], cf, h->h_Rp [cf+1] - h->h_Rp [cf]) ;
+            h->coop.armed = true ;
+        }
         if (li < h->ls_mine.levels.size () && h->ls_mine.levels [li].glevel == gl)
         {
-            if ((s = run_level (h, h->ls_mine, h->ls_mine.levels [li], gl)) != STMQR_OK) return s ;
+            if ((s = run_level (h, h->ls_mine, h->ls_mine.levels [li], gl)) != STMQR_OK) return tfail (s) ;
             li++ ;
             if ((s = stage ("the kernels", gl)) != STMQR_OK) return s ;
         }
+        else if (coop_lvl)
+        {
+            if ((s = coop_peer_level (h, gl)) != STMQR_OK) return tfail (s) ;
+            if ((s = stage ("the cooperative updates", gl)) != STMQR_OK) return s ;
+        }
+        h->coop.armed = false ; h->coop.on = false ;
         if (h->xedges [(size_t) gl].empty ()) continue ;
         edges.clear () ;
         for (int e : h->xedges [(size_t) gl]) edges.push_back (XEdge {h->xall_c [e], h->xall_src [e], h->xall_dst [e]}) ;
@@ -2499,6 +2748,8 @@ int stmqr_b200_factorize_dist (stmqr_handle h, double tol, int64_t ntol, stmqr_n
     if ((s = T->allreduce (h, N.sumrank, 1, X_I32, false)) != STMQR_OK) return tfail (s) ;
     if ((s = T->allreduce (h, N.sumrank + 1, 2, X_I32, true)) != STMQR_OK) return tfail (s) ;
     if ((s = T->allreduce (h, N.flops, 3, X_F64, false)) != STMQR_OK) return tfail (s) ;
+    static const bool coop_verbose = getenv ("STMQR_B200_COOP_VERBOSE") != nullptr ;
+    if (coop_verbose) fprintf (stderr, "stmqr_b200 factorize_dist: part %d of %d, %lld cooperative level(s)\n", h->mypart, h->nparts, (long long) h->coop.levels_run) ;
     return stmqr_b200_factorize_hpinv_b (h, info) ;
 }
 
