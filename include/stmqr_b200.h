@@ -268,6 +268,18 @@ int  stmqr_b200_factorize_multi (void *group, double tol, int64_t ntol, stmqr_nu
 int  stmqr_b200_gather_outputs (stmqr_handle h) ;
 int  stmqr_b200_factorize_multi_ex (void *group, double tol, int64_t ntol, stmqr_numeric_info *infos, int gather) ;
 
+/* Cooperative fronts (NCCL transport, 3 GPUs or more; STMQR_B200_COOP=0 off, =2 also on 2 GPUs).  An etree level
+ * that consists of ONE large front -- the top chain of a 3-D problem, where subtree ownership leaves most of the
+ * flops on one GPU (the reference's task tree has the same serial top, SparseQR_analyze.c:705-859)
+ * -- is factorized by all GPUs: the front's home GPU keeps assembly, every panel and the pack; the K = 128
+ * trailing update is spread over the GPUs by chunks of 512 columns.  Per outer block home broadcasts the block
+ * reflector; the owner of the block after next applies it to that block first and sends the block home, where it
+ * arrives while the block in between is being factorized.  factorize_dist decides per level (same test on every
+ * GPU).  stmqr_b200_coop_chunks returns the chunk -> GPU map it uses for a front of fn columns (host only:
+ * chunk_owner [ceil (fn / 512)]; chunk 0 always stays on home, home's share shrinks as GPUs are added because
+ * it also runs the panels). */
+int  stmqr_b200_coop_chunks (int nparts, int home, int64_t fn, int32_t *chunk_owner, int64_t *nchunks) ;
+
 #define STMQR_ARRAY_HM    0   /* int32 [nf] */
 #define STMQR_ARRAY_HR    1   /* int32 [nf] */
 #define STMQR_ARRAY_CM    2   /* int32 [nf] */

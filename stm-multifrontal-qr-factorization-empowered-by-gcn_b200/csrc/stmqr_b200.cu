@@ -2771,6 +2771,17 @@ int stmqr_b200_gather_outputs (stmqr_handle h)
     return STMQR_OK ;
 }
 
+int stmqr_b200_coop_chunks (int nparts, int home, int64_t fn, int32_t *chunk_owner, int64_t *nchunks)
+{
+    if (nparts < 1 || home < 0 || home >= nparts || fn < 0 || fn > INT32_MAX - 2 * COOP_CHUNK) return STMQR_ERR_INVALID ;
+    stmqr_handle_s::Coop C ;
+    coop_plan (C, nparts, home, 0, (I32) fn) ;
+    const int64_t nch = (fn + COOP_CHUNK - 1) / COOP_CHUNK ;
+    if (nchunks) *nchunks = nch ;
+    if (chunk_owner) for (int64_t c = 0 ; c < nch ; c++) chunk_owner [c] = C.chunk_owner [(size_t) c] ;
+    return STMQR_OK ;
+}
+
 // All handles of a peer group, one host thread each.
 int stmqr_b200_factorize_multi (void *group, double tol, int64_t ntol, stmqr_numeric_info *infos)
 {

@@ -106,6 +106,7 @@ EXPORTS = (
     "stmqr_b200_map_fronts", "stmqr_b200_set_ownership", "stmqr_b200_nccl_unique_id", "stmqr_b200_comm_init",
     "stmqr_b200_peer_group_create", "stmqr_b200_peer_group_destroy", "stmqr_b200_factorize_dist",
     "stmqr_b200_factorize_multi", "stmqr_b200_factorize_multi_ex", "stmqr_b200_gather_outputs",
+    "stmqr_b200_coop_chunks",
 )
 
 _lib = None
@@ -259,6 +260,22 @@ def map_fronts(sym: "Symbolic", nparts: int) -> np.ndarray:
     if st != STMQR_OK:
         raise RuntimeError(f"map_fronts: {ERRORS.get(st, st)}")
     return owner[:sym.nf]
+
+
+def coop_chunks(nparts: int, home: int, fn: int) -> np.ndarray:
+    """Host-only: owner GPU of every 512-column chunk of a cooperative front with fn columns whose home is
+    `home` (the map stmqr_b200_factorize_dist uses)."""
+    lib = load_library()
+    n = C.c_int64(0)
+    lib.stmqr_b200_coop_chunks.argtypes = [C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+    st = lib.stmqr_b200_coop_chunks(nparts, home, fn, None, C.byref(n))
+    if st != STMQR_OK:
+        raise RuntimeError(f"coop_chunks: {ERRORS.get(st, st)}")
+    out = np.zeros(max(int(n.value), 1), np.int32)
+    st = lib.stmqr_b200_coop_chunks(nparts, home, fn, out.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n))
+    if st != STMQR_OK:
+        raise RuntimeError(f"coop_chunks: {ERRORS.get(st, st)}")
+    return out[: int(n.value)]
 
 
 def nccl_unique_id() -> bytes:

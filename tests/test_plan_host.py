@@ -142,3 +142,30 @@ def check_no_overlap_general(sym, coff, csize, birth, alive, sent, par, level):
             _, _, b2, d2, c2 = ev[j]
             assert d <= b2 or d2 <= b, f"blocks of fronts {c} and {c2} overlap while both are alive"
             j += 1
+
+
+def test_cooperative_chunk_map():
+    """stmqr_b200_coop_chunks (host only): chunk 0 stays on the home GPU (blocks 0..3 are factorized before any
+    block can have travelled), every other GPU gets an equal share, the home GPU -- which also runs the panels --
+    a smaller one that vanishes as GPUs are added; deterministic."""
+    fn = 29388                                       # root front of the 96^3 Laplacian
+    nch = (fn + 511) // 512
+    for nparts, home in ((2, 0), (4, 0), (8, 0), (8, 3)):
+        own = sq.coop_chunks(nparts, home, fn)
+        assert own.shape == (nch,) and own[0] == home
+        assert own.min() >= 0 and own.max() < nparts
+        cnt = np.bincount(own, minlength=nparts)
+        others = np.delete(cnt, home)
+        assert others.max() - others.min() <= 1     # the peers share evenly
+        assert cnt[home] <= others.max() + 1        # home never holds more than a peer (beyond chunk 0)
+        assert np.array_equal(own, sq.coop_chunks(nparts, home, fn))
+        # cyclic enough that every GPU still has work late in the factorization: the last quarter of the chunks
+        # is spread over all the peers
+        tail = own[-(nch // 4):]
+        assert len(set(tail.tolist()) - {home}) == nparts - 1
+    assert sq.coop_chunks(8, 0, 29388)[1:].tolist().count(0) <= 1       # 8 GPUs: home keeps (almost) nothing but chunk 0
+    share2 = np.bincount(sq.coop_chunks(2, 0, fn), minlength=2)[0] / nch
+    assert 0.35 <= share2 <= 0.5                     # 2 GPUs: home takes about 43 %
+    assert sq.coop_chunks(1, 0, 1000).tolist() == [0, 0]
+    with pytest.raises(RuntimeError):
+        sq.coop_chunks(4, 4, 1000)
