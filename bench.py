@@ -407,8 +407,10 @@ def run_b200_arm(args):
                 "peak_source": peak_src,
                 "avg_launch_ms": asm_ms / max(1.0, float(cls_n[1] + cls_n[2] + cls_n[5] + cls_n[6]))}
     roof["class_ms"] = classes
+    # (several GPUs: bytes_assemble is the merged total of all ranks, asm_ms this rank's kernels -> aggregate rate
+    # against world x the per-GPU peak)
     roof["assembly_gbs"] = float(s2.bytes_assemble) / (asm_ms * 1e-3) * 1e-9 if asm_ms > 0 else None
-    roof["assembly_frac_of_hbm"] = roof["assembly_gbs"] / peaks["hbm_gbs"] if asm_ms > 0 else None
+    roof["assembly_frac_of_hbm"] = roof["assembly_gbs"] / (peaks["hbm_gbs"] * world) if asm_ms > 0 else None
     roof["front_qr_tflops"] = flops / (front_ms * 1e-3) * 1e-12 if front_ms > 0 else None
     roof["fp64_dmma_peak_tflops"] = dmma_tf
     roof["fp64_dfma_peak_tflops"] = dfma_tf
