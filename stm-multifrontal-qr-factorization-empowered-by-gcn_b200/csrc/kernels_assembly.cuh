@@ -352,7 +352,10 @@ __global__ void k_front_finish (const I32 *__restrict__ fronts, DSym S, DNum N)
 
 // Deterministic bump allocation of the level's R+H blocks: exclusive scan over the level's
 // fronts (in list order) on one CTA.
-__global__ void k_level_alloc (const I32 *__restrict__ fronts, I32 count, DNum N)
+// cap = doubles of the R+H arena: if the level does not fit (the symbolic bound was violated -- never seen,
+// the bound is the reference's own) the overflow flag N.griderr [1] is raised and k_pack writes no R+H block any
+// more, so nothing is stored outside the arena and the host reports the failure.
+__global__ void k_level_alloc (const I32 *__restrict__ fronts, I32 count, DNum N, I64 cap)
 {
     __shared__ I64 sh [34] ;
     __shared__ I64 carry_s ;
@@ -390,7 +393,11 @@ __global__ void k_level_alloc (const I32 *__restrict__ fronts, I32 count, DNum N
         if (tid == 0) carry_s += sh [32] ;
         __syncthreads () ;
     }
-    if (tid == 0) *N.rcursor = (unsigned long long) carry_s ;
+    if (tid == 0)
+    {
+        *N.rcursor = (unsigned long long) carry_s ;
+        if (carry_s > cap) N.griderr [1] = 1 ;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -416,6 +423,7 @@ __global__ void k_pack (const I32 *__restrict__ fronts, DSym S, DNum N)
     const I32 rm = N.Hr [f], cm = N.Cm [f], rank = N.rank [f] ;
     const I64 rsize = N.rsize [f] ;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5 ;
+    const bool keepR = (N.griderr [1] == 0) ;           // (R+H arena overflow: pack the C blocks only)
 
     // every column is a contiguous read and a contiguous write; four independent loads are in flight per lane
     // before the first store (source and destination never overlap)
@@ -424,6 +432,7 @@ __global__ void k_pack (const I32 *__restrict__ fronts, DSym S, DNum N)
         const double *__restrict__ Fk = F + (I64) k * fm ;
         double *__restrict__ Rk = R + colp [k] ;
         const I64 len = ((k+1 < fn) ? colp [k+1] : rsize) - colp [k] ;
+        if (!keepR) { if (k < fp) continue ; }
         if (k < fp)
         {
             I64 i = lane ;
@@ -439,7 +448,7 @@ __global__ void k_pack (const I32 *__restrict__ fronts, DSym S, DNum N)
             // rows 0..rm-1, then rows h..t-1 with h = min (rm + (k-fp+1), fm)
             const I32 h = min (rm + (k - fp + 1), fm) ;
             const I64 sh = (I64) h - rm ;
-            I64 i = lane ;
+            I64 i = keepR ? (I64) lane : len ;
             for ( ; i + 96 < len ; i += 128)
             {
                 const double v0 = Fk [i + ((i < rm) ? 0 : sh)], v1 = Fk [i + 32 + ((i + 32 < rm) ? 0 : sh)],

@@ -1232,6 +1232,7 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
             }
         }
         const I64 maxfn1 = std::max<I64> (sym->maxfn, 1) ;
+        const bool rbound_full = getenv ("STMQR_B200_RBOUND_FULL") != nullptr ;    // (A/B: the staircase bound without the C block taken off)
         // per-worker scratch, allocated without initialisation (every entry is written before it is read)
         const int nwk = plan_threads () ;
         std::vector<std::unique_ptr<I32 []>> FmapW ((size_t) nwk), stairW ((size_t) nwk) ;
@@ -1275,6 +1276,14 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
                     rh += std::min<I64> (std::max<I64> (j + 1, run), fm) ;
                 }
                 if (fm > FmB [f]) FmB [f] = (I32) fm ;     // never trust a smaller bound
+                if (!rbound_full)
+                {
+                    // the C block is not part of R+H: the reference's own bound takes off the smallest block the
+                    // front can leave (rhsize -= csize_min, :559-573) -- its stacks rely on exactly this figure
+                    const I64 rm = std::min<I64> (fm, fp) ;
+                    const I64 cmn = std::min<I64> (std::max<I64> (fm - rm, 0), cn) ;
+                    rh -= cmn * (cmn + 1) / 2 + cmn * (cn - cmn) ;
+                }
                 h->h_Rbound [(size_t) f] = rh ;
             }
         }) ;
@@ -1385,12 +1394,12 @@ int stmqr_b200_analyze (stmqr_handle h, const stmqr_symbolic_view *sym)
         ALLOC (N.gridred, gslots * 2 * 148) ;
         ALLOC (N.gridll, gslots * 2 * 148 * 128) ;
         ALLOC (N.gridctr, gslots * GRID_CTR_STRIDE) ;
-        ALLOC (N.griderr, 1) ;
+        ALLOC (N.griderr, 2) ;              // [0] a grid panel did not fit its slabs, [1] the R+H arena overflowed
         if (!h->host_only)
         {
             CK (cudaMemsetAsync (N.gridll, 0, gslots * 2 * 148 * 128 * sizeof (int4), h->stream)) ;
             CK (cudaMemsetAsync (N.gridctr, 0, gslots * GRID_CTR_STRIDE * sizeof (unsigned), h->stream)) ;
-            CK (cudaMemsetAsync (N.griderr, 0, sizeof (I32), h->stream)) ;
+            CK (cudaMemsetAsync (N.griderr, 0, 2 * sizeof (I32), h->stream)) ;
         }
     }
     PLAN_MARK ("arena allocations") ;
@@ -2104,7 +2113,7 @@ static int run_level (stmqr_handle h, const LevelSet &LS, const Level &Lv, long 
                 first += Lv.nsmall [c] ;
             }
         }
-        LAUNCH (5, k_level_alloc<<<1, 1024, 0, st>>> (fr, Lv.count, N)) ;
+        LAUNCH (5, k_level_alloc<<<1, 1024, 0, st>>> (fr, Lv.count, N, h->Rcap)) ;
         LAUNCH (6, k_pack<<<dim3 (Lv.count, nsl), 256, 0, st>>> (fr, S, N)) ;
         mark_level ("level " + std::to_string (levelno) + ": " + std::to_string (Lv.count) + " fronts (" + std::to_string (nbig) +
             " tiled), max " + std::to_string (Lv.maxFm) + " x " + std::to_string (Lv.maxfn) + (Lv.wide ? " wide" : "")) ;
@@ -2177,12 +2186,13 @@ int stmqr_b200_factorize_hpinv_b (stmqr_handle h, stmqr_numeric_info *info)
     CK (cudaMemcpyAsync (sc, N.sumrank, sizeof (sc), cudaMemcpyDeviceToHost, st)) ;
     CK (cudaMemcpyAsync (fl3, N.flops, sizeof (fl3), cudaMemcpyDeviceToHost, st)) ;
     CK (cudaMemcpyAsync (&err, h->d_err, sizeof (err), cudaMemcpyDeviceToHost, st)) ;
-    I32 gerr = 0 ;
-    CK (cudaMemcpyAsync (&gerr, N.griderr, sizeof (gerr), cudaMemcpyDeviceToHost, st)) ;
+    I32 gerr2 [2] = {0, 0} ;
+    CK (cudaMemcpyAsync (gerr2, N.griderr, sizeof (gerr2), cudaMemcpyDeviceToHost, st)) ;
     CK (cudaStreamSynchronize (st)) ;
     CK (cudaGetLastError ()) ;
     if (err) return fail (h, STMQR_ERR_INVALID, "factorize: an entry of A is not in the pattern of S") ;
-    if (gerr) return fail (h, STMQR_ERR_INVALID, "factorize: a panel did not fit the shared-memory slabs of k_panel_grid") ;
+    if (gerr2 [0]) return fail (h, STMQR_ERR_INVALID, "factorize: a panel did not fit the shared-memory slabs of k_panel_grid") ;
+    if (gerr2 [1]) return fail (h, STMQR_ERR_INVALID, "factorize: R+H arena bound exceeded (the packed blocks of the overflowing levels were not written)") ;
 #ifdef STMQR_PANEL_TIMING
     {
         unsigned long long dbg [64] ;
