@@ -8,6 +8,9 @@
 // transfers are ordered on the engine's stream between the pack of level l and the set-up of level l+1.
 // At the end the small integer side outputs are merged with element-wise max all-reduces (every entry is
 // written by exactly one GPU, the others hold the neutral element) and qr_hpinv finishes on every GPU.
+// A level that consists of ONE large front can be factorized cooperatively (stmqr_b200.cu: coop_plan,
+// coop_peer_level, the coop_on branch of run_level): the transports that offer plain byte transfers on the
+// engine stream (bcast / send / recv below; NCCL today) carry the block reflectors and the column blocks.
 //
 // Two transports with the same interface:
 //   NcclTransport   one process per GPU (torchrun): ncclSend/ncclRecv grouped per level, ncclAllReduce.
