@@ -149,7 +149,7 @@ private:
     char *dst_ = nullptr ; const char *src_ = nullptr ; size_t bytes_ = 0 ;
 } ;
 
-constexpr size_t D2H_CHUNK = (size_t) 32 << 20 ;     // bytes per staging buffer
+constexpr size_t D2H_CHUNK = (size_t) 32 << 20 ;     // bytes per pinned staging buffer (allocation size)
 constexpr int STREAM_MAX_LEVELS = 8192 ;
 
 } // namespace
@@ -243,6 +243,7 @@ struct stmqr_handle_s
     cudaStream_t streamV = nullptr ;        // uploads + compares the caller's pattern beside the numeric phase
     bool verify_pending = false, pattern_mismatch = false ;
     int speculative = 1 ;                   // STMQR_B200_SPECULATIVE=0: always upload the pattern first
+    size_t d2h_chunk = D2H_CHUNK ;          // bytes per DMA chunk of the download pipeline
     I64 n_values_only = 0, n_pattern_mismatch = 0 ;
     // int64 staging for the download
     I64 *d_HPinv64 = nullptr, *d_Hii64 = nullptr, *d_wide = nullptr ;
@@ -445,9 +446,13 @@ int d2h_pipelined (stmqr_handle h, void *dst, const void *src, size_t bytes)
         CK (cudaStreamSynchronize (h->streamCopy)) ;
         return STMQR_OK ;
     }
-    const size_t n = (bytes + D2H_CHUNK - 1) / D2H_CHUNK ;
+    // chunk size of the pipeline (<= the staging buffers): every call pays one chunk of DMA before the first host
+    // copy can start and one chunk of host copy after the last DMA, so smaller chunks shorten the fill and drain
+    // of the per-level slices of the streamed download (STMQR_B200_D2H_CHUNK_MB, default 32)
+    const size_t CH = h->d2h_chunk ;
+    const size_t n = (bytes + CH - 1) / CH ;
     auto issue = [&] (size_t c) -> cudaError_t {
-        const size_t off = c * D2H_CHUNK, len = std::min (D2H_CHUNK, bytes - off) ;
+        const size_t off = c * CH, len = std::min (CH, bytes - off) ;
         cudaError_t e = cudaMemcpyAsync (h->pin [c & 1], (const char *) src + off, len, cudaMemcpyDeviceToHost,
             h->streamCopy) ;
         if (e != cudaSuccess) return e ;
@@ -458,7 +463,7 @@ int d2h_pipelined (stmqr_handle h, void *dst, const void *src, size_t bytes)
     {
         if (c + 1 < n) CK (issue (c + 1)) ;
         CK (cudaEventSynchronize (h->evPin [c & 1])) ;
-        const size_t off = c * D2H_CHUNK, len = std::min (D2H_CHUNK, bytes - off) ;
+        const size_t off = c * CH, len = std::min (CH, bytes - off) ;
         h->pool->copy ((char *) dst + off, h->pin [c & 1], len) ;
     }
     return STMQR_OK ;
@@ -470,6 +475,7 @@ int ensure_copy_pipeline (stmqr_handle h)
     if (h->pool) return STMQR_OK ;
     int nt = (int) std::min<unsigned> (8, std::max<unsigned> (1, std::thread::hardware_concurrency () / 2)) ;
     if (const char *e = getenv ("STMQR_B200_COPY_THREADS")) nt = std::max (0, atoi (e)) ;
+    if (const char *e = getenv ("STMQR_B200_D2H_CHUNK_MB")) h->d2h_chunk = std::min (D2H_CHUNK, (size_t) std::max (1, atoi (e)) << 20) ;
     h->pool = new CopyPool (nt) ;
     CK (cudaStreamCreateWithFlags (&h->streamCopy, cudaStreamNonBlocking)) ;
     for (int i = 0 ; i < 2 ; i++)
