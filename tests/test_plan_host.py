@@ -169,3 +169,31 @@ def test_cooperative_chunk_map():
     assert sq.coop_chunks(1, 0, 1000).tolist() == [0, 0]
     with pytest.raises(RuntimeError):
         sq.coop_chunks(4, 4, 1000)
+
+
+def test_plan_is_the_same_for_any_number_of_planner_threads():
+    """The per-front symbolic pass of stmqr_b200_analyze runs in parallel slices (STMQR_B200_PLAN_THREADS): the plan
+    -- arena sizes, every contribution-block offset, the R+H bound -- must not depend on how many threads built it.
+    The thread count is read once per process, so every setting gets its own interpreter."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, hashlib; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np, refapi as R, stmqr_b200 as sq\n"
+        "out = []\n"
+        "for case in ('dwt_992_metis', 'lap2d_24_metis', 'lap3d_8_metis', 'rankdef_120x80_colamd'):\n"
+        "    sym = R.load_golden(case)[0]\n"
+        "    p = sq.Planner(); p.analyze(sym)\n"
+        "    info, coff, csize, level = p.plan_info()\n"
+        "    h = hashlib.sha256(coff.tobytes() + csize.tobytes() + level.tobytes()).hexdigest()[:16]\n"
+        "    out.append((case, int(info.F_doubles), int(info.C_doubles), int(info.R_doubles), int(info.device_bytes), h))\n"
+        "    p.close()\n"
+        "print(out)\n" % (os.path.join(R.PKG, "py"), os.path.join(R.ROOT, "tests")))
+    res = []
+    for nt in ("1", "3", "8"):
+        env = dict(os.environ, STMQR_B200_PLAN_THREADS=nt)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res.append(r.stdout.strip().splitlines()[-1])
+    assert res[0] == res[1] == res[2], res
